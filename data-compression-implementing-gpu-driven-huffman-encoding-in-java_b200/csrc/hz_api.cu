@@ -1,0 +1,362 @@
+// hz_api.cu — context management and the stage-level C ABI of libhuffb200 (include/huffb200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "hz_common.cuh"
+
+// ---- errors / utilities -----------------------------------------------------------------------
+int hz_fail(hz_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+int hz_cuda_fail(hz_ctx* ctx, cudaError_t e, const char* what) {
+    return hz_fail(ctx, e == cudaErrorMemoryAllocation ? HZ_ERR_NOMEM : HZ_ERR_CUDA,
+                   "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+int hz_reserve(hz_ctx* ctx, DevBuf* b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b->cap >= bytes) return HZ_OK;
+    if (b->p) { cudaStreamSynchronize(ctx->stream); cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;          // grow with slack; buffers are reused across calls
+    cudaError_t e = cudaMalloc(&b->p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&b->p, want = bytes); }
+    if (e != cudaSuccess) return hz_cuda_fail(ctx, e, "cudaMalloc(scratch)");
+    b->cap = want;
+    return HZ_OK;
+}
+
+bool hz_is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+void hz_prof_begin(hz_ctx* ctx) {
+    if (ctx->prof) cudaEventRecord(ctx->ev0, ctx->stream);
+}
+void hz_prof_end(hz_ctx* ctx, const char* name) {
+    if (!ctx->prof) return;
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaEventSynchronize(ctx->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    for (auto& e : ctx->prof_entries)
+        if (strcmp(e.name, name) == 0) { e.ms += ms; e.launches++; return; }
+    ctx->prof_entries.push_back({name, (double)ms, 1});
+}
+
+static int check_status(hz_ctx* ctx) {
+    // copy + reset the device status word; caller has synchronised or will right here
+    cudaError_t e = cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return hz_cuda_fail(ctx, e, "status readback");
+    int st = *ctx->h_status;
+    if (st != 0) {
+        cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream);
+        return hz_fail(ctx, st, "device-side error: %s", hz_strerror(st));
+    }
+    return HZ_OK;
+}
+
+extern "C" {
+
+const char* hz_strerror(int s) {
+    switch (s) {
+        case HZ_OK: return "ok";
+        case HZ_ERR_ARG: return "bad argument";
+        case HZ_ERR_CUDA: return "CUDA error";
+        case HZ_ERR_NOMEM: return "out of memory";
+        case HZ_ERR_CODE_TOO_LONG: return "a chunk needs a Huffman code longer than 32 bits";
+        case HZ_ERR_OUT_TOO_SMALL: return "output buffer too small";
+        case HZ_ERR_DECODE: return "Huffman decode error: bit pattern matches no codeword";
+        case HZ_ERR_BAD_LENGTHS: return "invalid code-length table";
+        case HZ_ERR_IO: return "I/O error";
+        case HZ_ERR_FORMAT: return "Invalid file format";
+        case HZ_ERR_CHECKSUM: return "Checksum mismatch";
+        case HZ_ERR_UNSUPPORTED: return "not supported";
+        default: return "unknown error";
+    }
+}
+
+uint32_t hz_version(void) { return 0x000100; }
+
+int hz_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+uint64_t hz_num_chunks(uint64_t n, uint32_t chunk_bytes) {
+    return chunk_bytes ? (n + chunk_bytes - 1) / chunk_bytes : 0;
+}
+
+int hz_create(int device, hz_ctx** out_ctx) {
+    if (!out_ctx) return HZ_ERR_ARG;
+    *out_ctx = nullptr;
+    int ndev = hz_device_count();
+    if (ndev <= 0 || device < 0 || device >= ndev) return HZ_ERR_CUDA;   // no CPU fallback
+    hz_ctx* c = new hz_ctx();
+    c->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_status, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_status, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_status, sizeof(int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) { cudaGetLastError(); hz_destroy(c); return HZ_ERR_CUDA; }
+    c->stream = c->own_stream;
+    *out_ctx = c;
+    return HZ_OK;
+}
+
+void hz_destroy(hz_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->seg_hist, &c->chunk_hist, &c->len, &c->code, &c->chunk_bits, &c->comp_size, &c->comp_off,
+                      &c->seg_bitoff, &c->counter, &c->stage_in, &c->stage_out, &c->stage_a, &c->stage_b,
+                      &c->stage_c, &c->stage_d, &c->stage_e, &c->dec_meta, &c->dec_rec, &c->dec_seqcnt, &c->dec_misc};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (c->d_status) cudaFree(c->d_status);
+    if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* hz_last_error(const hz_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int hz_set_stream(hz_ctx* ctx, void* s) {
+    if (!ctx) return HZ_ERR_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return HZ_OK;
+}
+
+int hz_sync(hz_ctx* ctx) {
+    if (!ctx) return HZ_ERR_ARG;
+    HZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    return check_status(ctx);
+}
+
+int hz_prof_enable(hz_ctx* ctx, int on) { if (!ctx) return HZ_ERR_ARG; ctx->prof = on != 0; return HZ_OK; }
+int hz_prof_reset(hz_ctx* ctx) { if (!ctx) return HZ_ERR_ARG; ctx->prof_entries.clear(); return HZ_OK; }
+int hz_prof_count(hz_ctx* ctx) { return ctx ? (int)ctx->prof_entries.size() : 0; }
+int hz_prof_get(hz_ctx* ctx, int i, const char** name, double* total_ms, uint64_t* launches) {
+    if (!ctx || i < 0 || i >= (int)ctx->prof_entries.size()) return HZ_ERR_ARG;
+    if (name) *name = ctx->prof_entries[i].name;
+    if (total_ms) *total_ms = ctx->prof_entries[i].ms;
+    if (launches) *launches = ctx->prof_entries[i].launches;
+    return HZ_OK;
+}
+uint64_t hz_launch_count(const hz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+// ---- host <-> device staging helpers ---------------------------------------------------------
+// Returns a device pointer holding `bytes` bytes of `p`: p itself when it is device memory, else
+// a copy in scratch buffer `b`.
+static int in_dev(hz_ctx* ctx, DevBuf* b, const void* p, size_t bytes, const void** d) {
+    if (bytes == 0 || hz_is_device_ptr(p)) { *d = p; return HZ_OK; }
+    HZ_TRY(hz_reserve(ctx, b, bytes));
+    HZ_CUDA(ctx, cudaMemcpyAsync(b->p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *d = b->p;
+    return HZ_OK;
+}
+// Device pointer to produce `bytes` bytes destined for `p` (p itself if device memory).
+static int out_dev(hz_ctx* ctx, DevBuf* b, void* p, size_t bytes, void** d, bool* staged) {
+    *staged = false;
+    if (!p) { *d = nullptr; return HZ_OK; }
+    if (hz_is_device_ptr(p)) { *d = p; return HZ_OK; }
+    HZ_TRY(hz_reserve(ctx, b, bytes));
+    *d = b->p; *staged = true;
+    return HZ_OK;
+}
+static int out_copy(hz_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    if (bytes) HZ_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return HZ_OK;
+}
+
+__global__ void sum_seg_hist_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* __restrict__ hist) {
+    const uint32_t k = blockIdx.x, t = threadIdx.x;
+    const uint32_t* sh = seg_hist + (size_t)k * spc * 256 + t;
+    uint32_t f = 0;
+    for (uint32_t s = 0; s < spc; ++s) f += sh[(size_t)s * 256];
+    hist[(size_t)k * 256 + t] = f;
+}
+
+extern "C" {
+
+int hz_histogram(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint32_t* hist) {
+    if (!ctx || !hist || chunk_bytes == 0 || (n && !in)) return hz_fail(ctx, HZ_ERR_ARG, "hz_histogram: bad argument");
+    HZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t K64 = hz_num_chunks(n, chunk_bytes);
+    if (K64 == 0) return HZ_OK;
+    if (K64 > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "too many chunks");
+    const uint32_t K = (uint32_t)K64;
+    const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
+    const void* d_in; void* d_hist; bool st;
+    HZ_TRY(in_dev(ctx, &ctx->stage_in, in, n, &d_in));
+    HZ_TRY(out_dev(ctx, &ctx->stage_a, hist, (size_t)K * 1024, &d_hist, &st));
+    HZ_TRY(hz_reserve(ctx, &ctx->seg_hist, (size_t)K * spc * 1024));
+    HZ_TRY(hzk_histogram(ctx, (const uint8_t*)d_in, n, chunk_bytes, K, (uint32_t*)ctx->seg_hist.p));
+    HZ_LAUNCH(ctx, "sum_seg_hist", sum_seg_hist_kernel, K, 256, 0, (const uint32_t*)ctx->seg_hist.p, spc, (uint32_t*)d_hist);
+    if (st) { HZ_TRY(out_copy(ctx, hist, d_hist, (size_t)K * 1024)); return check_status(ctx); }
+    return HZ_OK;
+}
+
+int hz_build_codebooks(hz_ctx* ctx, const uint32_t* hist, uint32_t K, uint8_t* len, uint32_t* code) {
+    if (!ctx || !hist || !len) return hz_fail(ctx, HZ_ERR_ARG, "hz_build_codebooks: bad argument");
+    HZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (K == 0) return HZ_OK;
+    const void* d_hist; void *d_len, *d_code; bool s1, s2;
+    HZ_TRY(in_dev(ctx, &ctx->stage_a, hist, (size_t)K * 1024, &d_hist));
+    HZ_TRY(out_dev(ctx, &ctx->stage_b, len, (size_t)K * 256, &d_len, &s1));
+    HZ_TRY(out_dev(ctx, &ctx->stage_c, code, (size_t)K * 1024, &d_code, &s2));
+    HZ_TRY(hzk_codebook(ctx, (const uint32_t*)d_hist, 0, K, nullptr, (uint8_t*)d_len, (uint32_t*)d_code,
+                        nullptr, nullptr, nullptr, nullptr, nullptr));
+    if (s1) HZ_TRY(out_copy(ctx, len, d_len, (size_t)K * 256));
+    if (s2) HZ_TRY(out_copy(ctx, code, d_code, (size_t)K * 1024));
+    if (s1 || s2) return check_status(ctx);
+    return HZ_OK;
+}
+
+int hz_codes_from_lengths(hz_ctx* ctx, const uint8_t* len, uint32_t K, uint32_t* code) {
+    if (!ctx || !len || !code) return hz_fail(ctx, HZ_ERR_ARG, "hz_codes_from_lengths: bad argument");
+    HZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (K == 0) return HZ_OK;
+    const void* d_len; void* d_code; bool st;
+    HZ_TRY(in_dev(ctx, &ctx->stage_b, len, (size_t)K * 256, &d_len));
+    HZ_TRY(out_dev(ctx, &ctx->stage_c, code, (size_t)K * 1024, &d_code, &st));
+    HZ_TRY(hzk_codes_from_lengths(ctx, (const uint8_t*)d_len, K, (uint32_t*)d_code));
+    if (st) { HZ_TRY(out_copy(ctx, code, d_code, (size_t)K * 1024)); return check_status(ctx); }
+    return HZ_OK;
+}
+
+static int encode_impl(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint8_t* fixed_len,
+                       uint8_t* out, uint64_t out_cap, uint64_t* comp_off, uint8_t* len_out, uint32_t* hist_out) {
+    if (!ctx || chunk_bytes == 0 || (n && (!in || !out)) || !comp_off)
+        return hz_fail(ctx, HZ_ERR_ARG, "hz_encode: bad argument");
+    HZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t K64 = hz_num_chunks(n, chunk_bytes);
+    if (K64 > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "too many chunks");
+    const uint32_t K = (uint32_t)K64;
+    const bool off_dev = hz_is_device_ptr(comp_off);
+    if (K == 0) {
+        if (off_dev) HZ_CUDA(ctx, cudaMemsetAsync(comp_off, 0, sizeof(uint64_t), ctx->stream));
+        else comp_off[0] = 0;
+        return HZ_OK;
+    }
+    const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
+    const size_t nseg = (size_t)K * spc;
+    const void *d_in, *d_fixed = nullptr;
+    void *d_out, *d_off, *d_len, *d_hist;
+    bool s_out, s_off, s_len, s_hist;
+    HZ_TRY(in_dev(ctx, &ctx->stage_in, in, n, &d_in));
+    if (fixed_len) HZ_TRY(in_dev(ctx, &ctx->stage_e, fixed_len, 256, &d_fixed));
+    const uint64_t dcap = hz_is_device_ptr(out) ? out_cap : (fixed_len ? out_cap : (out_cap < n ? out_cap : n));
+    HZ_TRY(out_dev(ctx, &ctx->stage_out, out, dcap + 16, &d_out, &s_out));
+    HZ_TRY(out_dev(ctx, &ctx->comp_off, comp_off, ((size_t)K + 1) * 8, &d_off, &s_off));
+    HZ_TRY(out_dev(ctx, &ctx->len, len_out, (size_t)K * 256, &d_len, &s_len));
+    if (!d_len) { HZ_TRY(hz_reserve(ctx, &ctx->len, (size_t)K * 256)); d_len = ctx->len.p; }
+    HZ_TRY(out_dev(ctx, &ctx->chunk_hist, hist_out, (size_t)K * 1024, &d_hist, &s_hist));
+    HZ_TRY(hz_reserve(ctx, &ctx->seg_hist, nseg * 1024));
+    HZ_TRY(hz_reserve(ctx, &ctx->code, (size_t)K * 1024));
+    HZ_TRY(hz_reserve(ctx, &ctx->chunk_bits, (size_t)K * 8));
+    HZ_TRY(hz_reserve(ctx, &ctx->comp_size, (size_t)K * 4));
+    HZ_TRY(hz_reserve(ctx, &ctx->seg_bitoff, nseg * 8));
+
+    HZ_TRY(hzk_histogram(ctx, (const uint8_t*)d_in, n, chunk_bytes, K, (uint32_t*)ctx->seg_hist.p));
+    HZ_TRY(hzk_codebook(ctx, (const uint32_t*)ctx->seg_hist.p, spc, K, (uint32_t*)d_hist, (uint8_t*)d_len,
+                        (uint32_t*)ctx->code.p, (uint64_t*)ctx->chunk_bits.p, (uint32_t*)ctx->comp_size.p,
+                        (uint64_t*)d_off, (uint64_t*)ctx->seg_bitoff.p, (const uint8_t*)d_fixed));
+    HZ_TRY(hzk_encode(ctx, (const uint8_t*)d_in, n, chunk_bytes, K, (const uint8_t*)d_len, (const uint32_t*)ctx->code.p,
+                      (const uint64_t*)d_off, (const uint64_t*)ctx->seg_bitoff.p, (uint8_t*)d_out, dcap));
+
+    if (!(s_out || s_off || s_len || s_hist)) return HZ_OK;       // fully device-resident: asynchronous
+    // host outputs: offsets first (their total tells how much payload to copy back)
+    uint64_t total = 0;
+    if (s_off) {
+        HZ_TRY(out_copy(ctx, comp_off, d_off, ((size_t)K + 1) * 8));
+    } else {
+        HZ_CUDA(ctx, cudaMemcpyAsync(&total, (uint64_t*)d_off + K, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (s_len) HZ_TRY(out_copy(ctx, len_out, d_len, (size_t)K * 256));
+    if (s_hist) HZ_TRY(out_copy(ctx, hist_out, d_hist, (size_t)K * 1024));
+    HZ_TRY(check_status(ctx));
+    if (s_off) total = comp_off[K];
+    if (s_out) {
+        if (total > out_cap) return hz_fail(ctx, HZ_ERR_OUT_TOO_SMALL, "payload %llu > capacity %llu",
+                                            (unsigned long long)total, (unsigned long long)out_cap);
+        HZ_TRY(out_copy(ctx, out, d_out, total));
+        HZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return HZ_OK;
+}
+
+int hz_encode(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint8_t* out, uint64_t out_cap,
+              uint64_t* comp_off, uint8_t* len_out, uint32_t* hist_out) {
+    return encode_impl(ctx, in, n, chunk_bytes, nullptr, out, out_cap, comp_off, len_out, hist_out);
+}
+
+int hz_encode_with_lengths(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint8_t* len256,
+                           uint8_t* out, uint64_t out_cap, uint64_t* comp_off) {
+    if (!len256) return hz_fail(ctx, HZ_ERR_ARG, "hz_encode_with_lengths: len256 is NULL");
+    return encode_impl(ctx, in, n, chunk_bytes, len256, out, out_cap, comp_off, nullptr, nullptr);
+}
+
+int hz_decode(hz_ctx* ctx, const uint8_t* comp, uint64_t comp_bytes, const uint64_t* comp_off,
+              const uint32_t* comp_size, const uint32_t* orig_size, const uint64_t* orig_off,
+              const uint8_t* len, uint32_t K, uint8_t* out, uint64_t out_cap) {
+    if (!ctx || (K && (!comp_off || !comp_size || !orig_size || !len)) || (comp_bytes && !comp) || (out_cap && !out))
+        return hz_fail(ctx, HZ_ERR_ARG, "hz_decode: bad argument");
+    HZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (K == 0) return HZ_OK;
+    const void *d_comp, *d_coff, *d_csz, *d_osz, *d_ooff = nullptr, *d_len;
+    void* d_out; bool s_out;
+    HZ_TRY(in_dev(ctx, &ctx->stage_in, comp, comp_bytes, &d_comp));
+    HZ_TRY(in_dev(ctx, &ctx->stage_a, comp_off, (size_t)K * 8, &d_coff));
+    HZ_TRY(in_dev(ctx, &ctx->stage_b, comp_size, (size_t)K * 4, &d_csz));
+    HZ_TRY(in_dev(ctx, &ctx->stage_c, orig_size, (size_t)K * 4, &d_osz));
+    if (orig_off) HZ_TRY(in_dev(ctx, &ctx->stage_d, orig_off, (size_t)K * 8, &d_ooff));
+    HZ_TRY(in_dev(ctx, &ctx->len, len, (size_t)K * 256, &d_len));
+    HZ_TRY(out_dev(ctx, &ctx->stage_out, out, out_cap, &d_out, &s_out));
+    HZ_TRY(hzk_decode(ctx, (const uint8_t*)d_comp, comp_bytes, (const uint64_t*)d_coff, (const uint32_t*)d_csz,
+                      (const uint32_t*)d_osz, (const uint64_t*)d_ooff, (const uint8_t*)d_len, K, (uint8_t*)d_out, out_cap));
+    if (s_out) {
+        HZ_TRY(out_copy(ctx, out, d_out, out_cap));
+        return check_status(ctx);
+    }
+    return HZ_OK;
+}
+
+int hz_sha256_chunks(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint8_t* digests) {
+    if (!ctx || chunk_bytes == 0 || !digests || (n && !in)) return hz_fail(ctx, HZ_ERR_ARG, "hz_sha256_chunks: bad argument");
+    HZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t K64 = hz_num_chunks(n, chunk_bytes);
+    if (K64 == 0) return HZ_OK;
+    if (K64 > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "too many chunks");
+    const uint32_t K = (uint32_t)K64;
+    const void* d_in; void* d_dig; bool st;
+    HZ_TRY(in_dev(ctx, &ctx->stage_in, in, n, &d_in));
+    HZ_TRY(out_dev(ctx, &ctx->stage_a, digests, (size_t)K * 32, &d_dig, &st));
+    HZ_TRY(hzk_sha256(ctx, (const uint8_t*)d_in, n, chunk_bytes, K, (uint8_t*)d_dig));
+    if (st) { HZ_TRY(out_copy(ctx, digests, d_dig, (size_t)K * 32)); return check_status(ctx); }
+    return HZ_OK;
+}
+
+}  // extern "C"

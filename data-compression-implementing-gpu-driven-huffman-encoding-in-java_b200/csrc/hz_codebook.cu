@@ -1,0 +1,306 @@
+// hz_codebook.cu — canonical Huffman codebooks, one CTA per chunk (stage 2 of encode).
+//
+// Replaces CanonicalHuffman.buildCanonicalCodes(long[256]) (core/CanonicalHuffman.java:19-132).
+// The code LENGTHS of the reference depend on how java.util.PriorityQueue orders
+// equal-frequency internal nodes (HuffmanNode.compareTo, core/HuffmanNode.java:52-58, returns 0
+// for two internal nodes of equal frequency), so the tree is built by ONE thread that replays the
+// JDK's binary heap literally: offer = siftUp (stop when cmp(x,parent) >= 0), poll = move last
+// to root + siftDown (pick right child only if cmp(left,right) > 0; stop when cmp(x,child) <= 0).
+// A heap entry is one uint64: (freq << 18) | ((symbol+1) << 9) | node_id — comparing
+// (entry >> 9) is exactly compareTo (internal nodes carry symbol -1 -> field 0).
+// Everything around the serial heap (summing segment histograms, leaf depths by parent chasing,
+// canonical code assignment, exact compressed sizes and per-segment output bit offsets) is
+// parallel over the CTA's 256 threads.
+#include "hz_common.cuh"
+
+#define CB_THREADS 256
+
+__device__ __forceinline__ void heap_offer(uint64_t* q, int& size, uint64_t x) {
+    int k = size++;
+    const uint64_t xk = x >> 9;
+    while (k > 0) {
+        int parent = (k - 1) >> 1;
+        uint64_t e = q[parent];
+        if (xk >= (e >> 9)) break;
+        q[k] = e;
+        k = parent;
+    }
+    q[k] = x;
+}
+
+__device__ __forceinline__ uint64_t heap_poll(uint64_t* q, int& size) {
+    uint64_t result = q[0];
+    int n = --size;
+    if (n > 0) {
+        uint64_t x = q[n];
+        const uint64_t xk = x >> 9;
+        int k = 0;
+        const int half = n >> 1;
+        while (k < half) {
+            int child = 2 * k + 1;
+            uint64_t c = q[child];
+            int right = child + 1;
+            if (right < n) {
+                uint64_t r = q[right];
+                if ((c >> 9) > (r >> 9)) { c = r; child = right; }
+            }
+            if (xk <= (c >> 9)) break;
+            q[k] = c;
+            k = child;
+        }
+        q[k] = x;
+    }
+    return result;
+}
+
+// Block-wide exclusive scan helper for 64-bit values over `count` items stored in global memory
+// (in place: in = per-item value, out = exclusive prefix).  Called by all CB_THREADS threads.
+__device__ void block_scan_inplace_u64(uint64_t* data, uint32_t count, uint64_t* s_warp /*[9]*/) {
+    const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    uint64_t carry = 0;
+    for (uint32_t base = 0; base < count; base += CB_THREADS) {
+        uint32_t i = base + t;
+        uint64_t v = i < count ? data[i] : 0;
+        uint64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (t == 0) {
+            uint64_t a = 0;
+            for (int w = 0; w < CB_THREADS / 32; ++w) { uint64_t x = s_warp[w]; s_warp[w] = a; a += x; }
+            s_warp[8] = a;
+        }
+        __syncthreads();
+        if (i < count) data[i] = carry + s_warp[wid] + inc - v;
+        carry += s_warp[8];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* __restrict__ chunk_hist_out,
+                uint8_t* __restrict__ len_out, uint32_t* __restrict__ code_out,
+                uint64_t* __restrict__ chunk_bits, uint32_t* __restrict__ comp_size,
+                uint64_t* __restrict__ seg_bitoff, const uint8_t* __restrict__ fixed_len,
+                const uint32_t* __restrict__ direct_hist, int* status) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t heap[256];
+    __shared__ uint16_t parent[512];
+    __shared__ uint16_t leaf_id[256];
+    __shared__ int s_len[256];
+    __shared__ uint32_t lcount[34];
+    __shared__ uint32_t first[34];
+    __shared__ uint64_t s_warp[9];
+    __shared__ int s_root, s_nsym, s_maxlen;
+
+    const uint32_t k = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+
+    // 1. chunk histogram = sum of its segment histograms (or a caller-supplied histogram)
+    uint32_t f = 0;
+    if (direct_hist) {
+        f = direct_hist[(size_t)k * 256 + t];
+    } else {
+        const uint32_t* sh = seg_hist + (size_t)k * spc * 256 + t;
+        for (uint32_t s = 0; s < spc; ++s) f += sh[(size_t)s * 256];
+    }
+    hist[t] = f;
+    if (chunk_hist_out) chunk_hist_out[(size_t)k * 256 + t] = f;
+    if (t < 34) lcount[t] = 0;
+    if (t == 0) s_maxlen = 0;
+    __syncthreads();
+
+    int mylen = 0;
+    if (fixed_len) {
+        mylen = fixed_len[t];
+        if (f > 0 && mylen == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS);
+    } else {
+        // 2. the serial part: replay java.util.PriorityQueue (CanonicalHuffman.java:55-70)
+        if (t == 0) {
+            int size = 0, n = 0;
+            for (int s = 0; s < 256; ++s) {
+                uint32_t fr = hist[s];
+                if (fr > 0) {
+                    leaf_id[s] = (uint16_t)n;
+                    heap_offer(heap, size, ((uint64_t)fr << 18) | ((uint64_t)(s + 1) << 9) | (uint64_t)n);
+                    ++n;
+                }
+            }
+            s_nsym = n;
+            while (size > 1) {
+                uint64_t l = heap_poll(heap, size);
+                uint64_t r = heap_poll(heap, size);
+                parent[l & 511] = (uint16_t)n;
+                parent[r & 511] = (uint16_t)n;
+                heap_offer(heap, size, (((l >> 18) + (r >> 18)) << 18) | (uint64_t)n);
+                ++n;
+            }
+            s_root = n - 1;
+        }
+        __syncthreads();
+        // 3. leaf depth = code length (extractLengths, :85-92); single symbol -> 1 (:35-45)
+        if (f > 0) {
+            if (s_nsym == 1) {
+                mylen = 1;
+            } else {
+                int id = leaf_id[t], root = s_root, d = 0;
+                while (id != root) { id = parent[id]; ++d; }
+                mylen = d;
+            }
+        }
+    }
+    if (mylen > 32) {                           // the reference throws here (:107)
+        hz_set_status(status, HZ_ERR_CODE_TOO_LONG);
+        mylen = 0;
+        s_maxlen = 99;
+    }
+    s_len[t] = mylen;
+    if (mylen > 0) atomicAdd(&lcount[mylen], 1u);
+    __syncthreads();
+    const bool bad = s_maxlen == 99;
+    if (bad) mylen = 0;
+
+    // 4. canonical codes (generateCanonicalCodes, :99-132)
+    if (t == 0) {
+        uint32_t c = 0;
+        first[0] = 0;
+        for (int l = 1; l <= 32; ++l) {
+            c = (c + (l > 1 ? lcount[l - 1] : 0u)) << 1;
+            first[l] = c;
+        }
+    }
+    __syncthreads();
+    uint32_t mycode = 0;
+    if (mylen > 0) {
+        uint32_t rank = 0;
+        for (uint32_t s = 0; s < t; ++s) rank += (s_len[s] == mylen);
+        mycode = first[mylen] + rank;
+    }
+    len_out[(size_t)k * 256 + t] = (uint8_t)mylen;
+    if (code_out) code_out[(size_t)k * 256 + t] = mycode;
+
+    // 5. exact compressed size of the chunk: sum(freq * len) bits
+    if (chunk_bits) {
+        uint64_t b = (uint64_t)f * (uint32_t)mylen;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) b += __shfl_xor_sync(0xffffffffu, b, d);
+        if (lane == 0) s_warp[wid] = b;
+        __syncthreads();
+        if (t == 0) {
+            uint64_t a = 0;
+            for (int w = 0; w < CB_THREADS / 32; ++w) a += s_warp[w];
+            chunk_bits[k] = a;
+            uint64_t bytes = (a + 7) >> 3;
+            if (bytes > 0x7fffffffull) { hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); bytes = 0; }
+            comp_size[k] = (uint32_t)bytes;
+        }
+        __syncthreads();
+    }
+
+    // 6. bit offset of every segment inside the chunk's stream
+    if (seg_bitoff && seg_hist) {
+        uint64_t* so = seg_bitoff + (size_t)k * spc;
+        for (uint32_t s = wid; s < spc; s += CB_THREADS / 32) {
+            const uint32_t* sh = seg_hist + ((size_t)k * spc + s) * 256;
+            uint64_t b = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int sym = lane + 32 * j;
+                b += (uint64_t)sh[sym] * (uint32_t)(bad ? 0 : s_len[sym]);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) b += __shfl_xor_sync(0xffffffffu, b, d);
+            if (lane == 0) so[s] = b;
+        }
+        __syncthreads();
+        block_scan_inplace_u64(so, spc, s_warp);
+    }
+}
+
+// comp_off[k] = exclusive prefix sum of comp_size (K+1 entries), one CTA of 1024 threads:
+// each thread sums a contiguous slice, the slice totals are scanned, then prefixes are written.
+__global__ void __launch_bounds__(1024)
+chunk_offsets_kernel(const uint32_t* __restrict__ comp_size, uint32_t K, uint64_t* __restrict__ comp_off) {
+    __shared__ uint64_t part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (K + 1023) / 1024;
+    const uint32_t lo = t * per, hi = min(K, lo + per);
+    uint64_t s = 0;
+    for (uint32_t i = lo; i < hi; ++i) s += comp_size[i];
+    part[t] = s;
+    __syncthreads();
+    if (t < 32) {   // warp 0 scans 1024 partials, 32 per lane
+        uint64_t loc[32]; uint64_t a = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { loc[j] = a; a += part[t * 32 + j]; }
+        uint64_t inc = a;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (t >= (uint32_t)d) inc += o;
+        }
+        uint64_t base = inc - a;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) part[t * 32 + j] = base + loc[j];
+        if (t == 31) comp_off[K] = inc;
+    }
+    __syncthreads();
+    uint64_t a = part[t];
+    for (uint32_t i = lo; i < hi; ++i) { comp_off[i] = a; a += comp_size[i]; }
+}
+
+// CanonicalHuffman.generateCanonicalCodesFromLengths (core/CanonicalHuffman.java:141-146)
+__global__ void __launch_bounds__(CB_THREADS)
+codes_from_lengths_kernel(const uint8_t* __restrict__ len_in, uint32_t* __restrict__ code_out, int* status) {
+    __shared__ int s_len[256];
+    __shared__ uint32_t lcount[34];
+    __shared__ uint32_t first[34];
+    const uint32_t k = blockIdx.x, t = threadIdx.x;
+    int mylen = len_in[(size_t)k * 256 + t];
+    if (t < 34) lcount[t] = 0;
+    __syncthreads();
+    if (mylen > 32) { hz_set_status(status, HZ_ERR_BAD_LENGTHS); mylen = 0; }
+    s_len[t] = mylen;
+    if (mylen > 0) atomicAdd(&lcount[mylen], 1u);
+    __syncthreads();
+    if (t == 0) {
+        uint32_t c = 0;
+        first[0] = 0;
+        for (int l = 1; l <= 32; ++l) { c = (c + (l > 1 ? lcount[l - 1] : 0u)) << 1; first[l] = c; }
+    }
+    __syncthreads();
+    uint32_t mycode = 0;
+    if (mylen > 0) {
+        uint32_t rank = 0;
+        for (uint32_t s = 0; s < t; ++s) rank += (s_len[s] == mylen);
+        mycode = first[mylen] + rank;
+    }
+    code_out[(size_t)k * 256 + t] = mycode;
+}
+
+int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t spc, uint32_t K,
+                 uint32_t* d_chunk_hist, uint8_t* d_len, uint32_t* d_code, uint64_t* d_chunk_bits,
+                 uint32_t* d_comp_size, uint64_t* d_comp_off, uint64_t* d_seg_bitoff,
+                 const uint8_t* d_fixed_len256) {
+    if (K == 0) {
+        if (d_comp_off) HZ_CUDA(ctx, cudaMemsetAsync(d_comp_off, 0, sizeof(uint64_t), ctx->stream));
+        return HZ_OK;
+    }
+    // spc == 0 means d_seg_hist is a caller-supplied K x 256 chunk histogram
+    const uint32_t* direct = spc == 0 ? d_seg_hist : nullptr;
+    HZ_LAUNCH(ctx, "codebook", codebook_kernel, K, CB_THREADS, 0,
+              spc == 0 ? nullptr : d_seg_hist, spc, d_chunk_hist, d_len, d_code, d_chunk_bits,
+              d_comp_size, d_seg_bitoff, d_fixed_len256, direct, ctx->d_status);
+    if (d_comp_off)
+        HZ_LAUNCH(ctx, "chunk_offsets", chunk_offsets_kernel, 1, 1024, 0, d_comp_size, K, d_comp_off);
+    return HZ_OK;
+}
+
+int hzk_codes_from_lengths(hz_ctx* ctx, const uint8_t* d_len, uint32_t K, uint32_t* d_code) {
+    if (K == 0) return HZ_OK;
+    HZ_LAUNCH(ctx, "codes_from_lengths", codes_from_lengths_kernel, K, CB_THREADS, 0, d_len, d_code, ctx->d_status);
+    return HZ_OK;
+}

@@ -1,0 +1,115 @@
+// hz_common.cuh — shared constants, context layout and device helpers of libhuffb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/huffb200.h"
+
+// ---------------------------------------------------------------------------------------------
+// Geometry shared by the histogram and encode kernels.
+//   segment = the unit one CTA histograms and later encodes; a chunk is split into
+//   ceil(chunk_bytes / HZ_SEG_BYTES) segments.  15 * 4096: with 256 threads every thread sees at
+//   most 240 bytes of a segment, so the per-thread 8-bit counters of the histogram cannot wrap.
+// ---------------------------------------------------------------------------------------------
+#define HZ_THREADS 256
+#define HZ_SEG_BYTES 61440u
+
+// Decode geometry: one thread decodes one subsequence of HZ_SUB_WORDS 32-bit words (an ODD
+// number of words, so that consecutive subsequences staged in shared memory fall into
+// different banks); a "sequence" = 256 subsequences = what one CTA pass covers.
+#define HZ_SUB_WORDS 17
+#define HZ_SUB_BITS (HZ_SUB_WORDS * 32)
+#define HZ_OVERLAP_BITS 128                  // speculative run-in before a subsequence
+#define HZ_DEC_THREADS 256
+#define HZ_SEQ_PER_CTA 4                     // sequences handled back to back by one CTA
+#define HZ_DEC_LUT_BITS 12
+
+struct hz_prof_entry { const char* name; double ms; uint64_t launches; };
+
+struct DevBuf {                               // grow-only device scratch buffer
+    void* p = nullptr; size_t cap = 0;
+};
+
+struct hz_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    // device-side status word (first error latched by kernels) + pinned host mirror
+    int* d_status = nullptr;
+    int* h_status = nullptr;
+    // scratch
+    DevBuf seg_hist, chunk_hist, len, code, chunk_bits, comp_size, comp_off, seg_bitoff, counter;
+    DevBuf stage_in, stage_out, stage_a, stage_b, stage_c, stage_d, stage_e;
+    DevBuf dec_meta, dec_rec, dec_seqcnt, dec_misc;
+    void* h_pin = nullptr; size_t h_pin_cap = 0;
+    // profiling
+    bool prof = false;
+    std::vector<hz_prof_entry> prof_entries;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+int hz_fail(hz_ctx* ctx, int code, const char* fmt, ...);
+int hz_cuda_fail(hz_ctx* ctx, cudaError_t e, const char* what);
+int hz_reserve(hz_ctx* ctx, DevBuf* b, size_t bytes);
+bool hz_is_device_ptr(const void* p);
+void hz_prof_begin(hz_ctx* ctx);
+void hz_prof_end(hz_ctx* ctx, const char* name);
+
+#define HZ_CUDA(ctx, call)                                                   \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return hz_cuda_fail((ctx), e__, #call);      \
+    } while (0)
+
+#define HZ_TRY(expr)                     \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != HZ_OK) return rc__;  \
+    } while (0)
+
+// kernel launch wrapper: counts launches, optional per-kernel event timing
+#define HZ_LAUNCH(ctx, name, kernel, grid, block, smem, ...)                              \
+    do {                                                                                  \
+        hz_prof_begin(ctx);                                                               \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                  \
+        (ctx)->launches++;                                                                \
+        hz_prof_end(ctx, name);                                                           \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) return hz_cuda_fail((ctx), e__, name);                    \
+    } while (0)
+
+// ---- launchers implemented in the kernel files ------------------------------------------------
+int hzk_histogram(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
+                  uint32_t* d_seg_hist);
+int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t segs_per_chunk, uint32_t K,
+                 uint32_t* d_chunk_hist, uint8_t* d_len, uint32_t* d_code, uint64_t* d_chunk_bits,
+                 uint32_t* d_comp_size, uint64_t* d_comp_off, uint64_t* d_seg_bitoff,
+                 const uint8_t* d_fixed_len256);
+int hzk_codes_from_lengths(hz_ctx* ctx, const uint8_t* d_len, uint32_t K, uint32_t* d_code);
+int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
+               const uint8_t* d_len, const uint32_t* d_code, const uint64_t* d_comp_off,
+               const uint64_t* d_seg_bitoff, uint8_t* d_out, uint64_t out_cap);
+int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const uint64_t* d_comp_off,
+               const uint32_t* d_comp_size, const uint32_t* d_orig_size, const uint64_t* d_orig_off,
+               const uint8_t* d_len, uint32_t K, uint8_t* d_out, uint64_t out_cap);
+int hzk_sha256(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
+               uint8_t* d_digests);
+
+#ifdef __CUDACC__
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {   // streaming 128-bit load
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+__device__ __forceinline__ void hz_set_status(int* status, int code) {
+    if (code != 0) atomicCAS(status, 0, code);
+}
+#endif

@@ -1,0 +1,331 @@
+"""GPU parity tests: every stage of the CUDA hot path (through the C ABI of libhuffb200.so)
+against the CPU oracle, bit-exact.  Mirrors the reference's tests."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import datasets
+import orc
+
+pytestmark = pytest.mark.gpu
+MiB = 1 << 20
+
+
+def oracle_encode(data, chunk):
+    """Per-chunk oracle encode -> (payload, comp_off[K+1], lens[K,256])."""
+    data = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    K = (data.size + chunk - 1) // chunk
+    parts, lens, off = [], np.zeros((K, 256), dtype=np.uint8), np.zeros(K + 1, dtype=np.uint64)
+    for k in range(K):
+        p, ln, _ = orc.encode_chunk(data[k * chunk:(k + 1) * chunk])
+        parts.append(p); lens[k] = ln; off[k + 1] = off[k] + p.size
+    return (np.concatenate(parts) if parts else np.zeros(0, np.uint8)), off, lens
+
+
+def check_encode(codec, data, chunk):
+    data = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    payload, off, lens, hist = codec.encode(data, chunk, want_hist=True)
+    rp, roff, rlens = oracle_encode(data, chunk)
+    K = len(roff) - 1
+    for k in range(K):
+        assert np.array_equal(hist[k].astype(np.uint64), orc.histogram(data[k * chunk:(k + 1) * chunk])), "hist chunk %d" % k
+    assert np.array_equal(lens, rlens), "code lengths"
+    assert np.array_equal(off, roff), "chunk offsets"
+    assert np.array_equal(payload, rp), "payload bytes"
+    # and back
+    sizes = np.diff(off).astype(np.uint32)
+    orig = np.array([min(chunk, data.size - k * chunk) for k in range(K)], dtype=np.uint32)
+    back = codec.decode(payload, off[:-1], sizes, orig, lens)
+    assert np.array_equal(back, data), "round trip"
+    return payload, off, lens
+
+
+# ---- histogram (CpuFrequencyServiceTest.java) ------------------------------------------------------
+def test_histogram_known_answers(hz, codec):
+    fs = hz.B200FrequencyService(codec)
+    h = fs.compute_histogram(bytes([0, 1, 2, 1, 0, 1]), 0, 6)
+    assert (h[0], h[1], h[2]) == (2, 3, 1) and h.sum() == 6 and h.dtype == np.int64
+    assert np.all(fs.compute_histogram(bytes(range(256)), 0, 256) == 1)
+    d = bytes(5 if i < 50 else 10 for i in range(100))
+    h = fs.compute_histogram(d, 25, 50)
+    assert h[5] == 25 and h[10] == 25
+    h = fs.compute_histogram(np.array([-1, -2, -3, -1], dtype=np.int8).view(np.uint8), 0, 4)
+    assert (h[255], h[254], h[253]) == (2, 1, 1)
+    d = (np.arange(128 * 1024) % 10).astype(np.uint8)
+    assert np.array_equal(fs.compute_histogram(d, 0, d.size).astype(np.uint64), orc.histogram(d))
+    assert fs.is_available() and "B200" in fs.get_service_name()
+
+
+@pytest.mark.parametrize("n,chunk", [(1, 1), (15, 64), (61440, 61440), (61441, 61440), (200_001, 50_000),
+                                      (3 * MiB + 17, MiB), (1_000_003, 333_337)])
+@pytest.mark.parametrize("kind", ["uniform", "zipf", "same"])
+def test_histogram_exact(codec, n, chunk, kind):
+    rng = np.random.default_rng(n + chunk)
+    data = {"uniform": lambda: rng.integers(0, 256, n, dtype=np.uint8),
+            "zipf": lambda: datasets.zipf_stream(n, 3, seed=n),
+            "same": lambda: np.full(n, 0x41, dtype=np.uint8)}[kind]()
+    hist = codec.histogram(data, chunk)
+    for k in range(hist.shape[0]):
+        assert np.array_equal(hist[k].astype(np.uint64), orc.histogram(data[k * chunk:(k + 1) * chunk]))
+
+
+def test_histogram_unaligned_device_pointer(codec):
+    import torch
+    rng = np.random.default_rng(3)
+    host = rng.integers(0, 256, 500_000, dtype=np.uint8)
+    dev = torch.from_numpy(host).cuda()
+    for shift in (1, 7, 13):
+        view = dev[shift:]
+        hist = torch.zeros((4, 256), dtype=torch.int32, device="cuda")
+        n = view.numel()
+        chunk = (n + 3) // 4
+        codec.histogram_raw(view.data_ptr(), n, chunk, hist)
+        codec.sync()
+        h = hist.cpu().numpy().astype(np.uint64)
+        for k in range(4):
+            assert np.array_equal(h[k], orc.histogram(host[shift:][k * chunk:(k + 1) * chunk]))
+
+
+# ---- codebook (CanonicalHuffmanTest.java, HuffmanPropertyTest.java) ----------------------------------
+def _check_codebooks(codec, hists):
+    hists = np.asarray(hists, dtype=np.uint32).reshape(-1, 256)
+    lens, codes = codec.build_codebooks(hists)
+    for k in range(hists.shape[0]):
+        ln, mx = orc.code_lengths(hists[k].astype(np.uint64))
+        cd, _ = orc.canonical_codes(ln)
+        assert mx >= 0
+        assert np.array_equal(lens[k], ln.astype(np.uint8)), "lengths, histogram %d" % k
+        assert np.array_equal(codes[k], cd), "codes, histogram %d" % k
+    assert np.array_equal(codec.codes_from_lengths(lens), codes)
+
+
+def test_codebook_jqwik_style(codec):
+    rng = np.random.default_rng(2024)
+    h = rng.integers(0, 1001, (400, 256)).astype(np.uint32)          # HuffmanPropertyTest.java:81-92
+    h[np.arange(400), rng.integers(0, 256, 400)] += 1
+    _check_codebooks(codec, h)
+
+
+def test_codebook_heavy_ties(codec):
+    rng = np.random.default_rng(7)
+    hs = [np.full(256, 100), np.full(256, 1), 2 ** (np.arange(256) % 20), rng.choice([3, 5], 256),
+          rng.choice([1, 2, 4, 8], 256), np.arange(1, 257), np.arange(256, 0, -1),
+          np.where(np.arange(256) % 3 == 0, 0, 7), rng.integers(0, 4, 256)]
+    for nsym in (2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 100, 255):
+        h = np.zeros(256, dtype=np.int64); h[rng.choice(256, nsym, replace=False)] = 1; hs.append(h)
+        h = np.zeros(256, dtype=np.int64); h[:nsym] = rng.integers(1, 4, nsym); hs.append(h)
+    _check_codebooks(codec, np.array(hs, dtype=np.uint32))
+
+
+def test_codebook_edge_cases(codec):
+    hs = np.zeros((4, 256), dtype=np.uint32)
+    hs[1, 42] = 1000                                                 # single symbol -> length 1, code 0
+    hs[2, 0], hs[2, 255] = 1, 1
+    hs[3, 10], hs[3, 20], hs[3, 30] = 5, 5, 10
+    lens, codes = codec.build_codebooks(hs)
+    assert not lens[0].any() and not codes[0].any()
+    assert lens[1, 42] == 1 and lens[1].sum() == 1 and codes[1, 42] == 0
+    _check_codebooks(codec, hs)
+
+
+def test_codebook_long_codes(codec, hz):
+    hs = [datasets.fib_like_hist(n).astype(np.uint32) for n in (10, 17, 24, 33)]     # max length 9..32
+    _check_codebooks(codec, np.array(hs))
+    assert orc.code_lengths(datasets.fib_like_hist(33))[1] == 32
+    with pytest.raises(hz.HzError) as e:                                             # depth 33: reference throws
+        codec.build_codebooks(datasets.fib_like_hist(34).astype(np.uint32))
+    assert e.value.status == hz.HZ_ERR_CODE_TOO_LONG
+
+
+# ---- encode + decode ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("idx", range(11))
+def test_reference_inputs(codec, idx):
+    data, name, chunk, _ = datasets.reference_cases()[idx]
+    check_encode(codec, data, chunk)
+    check_encode(codec, data, 1 * MiB)
+
+
+def test_fixtures(codec):
+    for chunk in (1 * MiB, 2 * MiB, 16 * MiB, 32 * MiB):
+        payload, off, lens = check_encode(codec, datasets.fixture_bytes("test_2mb.bin"), chunk)
+        assert not payload.any() and payload.size == 262144
+    payload, _, lens = check_encode(codec, datasets.fixture_bytes("test_small.bin"), 32 * MiB)
+    assert payload.size == 256 and lens[0, 65] == 1
+    uni = orc.java_random_bytes(7, 1 * MiB)                     # stand-in for test_input.bin
+    check_encode(codec, uni, 16 * MiB)
+
+
+@pytest.mark.parametrize("entropy", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("chunk", [64 * 1024, 1 * MiB])
+def test_zipf_streams(codec, entropy, chunk):
+    data = datasets.zipf_stream(2 * MiB + 4321, entropy, seed=entropy)
+    check_encode(codec, data, chunk)
+
+
+@pytest.mark.parametrize("n,chunk", [(0, 1024), (1, 1024), (7, 3), (1023, 4096), (61439, 1 << 20), (61440, 1 << 20),
+                                      (61441, 1 << 20), (122880, 61440), (1_000_003, 100_003), (300_000, 77)])
+def test_ragged_sizes(codec, n, chunk):
+    data = datasets.zipf_stream(n, 4, seed=n + 1) if n else np.zeros(0, np.uint8)
+    check_encode(codec, data, chunk)
+
+
+def test_wide_codes_encode_decode(codec):
+    """Chunks whose longest code is > 16 bits (wide encoder path) and > 12 bits (decoder fallback)."""
+    rng = np.random.default_rng(11)
+    for nsym in (18, 24, 30):
+        f = datasets.fib_like_hist(nsym)[:nsym].astype(np.int64)      # exact Fibonacci counts -> depth nsym-1
+        data = np.repeat(np.arange(nsym, dtype=np.uint8), f)
+        rng.shuffle(data)
+        payload, off, lens = check_encode(codec, data, 1 << 22)
+        assert lens.max() == nsym - 1
+
+
+def test_uniform_length_codes(codec):
+    """Equal-length codes never self-synchronise; lengths 7 / 5 / 3 do not divide the subsequence size."""
+    for nsym in (128, 32, 8, 2):
+        data = (np.arange(700_001) * 2654435761 % nsym).astype(np.uint8)
+        payload, off, lens = check_encode(codec, data, 1 << 20)
+        assert len(set(lens[0][lens[0] > 0])) == 1
+
+
+def test_decode_oracle_streams_and_errors(codec, hz):
+    data = datasets.zipf_stream(500_000, 5, seed=9)
+    rp, roff, rlens = oracle_encode(data, 200_000)
+    sizes = np.diff(roff).astype(np.uint32)
+    orig = np.array([200_000, 200_000, 100_000], dtype=np.uint32)
+    assert np.array_equal(codec.decode(rp, roff[:-1], sizes, orig, rlens), data)
+    # single-symbol chunk with a stray 1 bit: "Huffman decode error at position i"
+    ln = np.zeros((1, 256), dtype=np.uint8); ln[0, 65] = 1
+    comp = np.zeros(64, dtype=np.uint8); comp[10] = 0x10
+    with pytest.raises(hz.HzError) as e:
+        codec.decode(comp, [0], [64], [512], ln)
+    assert e.value.status == hz.HZ_ERR_DECODE
+    out = codec.decode(np.zeros(64, np.uint8), [0], [64], [512], ln)      # context still usable
+    assert np.all(out == 65)
+    # over-subscribed length table
+    bad = np.zeros((1, 256), dtype=np.uint8); bad[0, :3] = 1
+    with pytest.raises(hz.HzError) as e:
+        codec.decode(comp, [0], [64], [8], bad)
+    assert e.value.status == hz.HZ_ERR_BAD_LENGTHS
+
+
+def test_decode_reads_zero_bits_past_the_end(codec):
+    # TableBasedHuffmanDecoder.java:204-208: bits past the end of the chunk are 0
+    ln = np.zeros((1, 256), dtype=np.uint8); ln[0, 7] = 1; ln[0, 9] = 1      # 7 -> '0', 9 -> '1'
+    comp = np.array([0b10100000], dtype=np.uint8)
+    out = codec.decode(comp, [0], [1], [20], ln)
+    ref, rc = orc.decode(comp, ln[0].astype(np.int32), 20, literal=True)
+    assert rc == 0 and np.array_equal(out, ref)
+
+
+def test_deterministic(codec):
+    data = datasets.zipf_stream(3 * MiB, 4, seed=77)
+    a = codec.encode(data, MiB)
+    for _ in range(3):
+        b = codec.encode(data, MiB)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_global_codebook_extension(codec):
+    data = datasets.zipf_stream(1_000_000, 4, seed=5)
+    hist = codec.histogram(data, 250_000).astype(np.uint64).sum(axis=0)
+    lens, codes = codec.build_codebooks(hist.astype(np.uint32))
+    payload, off = codec.encode_with_lengths(data, 250_000, lens[0])
+    ln = lens[0].astype(np.int32)
+    cd, _ = orc.canonical_codes(ln)
+    for k in range(4):
+        ref = orc.encode(data[k * 250_000:(k + 1) * 250_000], ln, cd)
+        assert np.array_equal(payload[int(off[k]):int(off[k + 1])], ref)
+    back = codec.decode(payload, off[:-1], np.diff(off).astype(np.uint32), np.full(4, 250_000, np.uint32),
+                        np.tile(lens[0], (4, 1)))
+    assert np.array_equal(back, data)
+
+
+# ---- container (.dcz) ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("idx", range(11))
+def test_dcz_byte_identical(codec, idx):
+    data, name, chunk, expect = datasets.reference_cases()[idx]
+    z = codec.compress_buffer(data, chunk, name, 0)
+    assert len(z) == expect
+    assert z == orc.compress(data, chunk, name, 0)
+    golden = json.load(open(os.path.join(datasets.GOLDEN_DIR, "reference_cases.json")))[idx]
+    assert hashlib.sha256(z).hexdigest() == golden["dcz_sha256"]
+    assert codec.decompress_buffer(z) == data
+    assert orc.decompress(z) == data
+
+
+def test_service_files(hz, tmp_path):
+    data = datasets.zipf_stream(5 * MiB + 99, 4, seed=21).tobytes()
+    src = tmp_path / "in.bin"; src.write_bytes(data)
+    with hz.B200CompressionService(1) as svc:
+        seen = []
+        svc.compress(str(src), str(tmp_path / "out.dcz"), lambda f: seen.append(f))
+        assert len(seen) == 6 and seen[-1] == 1.0 and all(0 < f <= 1 for f in seen)
+        z = (tmp_path / "out.dcz").read_bytes()
+        mtime = int.from_bytes(z[int.from_bytes(z[-8:], "big") + 12 + 6 + 8:][:8], "big")
+        assert z == orc.compress(data, MiB, "in.bin", mtime)
+        assert svc.verify_integrity(str(tmp_path / "out.dcz"))
+        svc.decompress(str(tmp_path / "out.dcz"), str(tmp_path / "back.bin"))
+        assert (tmp_path / "back.bin").read_bytes() == data
+        with pytest.raises(NotImplementedError):
+            svc.resume_compression(str(src), str(tmp_path / "o2"), 0)
+        # corrupt one payload byte -> checksum / decode failure, verify says False
+        bad = bytearray(z); bad[1000] ^= 0x5A
+        (tmp_path / "bad.dcz").write_bytes(bytes(bad))
+        assert not svc.verify_integrity(str(tmp_path / "bad.dcz"))
+        with pytest.raises(hz.HzError):
+            svc.decompress(str(tmp_path / "bad.dcz"), str(tmp_path / "bad.out"))
+        # bad magic
+        (tmp_path / "junk.dcz").write_bytes(b"not a dcz file at all" * 10)
+        with pytest.raises(hz.HzError) as e:
+            svc.decompress(str(tmp_path / "junk.dcz"), str(tmp_path / "junk.out"))
+        assert e.value.status == hz.HZ_ERR_FORMAT
+
+
+def test_legacy_header_first_layout(codec):
+    data = b"Hello World! " * 100
+    z = orc.compress(data, MiB, "t.txt", 5)
+    payload_len = int.from_bytes(z[-8:], "big")
+    legacy = z[payload_len:-8] + z[:payload_len]                 # header first, payload after
+    assert codec.decompress_buffer(legacy) == data
+    assert orc.decompress(legacy) == data
+
+
+def test_sha256_chunks(codec):
+    data = datasets.zipf_stream(300_000, 6, seed=3)
+    dig = codec.sha256_chunks(data, 64 * 1024)
+    for k in range(dig.shape[0]):
+        assert dig[k].tobytes() == hashlib.sha256(data[k * 65536:(k + 1) * 65536].tobytes()).digest()
+
+
+# ---- large, device-resident (size-independent properties) --------------------------------------------------
+def test_large_device_resident_roundtrip(codec):
+    import torch
+    n, chunk = 256 * MiB, 16 * MiB
+    K = n // chunk
+    qt = datasets.zipf_qtable(4)
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    codec.synth_fill(src.data_ptr(), n, 0, 0x5EED0001, qt)
+    codec.sync()
+    assert np.array_equal(src[:100_000].cpu().numpy(), datasets.synth_host(100_000, 0x5EED0001, qt))
+    comp = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(K + 1, dtype=torch.int64, device="cuda")
+    lens = torch.zeros((K, 256), dtype=torch.uint8, device="cuda")
+    codec.encode_raw(src.data_ptr(), n, chunk, comp.data_ptr(), n, off.data_ptr(), lens.data_ptr(), None)
+    codec.sync()
+    offh = off.cpu().numpy().astype(np.uint64)
+    # chunk 0 and the last chunk against the oracle, all chunks through the round trip
+    for k in (0, K - 1):
+        ref, ln, _ = orc.encode_chunk(src[k * chunk:(k + 1) * chunk].cpu().numpy())
+        assert np.array_equal(lens[k].cpu().numpy(), ln.astype(np.uint8))
+        assert np.array_equal(comp[int(offh[k]):int(offh[k + 1])].cpu().numpy(), ref)
+    sizes = (off[1:] - off[:-1]).to(torch.int32)
+    orig = torch.full((K,), chunk, dtype=torch.int32, device="cuda")
+    back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    codec.decode_raw(comp.data_ptr(), int(offh[K]), off.data_ptr(), sizes.data_ptr(), orig.data_ptr(), None,
+                     lens.data_ptr(), K, back.data_ptr(), n)
+    codec.sync()
+    assert torch.equal(back, src)
