@@ -30,7 +30,7 @@
 #define LUTB HZ_DEC_LUT_BITS
 #define LUTN (1 << LUTB)
 
-struct DecTables {
+struct __align__(16) DecTables {
     uint16_t lut[LUTN];        // sym | len<<8 ; 0 = not resolvable by the table
     uint32_t first[34];        // first canonical code of each length
     uint32_t count[34];        // symbols per length
