@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — Huffman encode/decode throughput of the B200 hot path (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--size-mib M] [--entropy H] [--chunk-kib C]
+
+One STEP = one pass of the hot path over one synthetic stream: encode the whole stream
+(histogram -> codebook -> bit-pack, all chunks) and then decode it again, both through the C ABI
+of libhuffb200.so.  `value` = uncompressed GB (1e9 B) coded per second over both directions
+(2*N bytes per step; the harmonic mean of the encode and the decode GB/s), stream resident in
+HBM.  `e2e` = the same metric with HOST buffers (pinned), host<->device copies in the timed
+region.  N>1: one process per GPU (torchrun), every rank codes its own shard of the stream
+(weak scaling, no data-path collective; chunks are independent), time = max over ranks.
+
+`--impl reference` times the reference's CPU path (the C++ restatement in oracle/, because no
+JVM exists on these boxes) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+MiB = 1 << 20
+SEED = 0x5EED0001
+METRIC = "huffman_encode_decode_throughput"
+UNIT = "GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size-mib", type=int, default=4096, help="stream bytes per GPU (MiB)")
+    ap.add_argument("--entropy", type=int, default=4, help="order-0 entropy of the Zipf stream, bits/symbol (1..8)")
+    ap.add_argument("--chunk-kib", type=int, default=16 * 1024, help="chunk size in KiB (reference default 16 MiB)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-mib", type=int, default=1024)
+    ap.add_argument("--ref-sample-mib", type=int, default=256)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "zipf_H%d_%dMiB_per_gpu_chunk%dKiB" % (a.entropy, a.size_mib, a.chunk_kib)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of each kernel from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
+    NOTE = {"sw_power_cap": 0x4, "sync_boost": 0x10, "display_clock": 0x100, "app_clocks": 0x2}
+
+    def __init__(self, cuda_index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self._h = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(cuda_index).uuid)
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _loop(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for name, bit in list(self.BAD.items()) + list(self.NOTE.items()):
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self._h is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms (oracle = checker / baseline only; never on the product path)
+# ------------------------------------------------------------------------------------------------
+def cpu_roundtrip(sample, chunk, threads=0):
+    """Literal restatement of the reference CPU path (bit-at-a-time BitOutputStream encode,
+    one-bit-peek table decode, java.util.PriorityQueue codebook, chunk-parallel worker pool sized
+    max(2, min(nproc, 8)) as cpu/CpuCompressionService.java:42-44).  Returns (enc_s, dec_s, threads)."""
+    import orc
+    t0 = time.perf_counter()
+    comp, sizes, lens, T = orc.encode_chunks_mt(sample, chunk, literal=True, threads=threads)
+    t1 = time.perf_counter()
+    out, _ = orc.decode_chunks_mt(comp, sizes, lens, sample.size, chunk, literal=True, threads=threads)
+    t2 = time.perf_counter()
+    if not np.array_equal(out, sample):
+        raise RuntimeError("oracle round trip failed")
+    return t1 - t0, t2 - t1, T
+
+
+def host_stream(a, nbytes, offset=0):
+    import datasets
+    q = datasets.zipf_qtable(a.entropy)
+    parts = []
+    for o in range(0, nbytes, 64 * MiB):
+        parts.append(datasets.synth_host(min(64 * MiB, nbytes - o), SEED, q, offset + o))
+    return np.concatenate(parts)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    chunk = a.chunk_kib * 1024
+    nbytes = min(a.ref_sample_mib, a.size_mib) * MiB
+    sample = host_stream(a, nbytes)
+    for _ in range(a.warmup):
+        cpu_roundtrip(sample[: min(nbytes, 4 * chunk)], chunk)
+    te = td = 0.0
+    T = 0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e, d, T = cpu_roundtrip(sample, chunk)
+        te += e
+        td += d
+    total = time.perf_counter() - t0
+    val = 2.0 * nbytes * a.steps / total / 1e9
+    sample_desc = "first %d MiB of the same stream per step (warm-up steps: first %d chunks)" % (nbytes // MiB, 4)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample_desc,
+                   "encode_GBps": nbytes * a.steps / te / 1e9, "decode_GBps": nbytes * a.steps / td / 1e9},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": T, "kind": "port", "sample": sample_desc,
+                         "note": "no JVM on the box: the reference's CPU path restated literally in C++ (oracle/), "
+                                 "worker pool max(2,min(nproc,8)) as the reference; host has %d cores" % os.cpu_count()},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(name, n, C, K, spc):
+    """ALGORITHMIC bytes one launch of kernel `name` must move."""
+    if name.startswith("hist"):
+        return n
+    if name == "encode":
+        return n + C
+    if name == "dec_sync":
+        return C
+    if name in ("dec_write", "decode"):
+        return C + n
+    if name == "codebook":
+        return K * spc * 1024 + K * (256 + 1024)
+    return None
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    import datasets
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hz = ge.load_package()
+    codec = hz.Codec(local)
+    stream = torch.cuda.current_stream()
+    codec.set_stream(stream.cuda_stream)
+
+    n = a.size_mib * MiB
+    chunk = a.chunk_kib * 1024
+    K = (n + chunk - 1) // chunk
+    spc = (chunk + 61440 - 1) // 61440
+    q = datasets.zipf_qtable(a.entropy)
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    codec.synth_fill(src.data_ptr(), n, rank * n, SEED, q)
+    comp = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(K + 1, dtype=torch.int64, device="cuda")
+    lens = torch.zeros((K, 256), dtype=torch.uint8, device="cuda")
+    back = torch.empty(n, dtype=torch.uint8, device="cuda")
+    orig = torch.full((K,), chunk, dtype=torch.int32, device="cuda")
+    orig[K - 1] = n - (K - 1) * chunk
+
+    def enc():
+        codec.encode_raw(src.data_ptr(), n, chunk, comp.data_ptr(), n, off.data_ptr(), lens.data_ptr(), None)
+
+    enc()
+    codec.sync()
+    C = int(off[K].item())
+    sizes = (off[1:] - off[:-1]).to(torch.int32).contiguous()
+
+    def dec():
+        codec.decode_raw(comp.data_ptr(), C, off.data_ptr(), sizes.data_ptr(), orig.data_ptr(), None, lens.data_ptr(), K,
+                         back.data_ptr(), n)
+
+    dec()
+    codec.sync()
+    if not torch.equal(back, src):
+        raise SystemExit("bench.py: decode(encode(x)) != x")
+    if rank == 0:
+        # bit-exactness spot check of chunk 0 against the CPU oracle (checker use only)
+        import orc
+        c0 = src[:min(n, chunk)].cpu().numpy()
+        ref, ln, _ = orc.encode_chunk(c0)
+        got = comp[: int(off[1].item())].cpu().numpy()
+        if not (np.array_equal(got, ref) and np.array_equal(lens[0].cpu().numpy(), ln.astype(np.uint8))):
+            raise SystemExit("bench.py: chunk 0 differs from the oracle")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        enc()
+        dec()
+    barrier()
+    launches0 = codec.launch_count()
+    codec.prof_enable(True)
+    codec.prof_reset()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * a.steps + 1)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    ev[0].record()
+    for i in range(a.steps):
+        enc()
+        ev[2 * i + 1].record()
+        dec()
+        ev[2 * i + 2].record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = codec.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    enc_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(a.steps)) / a.steps
+    dec_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(a.steps)) / a.steps
+    prof = codec.prof()
+    codec.prof_enable(False)
+    codec.sync()
+    t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms = (float(x) for x in t.cpu())
+    ms_per_step = total_ms / a.steps
+    value = 2.0 * n * world / (ms_per_step * 1e6)
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        h_src = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_src.copy_(src)
+        h_comp = torch.empty(n + 16, dtype=torch.uint8).pin_memory()
+        h_back = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_off = np.zeros(K + 1, dtype=np.uint64)
+        h_lens = np.zeros((K, 256), dtype=np.uint8)
+        h_orig = orig.cpu().numpy().astype(np.uint32)
+
+        def e2e_step():
+            codec.encode_raw(h_src.data_ptr(), n, chunk, h_comp.data_ptr(), n, h_off, h_lens, None)
+            csz = np.diff(h_off).astype(np.uint32)
+            codec.decode_raw(h_comp.data_ptr(), int(h_off[K]), h_off, csz, h_orig, None, h_lens, K, h_back.data_ptr(), n)
+            codec.sync()
+
+        e2e_step()
+        if not torch.equal(h_back, h_src):
+            raise SystemExit("bench.py: e2e round trip failed")
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_s = float(dt.item()) / a.e2e_steps
+        meta = (K + 1) * 8 + K * 256
+        e2e = {"value": 2.0 * n * world / e2e_s / 1e9, "unit": UNIT, "ms_per_step": 1e3 * e2e_s, "steps": a.e2e_steps,
+               "h2d_bytes_per_step": n + C + 2 * meta + 8 * K, "d2h_bytes_per_step": C + n + meta,
+               "api": "hz_encode + hz_decode with pinned host buffers"}
+        del h_src, h_comp, h_back
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel + per-kernel table
+    peak, peak_src = measured_peak()
+    traffic = ncu_traffic()
+    kernels = []
+    for name, (ms, cnt) in prof.items():
+        per = ms / max(cnt, 1)
+        ab = algorithmic_bytes(name, n, C, K, spc)
+        kernels.append({"name": name, "launches_per_step": cnt / a.steps, "ms_per_launch": per,
+                        "share_of_step": ms / a.steps / ms_per_step,
+                        "algorithmic_bytes": ab,
+                        "achieved_GBps": (ab / (per * 1e6)) if ab and per > 0 else None})
+    kernels.sort(key=lambda k: -k["share_of_step"])
+    dom = next((k for k in kernels if k["algorithmic_bytes"]), None)
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": dom["achieved_GBps"] / peak, "traffic": traffic.get(dom["name"]),
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "ms_per_launch": dom["ms_per_launch"],
+                    "peak_source": peak_src}
+    stages = {
+        "encode": {"GBps": n / (enc_ms * 1e6), "ms": enc_ms, "algorithmic_bytes": n + C,
+                   "roofline_frac": (n + C) / (enc_ms * 1e6) / peak},
+        "decode": {"GBps": n / (dec_ms * 1e6), "ms": dec_ms, "algorithmic_bytes": C + n,
+                   "roofline_frac": (C + n) / (dec_ms * 1e6) / peak},
+    }
+
+    cpu = None
+    if not a.no_cpu and world == 1:
+        nb = min(a.cpu_sample_mib, a.size_mib) * MiB
+        sample = src[:nb].cpu().numpy()
+        e, d, T = cpu_roundtrip(sample, chunk)
+        cpu = {"value": 2.0 * nb / (e + d) / 1e9, "unit": UNIT, "cores": T, "kind": "port",
+               "sample": "first %d MiB of the benchmark stream, one encode+decode pass" % (nb // MiB),
+               "encode_GBps": nb / e / 1e9, "decode_GBps": nb / d / 1e9, "host_cores": os.cpu_count()}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "bytes_per_gpu": n, "chunk_bytes": chunk, "chunks_per_gpu": K,
+                   "compressed_bytes_per_gpu": C, "bits_per_symbol": 8.0 * C / n, "seed": SEED,
+                   "value_definition": "2*N*n_gpus / step time; step = encode(all chunks) then decode(all chunks), device-resident",
+                   "l2": "inputs (%d MiB) are larger than the 126 MB L2; no flush between iterations" % a.size_mib,
+                   "codebooks": "per chunk (reference parity mode)"},
+        "stages": stages, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_b200(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -42,18 +42,38 @@ bool hz_is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+static cudaEvent_t prof_event(hz_ctx* ctx) {
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
 void hz_prof_begin(hz_ctx* ctx) {
-    if (ctx->prof) cudaEventRecord(ctx->ev0, ctx->stream);
+    if (!ctx->prof) return;
+    ctx->ev_open = prof_event(ctx);
+    cudaEventRecord(ctx->ev_open, ctx->stream);
 }
 void hz_prof_end(hz_ctx* ctx, const char* name) {
-    if (!ctx->prof) return;
-    cudaEventRecord(ctx->ev1, ctx->stream);
-    cudaEventSynchronize(ctx->ev1);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    for (auto& e : ctx->prof_entries)
-        if (strcmp(e.name, name) == 0) { e.ms += ms; e.launches++; return; }
-    ctx->prof_entries.push_back({name, (double)ms, 1});
+    if (!ctx->prof || !ctx->ev_open) return;
+    cudaEvent_t e1 = prof_event(ctx);
+    cudaEventRecord(e1, ctx->stream);
+    ctx->prof_pending.push_back({name, ctx->ev_open, e1});
+    ctx->ev_open = nullptr;
+}
+// Turn recorded event pairs into per-kernel totals (waits for the last recorded event).
+void hz_prof_resolve(hz_ctx* ctx) {
+    for (auto& p : ctx->prof_pending) {
+        float ms = 0;
+        cudaEventSynchronize(p.e1);
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) != cudaSuccess) { cudaGetLastError(); ms = 0; }
+        bool found = false;
+        for (auto& e : ctx->prof_entries)
+            if (strcmp(e.name, p.name) == 0) { e.ms += ms; e.launches++; found = true; break; }
+        if (!found) ctx->prof_entries.push_back({p.name, (double)ms, 1});
+        ctx->ev_pool.push_back(p.e0);
+        ctx->ev_pool.push_back(p.e1);
+    }
+    ctx->prof_pending.clear();
 }
 
 static int check_status(hz_ctx* ctx) {
@@ -113,8 +133,6 @@ int hz_create(int device, hz_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaMalloc(&c->d_status, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(c->d_status, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaHostAlloc(&c->h_status, sizeof(int), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
-    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) { cudaGetLastError(); hz_destroy(c); return HZ_ERR_CUDA; }
     c->stream = c->own_stream;
@@ -133,8 +151,8 @@ void hz_destroy(hz_ctx* c) {
     if (c->d_status) cudaFree(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_pin) cudaFreeHost(c->h_pin);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
+    hz_prof_resolve(c);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -154,8 +172,17 @@ int hz_sync(hz_ctx* ctx) {
 }
 
 int hz_prof_enable(hz_ctx* ctx, int on) { if (!ctx) return HZ_ERR_ARG; ctx->prof = on != 0; return HZ_OK; }
-int hz_prof_reset(hz_ctx* ctx) { if (!ctx) return HZ_ERR_ARG; ctx->prof_entries.clear(); return HZ_OK; }
-int hz_prof_count(hz_ctx* ctx) { return ctx ? (int)ctx->prof_entries.size() : 0; }
+int hz_prof_reset(hz_ctx* ctx) {
+    if (!ctx) return HZ_ERR_ARG;
+    hz_prof_resolve(ctx);
+    ctx->prof_entries.clear();
+    return HZ_OK;
+}
+int hz_prof_count(hz_ctx* ctx) {
+    if (!ctx) return 0;
+    hz_prof_resolve(ctx);
+    return (int)ctx->prof_entries.size();
+}
 int hz_prof_get(hz_ctx* ctx, int i, const char** name, double* total_ms, uint64_t* launches) {
     if (!ctx || i < 0 || i >= (int)ctx->prof_entries.size()) return HZ_ERR_ARG;
     if (name) *name = ctx->prof_entries[i].name;

@@ -47,9 +47,13 @@ struct hz_ctx {
     DevBuf dec_meta, dec_rec, dec_seqcnt, dec_misc;
     void* h_pin = nullptr; size_t h_pin_cap = 0;
     // profiling
+    // profiling: event pairs are recorded without synchronising and resolved lazily
     bool prof = false;
     std::vector<hz_prof_entry> prof_entries;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    struct PendingProf { const char* name; cudaEvent_t e0, e1; };
+    std::vector<PendingProf> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_open = nullptr;
 };
 
 int hz_fail(hz_ctx* ctx, int code, const char* fmt, ...);
@@ -58,6 +62,7 @@ int hz_reserve(hz_ctx* ctx, DevBuf* b, size_t bytes);
 bool hz_is_device_ptr(const void* p);
 void hz_prof_begin(hz_ctx* ctx);
 void hz_prof_end(hz_ctx* ctx, const char* name);
+void hz_prof_resolve(hz_ctx* ctx);
 
 #define HZ_CUDA(ctx, call)                                                   \
     do {                                                                     \
