@@ -225,7 +225,8 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hz = ge.load_package()
     codec = hz.Codec(local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: the codec, torch and the events share it
+    torch.cuda.set_stream(stream)
     codec.set_stream(stream.cuda_stream)
 
     n = a.size_mib * MiB

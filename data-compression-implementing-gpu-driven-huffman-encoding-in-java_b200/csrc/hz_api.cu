@@ -146,7 +146,7 @@ void hz_destroy(hz_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->seg_hist, &c->chunk_hist, &c->len, &c->code, &c->chunk_bits, &c->comp_size, &c->comp_off,
                       &c->seg_bitoff, &c->counter, &c->stage_in, &c->stage_out, &c->stage_a, &c->stage_b,
-                      &c->stage_c, &c->stage_d, &c->stage_e, &c->dec_meta, &c->dec_rec, &c->dec_seqcnt, &c->dec_misc};
+                      &c->stage_c, &c->stage_d, &c->stage_e, &c->dec_meta, &c->dec_rec, &c->dec_seqcnt, &c->dec_misc, &c->dec_tables};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->d_status) cudaFree(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);

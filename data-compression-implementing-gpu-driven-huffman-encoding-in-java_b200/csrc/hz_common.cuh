@@ -15,16 +15,6 @@
 #define HZ_THREADS 256
 #define HZ_SEG_BYTES 61440u
 
-// Decode geometry: one thread decodes one subsequence of HZ_SUB_WORDS 32-bit words (an ODD
-// number of words, so that consecutive subsequences staged in shared memory fall into
-// different banks); a "sequence" = 256 subsequences = what one CTA pass covers.
-#define HZ_SUB_WORDS 17
-#define HZ_SUB_BITS (HZ_SUB_WORDS * 32)
-#define HZ_OVERLAP_BITS 128                  // speculative run-in before a subsequence
-#define HZ_DEC_THREADS 256
-#define HZ_SEQ_PER_CTA 4                     // sequences handled back to back by one CTA
-#define HZ_DEC_LUT_BITS 12
-
 struct hz_prof_entry { const char* name; double ms; uint64_t launches; };
 
 struct DevBuf {                               // grow-only device scratch buffer
@@ -44,7 +34,7 @@ struct hz_ctx {
     // scratch
     DevBuf seg_hist, chunk_hist, len, code, chunk_bits, comp_size, comp_off, seg_bitoff, counter;
     DevBuf stage_in, stage_out, stage_a, stage_b, stage_c, stage_d, stage_e;
-    DevBuf dec_meta, dec_rec, dec_seqcnt, dec_misc;
+    DevBuf dec_meta, dec_rec, dec_seqcnt, dec_misc, dec_tables;
     void* h_pin = nullptr; size_t h_pin_cap = 0;
     // profiling
     // profiling: event pairs are recorded without synchronising and resolved lazily

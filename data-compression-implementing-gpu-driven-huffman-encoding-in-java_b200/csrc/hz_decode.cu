@@ -5,163 +5,175 @@
 // CpuCompressionService.decodeChunkParallel, service/cpu/CpuCompressionService.java:511-532).
 // A chunk of the .dcz payload is ONE sequential bitstream without restart markers, and the
 // container must stay bit-identical, so parallelism inside a chunk comes from the
-// self-synchronisation property of Huffman codes:
+// self-synchronisation property of Huffman codes.  The stream of a chunk is cut into
+// subsequences of DEC_SUB_BITS bits (one per thread); 256 subsequences form a sequence (one CTA
+// pass); a CTA owns DEC_SEQ_PER_CTA consecutive sequences.
 //
-//   plan   (1 CTA)      per-chunk subsequence / sequence / CTA counts and their prefix sums.
-//   sync   (many CTAs)  thread i starts HZ_OVERLAP_BITS before subsequence i (a guess), records
-//                       where it crosses INTO the subsequence (entry), keeps decoding and
-//                       counting symbols until it crosses OUT (exit).  The chain is valid when
-//                       exit[i-1] == entry[i] for every i, anchored at bit 0 of the chunk.
-//                       Mismatches inside a CTA are repaired by re-decoding from the neighbour's
-//                       exit until nothing changes; the CTA's very first subsequence is left to:
-//   fix    (1 CTA/chunk) compares every CTA boundary, re-walks from the true position where the
-//                       guess was wrong (repeats until stable), then scans symbol counts into
-//                       output offsets.
-//   write  (many CTAs)  decodes every subsequence again from its verified entry and stores the
-//                       symbols; reports HZ_ERR_DECODE if a bit pattern matches no codeword.
+//   plan    (1 CTA)       per-chunk subsequence / sequence / CTA counts and their prefix sums.
+//   tables  (1 CTA/chunk) multi-symbol lookup tables of every chunk that spans several CTAs,
+//                         built once into global memory (single-CTA chunks build them in place).
+//   sync    (many CTAs)   the compressed bytes of a sequence are staged in shared memory with a
+//                         1-D TMA bulk copy (cp.async.bulk + mbarrier, double buffered).  Thread i
+//                         starts DEC_OVERLAP_BITS before subsequence i (a guess), records where it
+//                         crosses INTO the subsequence (entry), keeps decoding and counting
+//                         codewords until it crosses OUT (exit).  The chain is valid when
+//                         exit[i-1] == entry[i]; mismatches inside a CTA are repaired by
+//                         re-decoding from the neighbour's exit; the CTA's first subsequence is
+//                         left to:
+//   fix     (1 CTA/chunk) compares every CTA boundary, re-walks from the true position where the
+//                         guess was wrong, then scans sequence symbol counts into output offsets.
+//   write   (many CTAs)   decodes every subsequence again from its verified entry, 1-3 symbols per
+//                         table lookup, into a per-warp shared-memory window that is written out
+//                         with aligned 128-bit stores.
 //
-// Lookup: 2^12-entry shared-memory table (symbol | len<<8) built per CTA from the 256 code
-// lengths; longer codes fall back to the canonical first-code walk.  Codes whose used lengths
-// are all equal never self-synchronise but need no synchronisation either: entries are computed
-// arithmetically.
+// Tables (LUTB = 12 bits of look-ahead):
+//   slut u16: l0 | ltot<<4 | n<<8    first codeword length, bits / codewords of all n (<=12)
+//             complete codewords inside the 12 bits (counting pass); 0 = first code longer than
+//             12 bits or no code at all -> canonical first-code walk.
+//   wlut u32: s0 | s1<<8 | s2<<16 | ltot<<24 | n<<28   up to three symbols per lookup.
+// Codes whose used lengths are all equal never self-synchronise but need no synchronisation
+// either: entries are computed arithmetically.
 #include "hz_common.cuh"
 
-#define DT HZ_DEC_THREADS
-#define LUTB HZ_DEC_LUT_BITS
+#define DT 256
+#define DEC_SUB_WORDS 17                      // odd: subsequences start in different smem banks
+#define DEC_SUB_BITS (DEC_SUB_WORDS * 32)     // 544
+#define DEC_SUB_BYTES (DEC_SUB_WORDS * 4)     // 68
+#define DEC_SEQ_BYTES (DT * DEC_SUB_BYTES)    // 17408
+#define DEC_SEQ_BITS (DT * DEC_SUB_BITS)
+#define DEC_OVERLAP_BITS 128
+#define DEC_OVERLAP_BYTES 16
+#define DEC_SEQ_PER_CTA 8
+#define DEC_SUBS_PER_CTA (DT * DEC_SEQ_PER_CTA)
+#define LUTB 12
 #define LUTN (1 << LUTB)
+// staged bytes per sequence: 16 alignment slack + 16 overlap + sequence + 32 look-ahead
+#define DEC_STAGE_BYTES (16 + DEC_OVERLAP_BYTES + DEC_SEQ_BYTES + 32)
+#define DEC_STAGE_WORDS (DEC_STAGE_BYTES / 4)
+#define DEC_WIN_BYTES 4096                    // per-warp output window of the write kernel
+#define DEC_NO_TABLE 0xFFFFFFFFu
+#define DEC_TABLE_BYTES (LUTN * 4 + LUTN * 2 + 1024)
 
-struct __align__(16) DecTables {
-    uint16_t lut[LUTN];        // sym | len<<8 ; 0 = not resolvable by the table
+struct __align__(16) DecAux {
     uint32_t first[34];        // first canonical code of each length
     uint32_t count[34];        // symbols per length
     uint32_t offs[34];         // offset of each length in `sorted`
     uint8_t sorted[256];       // symbols ordered by (length, symbol)
-    uint8_t len[256];
+    uint8_t len[256];          // code length of every symbol
     int maxlen, minlen, uniform, bad;
 };
+static_assert(sizeof(DecAux) <= 1024, "DecAux must fit its 1 KiB slot");
 
-// Build the decode tables of one chunk; all DT threads participate.
-__device__ void build_tables(DecTables& T, const uint8_t* __restrict__ len_k) {
+// ---------------------------------------------------------------------------------------------
+// table construction (all DT threads).  scratch: >= 8 KiB + 2 KiB of shared memory.
+// ---------------------------------------------------------------------------------------------
+template <bool WANT_W, bool WANT_S>
+__device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* __restrict__ slut,
+                             uint8_t* __restrict__ scratch, const uint8_t* __restrict__ len_k) {
+    uint16_t* base = reinterpret_cast<uint16_t*>(scratch);                // [LUTN] sym | len<<8
+    uint16_t* lj = reinterpret_cast<uint16_t*>(scratch + LUTN * 2);       // [256] left-justified codes (len<=12)
+    uint8_t* ljl = scratch + LUTN * 2 + 512;                              // [256] their lengths
+    uint32_t* cntw = reinterpret_cast<uint32_t*>(scratch + LUTN * 2 + 768);   // [8][34]
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    for (uint32_t i = t; i < LUTN / 8; i += DT) reinterpret_cast<uint4*>(T.lut)[i] = make_uint4(0, 0, 0, 0);
-    if (t < 34) T.count[t] = 0;
+    uint32_t l = len_k[t];
+    if (l > 32) l = 33;
+    A.len[t] = (uint8_t)l;
+    for (uint32_t i = t; i < 8 * 34; i += DT) cntw[i] = 0;
     __syncthreads();
-    uint32_t l = t < 256 ? len_k[t] : 0;
-    if (t < 256) {
-        if (l > 32) l = 33;                       // flagged below
-        T.len[t] = (uint8_t)l;
-        if (l > 0) atomicAdd(&T.count[l], 1u);
+    const uint32_t same = __match_any_sync(0xffffffffu, l);
+    const uint32_t rank_w = __popc(same & ((1u << lane) - 1));
+    if (rank_w == 0) cntw[wid * 34 + l] = __popc(same);
+    __syncthreads();
+    if (t < 34) {
+        uint32_t c = 0;
+        for (int w = 0; w < 8; ++w) c += cntw[w * 34 + t];
+        A.count[t] = t == 0 ? 0 : c;
     }
     __syncthreads();
     if (t == 0) {
         uint32_t c = 0, o = 0;
-        int mx = 0, mn = 99;
+        int mx = 0, mn = 0;
         uint64_t kraft = 0;                       // in units of 2^-32
-        T.first[0] = 0; T.offs[0] = 0;
+        A.first[0] = 0; A.offs[0] = 0;
         for (int L = 1; L <= 32; ++L) {
-            c = (c + (L > 1 ? T.count[L - 1] : 0u)) << 1;
-            T.first[L] = c; T.offs[L] = o; o += T.count[L];
-            if (T.count[L]) { mx = L; if (mn == 99) mn = L; kraft += (uint64_t)T.count[L] << (32 - L); }
+            c = (c + (L > 1 ? A.count[L - 1] : 0u)) << 1;
+            A.first[L] = c; A.offs[L] = o; o += A.count[L];
+            if (A.count[L]) { mx = L; if (!mn) mn = L; kraft += (uint64_t)A.count[L] << (32 - L); }
         }
-        T.maxlen = mx; T.minlen = mn == 99 ? 0 : mn;
-        T.uniform = (mx > 0 && mx == mn) ? mx : 0;
-        T.bad = (T.count[33] != 0) || (kraft > (1ull << 32));
+        A.offs[33] = o; A.first[33] = 0;
+        A.maxlen = mx; A.minlen = mn;
+        A.uniform = (mx > 0 && mx == mn) ? mx : 0;
+        A.bad = (A.count[33] != 0) || (kraft > (1ull << 32));
     }
     __syncthreads();
-    if (t < 256 && l > 0 && l <= 32) {
-        uint32_t rank = 0;
-        for (uint32_t s = 0; s < t; ++s) rank += (T.len[s] == l);
-        T.sorted[T.offs[l] + rank] = (uint8_t)t;
+    if (A.bad) return;
+    if (l >= 1 && l <= 32) {
+        uint32_t rank = rank_w;
+        for (uint32_t w = 0; w < wid; ++w) rank += cntw[w * 34 + l];
+        const uint32_t pos = A.offs[l] + rank;
+        A.sorted[pos] = (uint8_t)t;
+        if (l <= LUTB) { lj[pos] = (uint16_t)((A.first[l] + rank) << (LUTB - l)); ljl[pos] = (uint8_t)l; }
     }
     __syncthreads();
-    if (T.bad) return;
-    // warp-cooperative table fill: warp w takes symbols w, w+8, ...
-    for (uint32_t s = wid; s < 256; s += DT / 32) {
-        uint32_t ls = T.len[s];
-        if (ls == 0 || ls > LUTB) continue;
-        uint32_t rank = 0;   // recompute code = first + rank via sorted position
-        // position of s inside its length class
-        // (sorted[] is ordered, so binary search is possible; a linear warp vote is simpler)
-        uint32_t cnt = T.count[ls], base_o = T.offs[ls];
-        for (uint32_t j = lane; j < cnt; j += 32) if (T.sorted[base_o + j] == s) rank = j + 1;
-        rank = __reduce_max_sync(0xffffffffu, rank) - 1;
-        uint32_t code = T.first[ls] + rank;
-        uint32_t span = 1u << (LUTB - ls), b = code << (LUTB - ls);
-        uint16_t e = (uint16_t)(s | (ls << 8));
-        for (uint32_t x = lane; x < span; x += 32) T.lut[b + x] = e;
+    // single-symbol table: thread t fills entries [16t, 16t+16)
+    const uint32_t n12 = A.offs[LUTB + 1];        // symbols with length <= LUTB, sorted by code value
+    {
+        const uint32_t x0 = t * 16;
+        uint32_t i = 0;
+        if (n12) {                                 // largest i with lj[i] <= x0 (lj[0] == 0)
+            uint32_t lo = 0, hi = n12;
+            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (lj[mid] <= x0) lo = mid; else hi = mid; }
+            i = lo;
+        }
+#pragma unroll 4
+        for (uint32_t x = x0; x < x0 + 16; ++x) {
+            uint16_t e = 0;
+            if (n12) {
+                while (i + 1 < n12 && lj[i + 1] <= x) ++i;
+                const uint32_t li = ljl[i], b = lj[i];
+                if (x >= b && x < b + (1u << (LUTB - li))) e = (uint16_t)(A.sorted[i] | (li << 8));
+            }
+            base[x] = e;
+        }
+    }
+    __syncthreads();
+    // multi-symbol tables
+    for (uint32_t x = t * 16; x < t * 16 + 16; ++x) {
+        const uint32_t e0 = base[x];
+        uint32_t we = 0, se = 0;
+        if (e0) {
+            const uint32_t l0 = e0 >> 8;
+            uint32_t syms = e0 & 0xFF, used = l0, n = 1, wtot = l0, wn = 1, cur = x, lprev = l0;
+            for (;;) {
+                cur = (cur << lprev) & (LUTN - 1);
+                const uint32_t e = base[cur];
+                if (!e) break;
+                const uint32_t le = e >> 8;
+                if (used + le > LUTB) break;
+                if (n < 3) { syms |= (e & 0xFF) << (8 * n); wtot = used + le; wn = n + 1; }
+                used += le; ++n; lprev = le;
+            }
+            we = syms | (wtot << 24) | (wn << 28);
+            se = l0 | (used << 4) | (n << 8);
+        }
+        if (WANT_W) wlut[x] = we;
+        if (WANT_S) slut[x] = (uint16_t)se;
     }
     __syncthreads();
 }
 
-// Bit reader over one chunk: 64-bit window, zero bits past the end of the chunk.
-struct BitWin {
-    const uint8_t* base;     // first byte of the chunk
-    uint32_t csize;          // bytes in the chunk
-    uint64_t win;            // upcoming bits, MSB first
-    int avail;               // valid bits in win
-    uint64_t next;           // next byte offset to fetch (multiple of 4 relative to `algn`)
-    int algn;                // base address & 3
-};
-
-__device__ __forceinline__ uint32_t fetch_word(const BitWin& r, int64_t boff) {
-    // 4 bytes at chunk byte offset boff (may be negative / past the end -> zeros), big-endian
-    if (boff >= 0 && boff + 4 <= (int64_t)r.csize) {
-        uint32_t w = *reinterpret_cast<const uint32_t*>(r.base + boff);   // aligned by construction
-        return bswap32(w);
-    }
-    uint32_t w = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int64_t b = boff + i;
-        uint32_t v = (b >= 0 && b < (int64_t)r.csize) ? r.base[b] : 0;
-        w = (w << 8) | v;
-    }
-    return w;
+// copy `bytes` (multiple of 16) from global to shared with all DT threads
+__device__ __forceinline__ void copy_g2s16(void* dst, const void* src, uint32_t bytes) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (uint32_t i = threadIdx.x; i < bytes / 16; i += DT) d[i] = s[i];
 }
 
-__device__ __forceinline__ void bw_seek(BitWin& r, uint64_t bitpos) {
-    // word-aligned (in address space) fetches: aligned byte offset = ((algn + bitpos/8) & ~3) - algn
-    int64_t byte = (int64_t)(bitpos >> 3);
-    int64_t a = ((byte + r.algn) & ~(int64_t)3) - r.algn;
-    uint32_t skip = (uint32_t)((byte - a) * 8 + (bitpos & 7));       // 0..31
-    uint64_t w0 = fetch_word(r, a), w1 = fetch_word(r, a + 4);
-    r.win = ((w0 << 32) | w1) << skip;
-    r.avail = 64 - (int)skip;
-    r.next = (uint64_t)(a + 8);
-}
-
-__device__ __forceinline__ void bw_refill(BitWin& r) {
-    if (r.avail <= 32) {
-        uint64_t w = fetch_word(r, (int64_t)r.next);
-        r.win |= w << (32 - r.avail);
-        r.avail += 32;
-        r.next += 4;
-    }
-}
-
-// Decode one codeword from the window.  Returns its length (>=1) and the symbol;
-// an unmatched pattern consumes 1 bit and returns sym = -1.
-__device__ __forceinline__ int decode_one(const DecTables& T, uint64_t win, int* sym) {
-    uint32_t e = T.lut[(uint32_t)(win >> (64 - LUTB))];
-    if (e) { *sym = e & 0xFF; return e >> 8; }
-    const uint32_t top = (uint32_t)(win >> 32);
-    for (int l = LUTB + 1; l <= T.maxlen; ++l) {
-        uint32_t c = top >> (32 - l);
-        uint32_t d = c - T.first[l];
-        if (c >= T.first[l] && d < T.count[l]) { *sym = T.sorted[T.offs[l] + d]; return l; }
-    }
-    *sym = -1;
-    return 1;
-}
-
-struct ChunkGeom {
-    uint64_t comp_off; uint32_t comp_size; uint32_t orig_size; uint64_t orig_off;
-    uint32_t nsub, nseq, sub_base, seq_base, cta_base, ncta;
-};
-
-// plan arrays (SoA, K+1 entries each where a total is needed)
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
 struct DecPlan {
-    uint32_t* nsub; uint32_t* sub_base; uint32_t* seq_base; uint32_t* cta_base; uint64_t* orig_off;
+    uint32_t* nsub; uint32_t* sub_base; uint32_t* seq_base; uint32_t* cta_base; uint32_t* tab_idx; uint64_t* orig_off;
 };
 
 __device__ __forceinline__ uint32_t ceil_div_u64(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
@@ -169,19 +181,20 @@ __device__ __forceinline__ uint32_t ceil_div_u64(uint64_t a, uint32_t b) { retur
 __global__ void __launch_bounds__(1024)
 dec_plan_kernel(const uint32_t* __restrict__ comp_size, const uint32_t* __restrict__ orig_size,
                 const uint64_t* __restrict__ orig_off_in, uint32_t K, DecPlan P) {
-    __shared__ uint64_t part[4][1024];
+    __shared__ uint64_t part[5][1024];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (K + 1023) / 1024;
     const uint32_t lo = min(K, t * per), hi = min(K, lo + per);
-    uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
     for (uint32_t i = lo; i < hi; ++i) {
-        uint32_t ns = orig_size[i] ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, HZ_SUB_BITS)) : 0;
+        uint32_t ns = orig_size[i] ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, DEC_SUB_BITS)) : 0;
         uint32_t nq = (ns + DT - 1) / DT;
-        s0 += ns; s1 += nq; s2 += (nq + HZ_SEQ_PER_CTA - 1) / HZ_SEQ_PER_CTA; s3 += orig_size[i];
+        s0 += ns; s1 += nq; s2 += (nq + DEC_SEQ_PER_CTA - 1) / DEC_SEQ_PER_CTA; s3 += orig_size[i];
+        s4 += nq > DEC_SEQ_PER_CTA;
     }
-    part[0][t] = s0; part[1][t] = s1; part[2][t] = s2; part[3][t] = s3;
+    part[0][t] = s0; part[1][t] = s1; part[2][t] = s2; part[3][t] = s3; part[4][t] = s4;
     __syncthreads();
-    if (t < 4) {
+    if (t < 5) {
         uint64_t a = 0;
         for (int j = 0; j < 1024; ++j) { uint64_t x = part[t][j]; part[t][j] = a; a += x; }
         if (t == 0) P.sub_base[K] = (uint32_t)a;
@@ -190,13 +203,15 @@ dec_plan_kernel(const uint32_t* __restrict__ comp_size, const uint32_t* __restri
         if (t == 3) P.orig_off[K] = a;
     }
     __syncthreads();
-    s0 = part[0][t]; s1 = part[1][t]; s2 = part[2][t]; s3 = part[3][t];
+    s0 = part[0][t]; s1 = part[1][t]; s2 = part[2][t]; s3 = part[3][t]; s4 = part[4][t];
     for (uint32_t i = lo; i < hi; ++i) {
-        uint32_t ns = orig_size[i] ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, HZ_SUB_BITS)) : 0;
+        uint32_t ns = orig_size[i] ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, DEC_SUB_BITS)) : 0;
         uint32_t nq = (ns + DT - 1) / DT;
         P.nsub[i] = ns; P.sub_base[i] = (uint32_t)s0; P.seq_base[i] = (uint32_t)s1; P.cta_base[i] = (uint32_t)s2;
         P.orig_off[i] = orig_off_in ? orig_off_in[i] : s3;
-        s0 += ns; s1 += nq; s2 += (nq + HZ_SEQ_PER_CTA - 1) / HZ_SEQ_PER_CTA; s3 += orig_size[i];
+        P.tab_idx[i] = nq > DEC_SEQ_PER_CTA ? (uint32_t)s4 : DEC_NO_TABLE;
+        s0 += ns; s1 += nq; s2 += (nq + DEC_SEQ_PER_CTA - 1) / DEC_SEQ_PER_CTA; s3 += orig_size[i];
+        s4 += nq > DEC_SEQ_PER_CTA;
     }
 }
 
@@ -210,33 +225,159 @@ __device__ __forceinline__ uint32_t find_chunk(const uint32_t* __restrict__ cta_
     return lo;
 }
 
-// Decode subsequence `i` of a chunk starting at absolute bit `start` (>= nominal unless run-in):
-// counts the codewords that BEGIN in [max(start, nominal_i), nominal_{i+1}) and returns the exit
-// offset (first codeword boundary at or after nominal_{i+1}, relative to it).  If `entry` is
-// non-null the run-in phase is performed first and *entry receives the crossing offset.
-__device__ __forceinline__ void scan_subseq(const DecTables& T, BitWin& r, uint64_t start, uint64_t nominal,
-                                            uint32_t* entry, uint32_t* count, uint32_t* exitv) {
-    uint64_t pos = start;
-    bw_seek(r, pos);
-    int sym;
-    if (entry) {
-        while (pos < nominal) {
-            bw_refill(r);
-            int l = decode_one(T, r.win, &sym);
-            r.win <<= l; r.avail -= l; pos += l;
+// ---------------------------------------------------------------------------------------------
+// tables kernel: one CTA per chunk; chunks handled by a single CTA build their tables in place
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DT)
+dec_tables_kernel(const uint8_t* __restrict__ len_tab, DecPlan P, uint8_t* __restrict__ tables, int* status) {
+    __shared__ __align__(16) uint32_t wlut[LUTN];
+    __shared__ __align__(16) uint16_t slut[LUTN];
+    __shared__ __align__(16) uint8_t scratch[LUTN * 2 + 768 + 8 * 34 * 4];
+    __shared__ __align__(16) uint8_t aux_raw[1024];
+    const uint32_t k = blockIdx.x;
+    const uint32_t ti = P.tab_idx[k];
+    if (ti == DEC_NO_TABLE) return;
+    DecAux& A = *reinterpret_cast<DecAux*>(aux_raw);
+    build_tables<true, true>(A, wlut, slut, scratch, len_tab + (size_t)k * 256);
+    if (A.bad && threadIdx.x == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS);
+    uint8_t* dst = tables + (size_t)ti * DEC_TABLE_BYTES;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < LUTN * 4 / 16; i += DT) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<uint4*>(wlut)[i];
+    for (uint32_t i = threadIdx.x; i < LUTN * 2 / 16; i += DT) reinterpret_cast<uint4*>(dst + LUTN * 4)[i] = reinterpret_cast<uint4*>(slut)[i];
+    for (uint32_t i = threadIdx.x; i < 1024 / 16; i += DT) reinterpret_cast<uint4*>(dst + LUTN * 6)[i] = reinterpret_cast<uint4*>(aux_raw)[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// staging of one sequence's compressed bytes: 1-D TMA bulk copy + mbarrier
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+struct StageGeom {
+    uint64_t a0;         // 16-byte aligned global address of stage byte 0
+    int64_t vlo, vhi;    // stage-relative byte range that belongs to the chunk
+    int64_t tlo, thi;    // stage-relative byte range delivered by the bulk copy
+    uint32_t bit0;       // stage-relative bit index of the sequence's first bit
+};
+
+__device__ __forceinline__ StageGeom stage_geom(const uint8_t* comp, uint64_t comp_bytes, uint64_t chunk_off,
+                                                uint32_t chunk_size, uint32_t sq) {
+    StageGeom g;
+    const uint64_t cb = reinterpret_cast<uint64_t>(comp) + chunk_off;
+    const uint64_t seq0 = cb + (uint64_t)sq * DEC_SEQ_BYTES;                 // address of the sequence's first byte
+    const uint64_t lo = seq0 - DEC_OVERLAP_BYTES;
+    g.a0 = lo & ~(uint64_t)15;
+    g.bit0 = (uint32_t)(seq0 - g.a0) * 8;
+    g.vlo = (int64_t)cb - (int64_t)g.a0;
+    g.vhi = g.vlo + chunk_size;
+    if (g.vlo < 0) g.vlo = 0;
+    if (g.vhi > DEC_STAGE_BYTES) g.vhi = DEC_STAGE_BYTES;
+    if (g.vhi < g.vlo) g.vhi = g.vlo;
+    const uint64_t blo = (reinterpret_cast<uint64_t>(comp) + 15) & ~(uint64_t)15;
+    const uint64_t bhi = (reinterpret_cast<uint64_t>(comp) + comp_bytes) & ~(uint64_t)15;
+    uint64_t tl = g.a0 > blo ? g.a0 : blo;
+    uint64_t th = g.a0 + DEC_STAGE_BYTES < bhi ? g.a0 + DEC_STAGE_BYTES : bhi;
+    if (th < tl) th = tl;
+    g.tlo = (int64_t)(tl - g.a0); g.thi = (int64_t)(th - g.a0);
+    return g;
+}
+
+// issued by ONE thread
+__device__ __forceinline__ void stage_issue(uint8_t* stage, uint64_t* bar, const StageGeom& g) {
+    const uint32_t bytes = (uint32_t)(g.thi - g.tlo);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (bytes) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(stage + g.tlo)), "l"(g.a0 + (uint64_t)g.tlo), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    }
+}
+
+// after the bulk copy landed: bytes outside the chunk read as zero (TableBasedHuffmanDecoder.java:204-208),
+// chunk bytes the 16-byte aligned copy could not deliver are fetched one by one.  All DT threads.
+__device__ __forceinline__ void stage_fixup(uint8_t* stage, const StageGeom& g) {
+    const int64_t glo = g.vlo > g.tlo ? g.vlo : g.tlo, ghi = g.vhi < g.thi ? g.vhi : g.thi;   // good bytes
+    if (glo == 0 && ghi == DEC_STAGE_BYTES) return;
+    for (int64_t u = threadIdx.x; u < DEC_STAGE_BYTES / 16; u += DT) {
+        const int64_t b0 = u * 16;
+        if (b0 >= glo && b0 + 16 <= ghi) continue;
+        for (int64_t b = b0; b < b0 + 16; ++b) {
+            if (b >= glo && b < ghi) continue;
+            uint8_t v = 0;
+            if (b >= g.vlo && b < g.vhi) v = *reinterpret_cast<const uint8_t*>(g.a0 + (uint64_t)b);
+            stage[b] = v;
         }
-        *entry = (uint32_t)(pos - nominal);
     }
-    const uint64_t end = nominal + HZ_SUB_BITS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bit reader over the staged bytes: (hi, lo) = 64 upcoming stream bits, sh = consumed bits of hi
+// ---------------------------------------------------------------------------------------------
+struct BitRd {
+    const uint32_t* w;     // stage words (raw little-endian loads of the big-endian stream)
+    uint32_t hi, lo, sh, next;
+};
+__device__ __forceinline__ uint32_t rd_word(const uint32_t* w, uint32_t i) {
+    return i < DEC_STAGE_WORDS ? bswap32(w[i]) : 0u;
+}
+__device__ __forceinline__ void rd_seek(BitRd& r, uint32_t bitpos) {
+    const uint32_t i = bitpos >> 5;
+    r.sh = bitpos & 31;
+    r.hi = rd_word(r.w, i); r.lo = rd_word(r.w, i + 1); r.next = i + 2;
+}
+__device__ __forceinline__ uint32_t rd_peek32(const BitRd& r) { return __funnelshift_l(r.lo, r.hi, r.sh); }
+__device__ __forceinline__ void rd_skip(BitRd& r, uint32_t l) {
+    r.sh += l;
+    if (r.sh >= 32) { r.sh -= 32; r.hi = r.lo; r.lo = rd_word(r.w, r.next); ++r.next; }
+}
+
+// canonical first-code walk for codes longer than LUTB bits; returns the length, 0 if no code matches
+__device__ __forceinline__ uint32_t slow_code(const DecAux& A, uint32_t v, int* sym) {
+    for (int l = LUTB + 1; l <= A.maxlen; ++l) {
+        const uint32_t c = v >> (32 - l);
+        const uint32_t d = c - A.first[l];
+        if (c >= A.first[l] && d < A.count[l]) { *sym = A.sorted[A.offs[l] + d]; return (uint32_t)l; }
+    }
+    *sym = -1;
+    return 0;
+}
+
+// Advance from `pos` to the first codeword boundary >= limit; returns the number of codewords
+// that began before `limit`.  Unmatched patterns consume one bit.
+__device__ __forceinline__ uint32_t advance(const DecAux& A, const uint16_t* __restrict__ slut, BitRd& r,
+                                            uint32_t& pos, uint32_t limit) {
     uint32_t cnt = 0;
-    while (pos < end) {
-        bw_refill(r);
-        int l = decode_one(T, r.win, &sym);
-        r.win <<= l; r.avail -= l; pos += l;
-        ++cnt;
+    while (pos + LUTB <= limit) {
+        const uint32_t v = rd_peek32(r);
+        const uint32_t e = slut[v >> (32 - LUTB)];
+        uint32_t l, n;
+        if (e & 15) { l = (e >> 4) & 15; n = e >> 8; }
+        else { int s; l = slow_code(A, v, &s); n = 1; if (!l) l = 1; }
+        rd_skip(r, l); pos += l; cnt += n;
     }
-    *count = cnt;
-    *exitv = (uint32_t)(pos - end);
+    while (pos < limit) {
+        const uint32_t v = rd_peek32(r);
+        uint32_t l = slut[v >> (32 - LUTB)] & 15;
+        if (!l) { int s; l = slow_code(A, v, &s); if (!l) l = 1; }
+        rd_skip(r, l); pos += l; ++cnt;
+    }
+    return cnt;
 }
 
 // record layout: entry (8) | exit (8) | count (16)
@@ -244,118 +385,198 @@ __device__ __forceinline__ uint32_t pack_rec(uint32_t entry, uint32_t exitv, uin
     return entry | (exitv << 8) | (count << 16);
 }
 
+struct SyncSmem {
+    __align__(16) uint8_t stage[2][DEC_STAGE_BYTES];
+    __align__(16) uint16_t slut[LUTN];
+    __align__(16) uint8_t aux[1024];
+    __align__(8) uint64_t bar[2];
+    uint32_t s_exit[DT];
+    uint32_t s_red[DT / 32];
+    uint32_t s_k;
+};
+
 __global__ void __launch_bounds__(DT)
-dec_sync_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ comp_off,
+dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uint64_t* __restrict__ comp_off,
                 const uint32_t* __restrict__ comp_size, const uint8_t* __restrict__ len_tab,
-                uint32_t K, DecPlan P, uint32_t* __restrict__ rec, uint32_t* __restrict__ seqcnt, int* status) {
-    __shared__ DecTables T;
-    __shared__ uint32_t s_exit[DT];
-    __shared__ uint32_t s_red[DT / 32];
-    __shared__ uint32_t s_k;
+                uint32_t K, DecPlan P, const uint8_t* __restrict__ tables,
+                uint32_t* __restrict__ rec, uint32_t* __restrict__ seqcnt, int* status) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    SyncSmem& S = *reinterpret_cast<SyncSmem*>(smem_raw);
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
     if (blockIdx.x >= P.cta_base[K]) return;
-    if (t == 0) s_k = find_chunk(P.cta_base, K, blockIdx.x);
+    if (t == 0) {
+        S.s_k = find_chunk(P.cta_base, K, blockIdx.x);
+        mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    const uint32_t k = s_k;
-    build_tables(T, len_tab + (size_t)k * 256);
-    if (T.bad) { if (t == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS); return; }
+    const uint32_t k = S.s_k;
+    DecAux& A = *reinterpret_cast<DecAux*>(S.aux);
+    const uint32_t ti = P.tab_idx[k];
+    if (ti == DEC_NO_TABLE) {
+        build_tables<false, true>(A, nullptr, S.slut, S.stage[0], len_tab + (size_t)k * 256);
+    } else {
+        const uint8_t* tb = tables + (size_t)ti * DEC_TABLE_BYTES;
+        copy_g2s16(S.slut, tb + LUTN * 4, LUTN * 2);
+        copy_g2s16(S.aux, tb + LUTN * 6, 1024);
+    }
+    __syncthreads();
+    if (A.bad) { if (t == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS); return; }
 
-    BitWin r;
-    r.base = comp + comp_off[k];
-    r.csize = comp_size[k];
-    r.algn = (int)(reinterpret_cast<uintptr_t>(r.base) & 3);
+    const uint64_t coff = comp_off[k];
+    const uint32_t csize = comp_size[k];
     const uint32_t nsub = P.nsub[k];
     const uint32_t nseq = (nsub + DT - 1) / DT;
     const uint32_t cta_in_chunk = blockIdx.x - P.cta_base[k];
-    const uint32_t U = (uint32_t)T.uniform;
+    const uint32_t sq0 = cta_in_chunk * DEC_SEQ_PER_CTA;
+    const uint32_t nq = min((uint32_t)DEC_SEQ_PER_CTA, nseq - sq0);
+    const uint32_t U = (uint32_t)A.uniform;
 
+    if (t == 0) stage_issue(S.stage[0], &S.bar[0], stage_geom(comp, comp_bytes, coff, csize, sq0));
     uint32_t carry_exit = 0;         // exit of the previous sequence's last subsequence (q > 0)
-    for (uint32_t q = 0; q < HZ_SEQ_PER_CTA; ++q) {
-        const uint32_t sq = cta_in_chunk * HZ_SEQ_PER_CTA + q;
-        if (sq >= nseq) break;
+    for (uint32_t q = 0; q < nq; ++q) {
+        const uint32_t sq = sq0 + q;
+        const uint32_t b = q & 1;
+        if (t == 0 && q + 1 < nq)
+            stage_issue(S.stage[b ^ 1], &S.bar[b ^ 1], stage_geom(comp, comp_bytes, coff, csize, sq + 1));
+        const StageGeom g = stage_geom(comp, comp_bytes, coff, csize, sq);
+        mbar_wait(&S.bar[b], (q >> 1) & 1);
+        stage_fixup(S.stage[b], g);
+        __syncthreads();
+
+        BitRd r; r.w = reinterpret_cast<const uint32_t*>(S.stage[b]);
         const uint32_t i = sq * DT + t;
         const bool active = i < nsub;
-        const uint64_t nominal = (uint64_t)i * HZ_SUB_BITS;
+        const uint32_t nominal = g.bit0 + t * DEC_SUB_BITS;       // stage-relative
+        const uint32_t end = nominal + DEC_SUB_BITS;
         uint32_t entry = 0, count = 0, exitv = 0;
         if (active) {
-            if (U) {
-                // equal-length code: boundaries are the multiples of U
-                entry = (uint32_t)((U - nominal % U) % U);
-                scan_subseq(T, r, nominal + entry, nominal, nullptr, &count, &exitv);
+            uint32_t pos;
+            if (U) {                     // equal-length code: boundaries are the multiples of U
+                const uint64_t nomc = (uint64_t)i * DEC_SUB_BITS;
+                entry = (uint32_t)((U - nomc % U) % U);
+                pos = nominal + entry;
+                rd_seek(r, pos);
             } else if (i == 0) {
-                scan_subseq(T, r, 0, 0, nullptr, &count, &exitv);
+                pos = nominal; rd_seek(r, pos);
             } else if (t == 0 && q > 0) {
-                entry = carry_exit;
-                scan_subseq(T, r, nominal + entry, nominal, nullptr, &count, &exitv);
+                entry = carry_exit; pos = nominal + entry; rd_seek(r, pos);
             } else {
-                uint64_t start = nominal > HZ_OVERLAP_BITS ? nominal - HZ_OVERLAP_BITS : 0;
-                scan_subseq(T, r, start, nominal, &entry, &count, &exitv);
+                pos = nominal - DEC_OVERLAP_BITS; rd_seek(r, pos);
+                advance(A, S.slut, r, pos, nominal);
+                entry = pos - nominal;
             }
+            count = advance(A, S.slut, r, pos, end);
+            exitv = pos - end;
         }
-        s_exit[t] = exitv;
+        S.s_exit[t] = exitv;
         __syncthreads();
         // repair mismatches inside the sequence until the chain is consistent
         if (!U) {
             for (;;) {
                 bool fix = false;
                 uint32_t want = 0;
-                if (active && t > 0) { want = s_exit[t - 1]; fix = want != entry; }
+                if (active && t > 0) { want = S.s_exit[t - 1]; fix = want != entry; }
                 if (!__syncthreads_or(fix)) break;
                 if (fix) {
                     entry = want;
-                    scan_subseq(T, r, nominal + entry, nominal, nullptr, &count, &exitv);
-                    s_exit[t] = exitv;
+                    uint32_t pos = nominal + entry;
+                    rd_seek(r, pos);
+                    count = advance(A, S.slut, r, pos, end);
+                    exitv = pos - end;
+                    S.s_exit[t] = exitv;
                 }
                 __syncthreads();
             }
         }
         if (active) rec[P.sub_base[k] + i] = pack_rec(entry, exitv, count);
-        // symbols of this sequence
         uint32_t c = active ? count : 0;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-        if (lane == 0) s_red[wid] = c;
+        if (lane == 0) S.s_red[wid] = c;
         __syncthreads();
         if (t == 0) {
             uint32_t a = 0;
-            for (int w = 0; w < DT / 32; ++w) a += s_red[w];
+            for (int w = 0; w < DT / 32; ++w) a += S.s_red[w];
             seqcnt[P.seq_base[k] + sq] = a;
         }
-        carry_exit = s_exit[DT - 1];
+        carry_exit = S.s_exit[DT - 1];
         __syncthreads();
     }
 }
 
-// One CTA per chunk: repair CTA boundaries, then turn per-sequence symbol counts into offsets.
+// ---------------------------------------------------------------------------------------------
+// fix kernel: CTA boundaries + scan of sequence counts.  Reads the stream from global memory.
+// ---------------------------------------------------------------------------------------------
+struct GRd {                  // bit reader over global memory, zero bits outside the chunk
+    const uint8_t* base; uint32_t csize; uint32_t hi, lo, sh; int64_t next;
+};
+__device__ __forceinline__ uint32_t g_word(const GRd& r, int64_t boff) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t b = boff + j;
+        const uint32_t v = (b >= 0 && b < (int64_t)r.csize) ? r.base[b] : 0;
+        w = (w << 8) | v;
+    }
+    return w;
+}
+__device__ __forceinline__ void g_seek(GRd& r, uint64_t bitpos) {
+    const int64_t b = (int64_t)(bitpos >> 5) * 4;
+    r.sh = (uint32_t)(bitpos & 31);
+    r.hi = g_word(r, b); r.lo = g_word(r, b + 4); r.next = b + 8;
+}
+__device__ __forceinline__ void g_skip(GRd& r, uint32_t l) {
+    r.sh += l;
+    if (r.sh >= 32) { r.sh -= 32; r.hi = r.lo; r.lo = g_word(r, r.next); r.next += 4; }
+}
+// counts the codewords that begin in [start, nominal + SUB_BITS) (start >= nominal); exit offset
+__device__ __forceinline__ void g_scan(const DecAux& A, const uint16_t* __restrict__ slut, GRd& r, uint64_t start,
+                                       uint64_t nominal, uint32_t* count, uint32_t* exitv) {
+    uint64_t pos = start;
+    const uint64_t end = nominal + DEC_SUB_BITS;
+    g_seek(r, pos);
+    uint32_t cnt = 0;
+    while (pos < end) {
+        const uint32_t v = __funnelshift_l(r.lo, r.hi, r.sh);
+        uint32_t l = slut[v >> (32 - LUTB)] & 15;
+        if (!l) { int s; l = slow_code(A, v, &s); if (!l) l = 1; }
+        g_skip(r, l); pos += l; ++cnt;
+    }
+    *count = cnt; *exitv = (uint32_t)(pos - end);
+}
+
 __global__ void __launch_bounds__(DT)
 dec_fix_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ comp_off,
-               const uint32_t* __restrict__ comp_size, const uint8_t* __restrict__ len_tab,
-               DecPlan P, uint32_t* __restrict__ rec, uint32_t* __restrict__ seqcnt, int* status) {
-    __shared__ DecTables T;
+               const uint32_t* __restrict__ comp_size, DecPlan P, const uint8_t* __restrict__ tables,
+               uint32_t* __restrict__ rec, uint32_t* __restrict__ seqcnt, int* status) {
+    __shared__ __align__(16) uint16_t slut[LUTN];
+    __shared__ __align__(16) uint8_t aux_raw[1024];
     __shared__ uint32_t s_warp[DT / 32 + 1];
     const uint32_t k = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const uint32_t nsub = P.nsub[k];
     if (nsub == 0) return;
     const uint32_t nseq = (nsub + DT - 1) / DT;
-    const uint32_t ncta = (nseq + HZ_SEQ_PER_CTA - 1) / HZ_SEQ_PER_CTA;
+    const uint32_t ncta = (nseq + DEC_SEQ_PER_CTA - 1) / DEC_SEQ_PER_CTA;
     uint32_t* R = rec + P.sub_base[k];
     uint32_t* SC = seqcnt + P.seq_base[k];
-    const uint32_t SUBS_PER_CTA = DT * HZ_SEQ_PER_CTA;
 
     if (ncta > 1) {
-        // quick check first: any boundary mismatch at all?
         bool any = false;
         for (uint32_t b = 1 + t; b < ncta; b += DT) {
-            uint32_t i = b * SUBS_PER_CTA;
+            const uint32_t i = b * DEC_SUBS_PER_CTA;
             any |= ((R[i - 1] >> 8) & 0xFF) != (R[i] & 0xFF);
         }
         if (__syncthreads_or(any)) {
-            build_tables(T, len_tab + (size_t)k * 256);
-            if (T.bad) return;
-            BitWin r;
+            const uint8_t* tb = tables + (size_t)P.tab_idx[k] * DEC_TABLE_BYTES;
+            copy_g2s16(slut, tb + LUTN * 4, LUTN * 2);
+            copy_g2s16(aux_raw, tb + LUTN * 6, 1024);
+            __syncthreads();
+            const DecAux& A = *reinterpret_cast<const DecAux*>(aux_raw);
+            if (A.bad) return;
+            GRd r;
             r.base = comp + comp_off[k];
             r.csize = comp_size[k];
-            r.algn = (int)(reinterpret_cast<uintptr_t>(r.base) & 3);
             for (;;) {
                 bool changed = false;
                 for (uint32_t b0 = 1; b0 < ncta; b0 += DT) {
@@ -363,18 +584,18 @@ dec_fix_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ co
                     uint32_t want = 0, i = 0;
                     bool walk = false;
                     if (b < ncta) {
-                        i = b * SUBS_PER_CTA;
+                        i = b * DEC_SUBS_PER_CTA;
                         want = (R[i - 1] >> 8) & 0xFF;
                         walk = want != (R[i] & 0xFF);
                     }
                     __syncthreads();           // all reads of neighbours' exits before any update
                     if (walk) {
-                        const uint32_t iend = min(nsub, i + SUBS_PER_CTA);
+                        const uint32_t iend = min(nsub, i + DEC_SUBS_PER_CTA);
                         uint32_t entry = want;
                         for (; i < iend; ++i) {
-                            const uint64_t nominal = (uint64_t)i * HZ_SUB_BITS;
+                            const uint64_t nominal = (uint64_t)i * DEC_SUB_BITS;
                             uint32_t count, exitv;
-                            scan_subseq(T, r, nominal + entry, nominal, nullptr, &count, &exitv);
+                            g_scan(A, slut, r, nominal + entry, nominal, &count, &exitv);
                             const uint32_t old = R[i];
                             R[i] = pack_rec(entry, exitv, count);
                             atomicAdd(&SC[i / DT], count - (old >> 16));
@@ -415,109 +636,226 @@ dec_fix_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ co
     (void)status;
 }
 
+// ---------------------------------------------------------------------------------------------
+// write kernel
+// ---------------------------------------------------------------------------------------------
+struct WriteSmem {
+    __align__(16) uint8_t stage[DEC_STAGE_BYTES];
+    __align__(16) uint32_t wlut[LUTN];
+    __align__(16) uint8_t aux[1024];
+    __align__(16) uint8_t win[DT / 32][DEC_WIN_BYTES];
+    __align__(8) uint64_t bar;
+    uint32_t s_warp[DT / 32 + 1];
+    uint32_t s_k;
+};
+
 __global__ void __launch_bounds__(DT)
-dec_write_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ comp_off,
+dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uint64_t* __restrict__ comp_off,
                  const uint32_t* __restrict__ comp_size, const uint32_t* __restrict__ orig_size,
-                 const uint8_t* __restrict__ len_tab, uint32_t K, DecPlan P,
+                 const uint8_t* __restrict__ len_tab, uint32_t K, DecPlan P, const uint8_t* __restrict__ tables,
                  const uint32_t* __restrict__ rec, const uint32_t* __restrict__ seqoff,
                  uint8_t* __restrict__ out, uint64_t out_cap, int* status) {
-    __shared__ DecTables T;
-    __shared__ uint32_t s_warp[DT / 32 + 1];
-    __shared__ uint32_t s_k;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    WriteSmem& S = *reinterpret_cast<WriteSmem*>(smem_raw);
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
     if (blockIdx.x >= P.cta_base[K]) return;
-    if (t == 0) s_k = find_chunk(P.cta_base, K, blockIdx.x);
+    if (t == 0) {
+        S.s_k = find_chunk(P.cta_base, K, blockIdx.x);
+        mbar_init(&S.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    const uint32_t k = s_k;
+    const uint32_t k = S.s_k;
     const uint32_t osize = orig_size[k];
     const uint64_t ooff = P.orig_off[k];
     if (ooff + osize > out_cap) { if (t == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
-    build_tables(T, len_tab + (size_t)k * 256);
-    if (T.bad) { if (t == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS); return; }
-    BitWin r;
-    r.base = comp + comp_off[k];
-    r.csize = comp_size[k];
-    r.algn = (int)(reinterpret_cast<uintptr_t>(r.base) & 3);
+    DecAux& A = *reinterpret_cast<DecAux*>(S.aux);
+    const uint32_t ti = P.tab_idx[k];
+    if (ti == DEC_NO_TABLE) {
+        build_tables<true, false>(A, S.wlut, nullptr, S.stage, len_tab + (size_t)k * 256);
+    } else {
+        const uint8_t* tb = tables + (size_t)ti * DEC_TABLE_BYTES;
+        copy_g2s16(S.wlut, tb, LUTN * 4);
+        copy_g2s16(S.aux, tb + LUTN * 6, 1024);
+    }
+    __syncthreads();
+    if (A.bad) { if (t == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS); return; }
+
+    const uint64_t coff = comp_off[k];
+    const uint32_t csize = comp_size[k];
     const uint32_t nsub = P.nsub[k];
     const uint32_t nseq = (nsub + DT - 1) / DT;
     const uint32_t cta_in_chunk = blockIdx.x - P.cta_base[k];
-    uint8_t* o = out + ooff;
+    const uint32_t sq0 = cta_in_chunk * DEC_SEQ_PER_CTA;
+    const uint32_t nq = min((uint32_t)DEC_SEQ_PER_CTA, nseq - sq0);
+    const uint64_t gout = reinterpret_cast<uint64_t>(out) + ooff;      // address of the chunk's first output byte
+    uint8_t* win = S.win[wid];
+    bool err = false;
 
-    for (uint32_t q = 0; q < HZ_SEQ_PER_CTA; ++q) {
-        const uint32_t sq = cta_in_chunk * HZ_SEQ_PER_CTA + q;
-        if (sq >= nseq) break;
+    for (uint32_t q = 0; q < nq; ++q) {
+        const uint32_t sq = sq0 + q;
+        const StageGeom g = stage_geom(comp, comp_bytes, coff, csize, sq);
+        if (t == 0) stage_issue(S.stage, &S.bar, g);
+        // while the copy is in flight: output offsets of this sequence
         const uint32_t i = sq * DT + t;
         const bool active = i < nsub;
-        uint32_t rv = active ? rec[P.sub_base[k] + i] : 0;
-        uint32_t count = rv >> 16;
-        // exclusive scan of counts inside the sequence
+        const uint32_t rv = active ? rec[P.sub_base[k] + i] : 0;
+        const uint32_t count = rv >> 16;
         uint32_t inc = count;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += x;
         }
-        if (lane == 31) s_warp[wid] = inc;
+        if (lane == 31) S.s_warp[wid] = inc;
         __syncthreads();
         if (t == 0) {
             uint32_t a = 0;
-            for (int w = 0; w < DT / 32; ++w) { uint32_t x = s_warp[w]; s_warp[w] = a; a += x; }
+            for (int w = 0; w < DT / 32; ++w) { uint32_t x = S.s_warp[w]; S.s_warp[w] = a; a += x; }
         }
         __syncthreads();
-        uint32_t obase = seqoff[P.seq_base[k] + sq] + s_warp[wid] + inc - count;
-        __syncthreads();
-        if (!active) continue;
-        // the last subsequence of the chunk runs until orig_size symbols exist (bits past the end
-        // of the chunk read as zero, TableBasedHuffmanDecoder.java:204-208)
-        uint32_t todo = count;
-        if (i == nsub - 1) todo = osize > obase ? osize - obase : 0;
-        else if (obase >= osize) todo = 0;
-        else if (obase + todo > osize) todo = osize - obase;
-        if (todo == 0) continue;
-        uint64_t pos = (uint64_t)i * HZ_SUB_BITS + (rv & 0xFF);
-        bw_seek(r, pos);
-        uint8_t* dst = o + obase;
-        bool err = false;
-        for (uint32_t j = 0; j < todo; ++j) {
-            bw_refill(r);
-            int sym;
-            int l = decode_one(T, r.win, &sym);
-            r.win <<= l; r.avail -= l;
-            if (sym < 0) { err = true; sym = 0; }
-            dst[j] = (uint8_t)sym;
+        const uint32_t obase = seqoff[P.seq_base[k] + sq] + S.s_warp[wid] + inc - count;
+        // the last subsequence of the chunk runs until orig_size symbols exist
+        uint32_t todo = 0;
+        if (active) {
+            if (i == nsub - 1) {
+                todo = osize > obase ? osize - obase : 0;
+                if (todo > DEC_SUB_BITS + 32) { err = true; todo = 0; }      // stream holds fewer symbols than orig_size
+            } else if (obase < osize) {
+                todo = obase + count > osize ? osize - obase : count;
+            }
         }
-        if (err) hz_set_status(status, HZ_ERR_DECODE);
+        mbar_wait(&S.bar, q & 1);
+        stage_fixup(S.stage, g);
+        __syncthreads();
+
+        // ---- per-warp windowed decode -------------------------------------------------------
+        BitRd r; r.w = reinterpret_cast<const uint32_t*>(S.stage);
+        rd_seek(r, g.bit0 + t * DEC_SUB_BITS + (rv & 0xFF));
+        uint64_t my_addr = gout + obase;                            // address of this lane's next symbol
+        uint64_t ws = todo ? my_addr : ~0ull, we = todo ? my_addr + todo : 0ull;   // the warp's output range
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const uint64_t a = __shfl_xor_sync(0xffffffffu, ws, d), b = __shfl_xor_sync(0xffffffffu, we, d);
+            ws = a < ws ? a : ws; we = b > we ? b : we;
+        }
+        uint64_t acc = 0;
+        uint32_t fill = 0;
+        bool first = true;
+        uint32_t head = 0;
+        for (uint64_t wa = ws & ~(uint64_t)15; wa < we; wa += DEC_WIN_BYTES) {
+            uint32_t n = 0;
+            if (todo && my_addr < wa + DEC_WIN_BYTES) {
+                const uint64_t room = wa + DEC_WIN_BYTES - my_addr;
+                n = todo < room ? todo : (uint32_t)room;
+            }
+            if (n) {
+                uint32_t woff = (uint32_t)(my_addr - wa);           // byte offset of the next symbol in the window
+                if (first) { head = woff & 3; fill = head; }
+                uint32_t* wp = reinterpret_cast<uint32_t*>(win + (woff & ~3u));
+                uint32_t left = n;
+                while (left) {
+                    const uint32_t v = rd_peek32(r);
+                    uint32_t e = S.wlut[v >> (32 - LUTB)];
+                    uint32_t c = e >> 28, l, syms;
+                    if (c) {
+                        l = (e >> 24) & 15; syms = e & 0xFFFFFF;
+                        if (c > left) {          // window / subsequence ends inside this entry: take `left` symbols
+                            c = left;
+                            l = A.len[syms & 0xFF];
+                            if (c == 2) l += A.len[(syms >> 8) & 0xFF];
+                            syms &= 0xFFFFFFu >> (8 * (3 - c));
+                        }
+                    } else {
+                        int s; l = slow_code(A, v, &s);
+                        if (!l) { l = 1; s = 0; err = true; }
+                        c = 1; syms = (uint32_t)s;
+                    }
+                    rd_skip(r, l);
+                    left -= c;
+                    acc |= (uint64_t)syms << (8 * fill);
+                    fill += c;
+                    if (fill >= 4) {
+                        if (first) {
+                            uint8_t* bp = reinterpret_cast<uint8_t*>(wp);
+                            for (uint32_t j = head; j < 4; ++j) bp[j] = (uint8_t)(acc >> (8 * j));
+                            first = false;
+                        } else {
+                            *wp = (uint32_t)acc;
+                        }
+                        ++wp; acc >>= 32; fill -= 4;
+                    }
+                }
+                todo -= n; my_addr += n;
+                if (todo == 0 && fill) {                             // tail bytes of this lane
+                    uint8_t* bp = reinterpret_cast<uint8_t*>(wp);
+                    for (uint32_t j = first ? head : 0; j < fill; ++j) bp[j] = (uint8_t)(acc >> (8 * j));
+                    fill = 0;
+                }
+            }
+            __syncwarp();
+            // copy the window out: aligned 16-byte units, bytes at the ragged ends
+            const uint64_t lo = ws > wa ? ws : wa;
+            const uint64_t hi = we < wa + DEC_WIN_BYTES ? we : wa + DEC_WIN_BYTES;
+            const uint32_t u0 = (uint32_t)(lo - wa) >> 4, u1 = (uint32_t)(hi - wa + 15) >> 4;
+            for (uint32_t u = u0 + lane; u < u1; u += 32) {
+                const uint64_t ua = wa + (uint64_t)u * 16;
+                if (ua >= lo && ua + 16 <= hi) {
+                    *reinterpret_cast<uint4*>(ua) = *reinterpret_cast<const uint4*>(win + u * 16);
+                } else {
+                    for (uint32_t bb = 0; bb < 16; ++bb)
+                        if (ua + bb >= lo && ua + bb < hi) *reinterpret_cast<uint8_t*>(ua + bb) = win[u * 16 + bb];
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();            // stage is re-filled by the next iteration
     }
+    if (err) hz_set_status(status, HZ_ERR_DECODE);
 }
 
+// ---------------------------------------------------------------------------------------------
 int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const uint64_t* d_comp_off,
                const uint32_t* d_comp_size, const uint32_t* d_orig_size, const uint64_t* d_orig_off,
                const uint8_t* d_len, uint32_t K, uint8_t* d_out, uint64_t out_cap) {
     if (K == 0) return HZ_OK;
     // plan arrays
-    HZ_TRY(hz_reserve(ctx, &ctx->dec_meta, ((size_t)K + 1) * (4 * sizeof(uint32_t) + sizeof(uint64_t)) + 64));
+    HZ_TRY(hz_reserve(ctx, &ctx->dec_meta, ((size_t)K + 1) * (5 * sizeof(uint32_t) + sizeof(uint64_t)) + 64));
     DecPlan P;
     uint8_t* m = (uint8_t*)ctx->dec_meta.p;
     P.orig_off = (uint64_t*)m; m += ((size_t)K + 1) * sizeof(uint64_t);
     P.nsub = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
     P.sub_base = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
     P.seq_base = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
-    P.cta_base = (uint32_t*)m;
+    P.cta_base = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
+    P.tab_idx = (uint32_t*)m;
     HZ_LAUNCH(ctx, "dec_plan", dec_plan_kernel, 1, 1024, 0, d_comp_size, d_orig_size, d_orig_off, K, P);
     // upper bounds (no host sync): every chunk has at most ceil(comp_size*8/SUB_BITS)+1 subsequences
-    const uint64_t max_sub = comp_bytes * 8 / HZ_SUB_BITS + 2ull * K + 2;
+    const uint64_t max_sub = comp_bytes * 8 / DEC_SUB_BITS + 2ull * K + 2;
     const uint64_t max_seq = max_sub / DT + K + 1;
-    const uint64_t max_cta = max_seq / HZ_SEQ_PER_CTA + K + 1;
+    const uint64_t max_cta = max_seq / DEC_SEQ_PER_CTA + K + 1;
+    uint64_t max_tab = comp_bytes / ((uint64_t)DEC_SEQ_PER_CTA * DEC_SEQ_BYTES) + 1;
+    if (max_tab > K) max_tab = K;
     if (max_cta > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "decode grid too large");
     HZ_TRY(hz_reserve(ctx, &ctx->dec_rec, max_sub * sizeof(uint32_t)));
     HZ_TRY(hz_reserve(ctx, &ctx->dec_seqcnt, max_seq * sizeof(uint32_t)));
+    HZ_TRY(hz_reserve(ctx, &ctx->dec_tables, max_tab * DEC_TABLE_BYTES));
     uint32_t* rec = (uint32_t*)ctx->dec_rec.p;
     uint32_t* seqcnt = (uint32_t*)ctx->dec_seqcnt.p;
-    HZ_LAUNCH(ctx, "dec_sync", dec_sync_kernel, (unsigned)max_cta, DT, 0,
-              d_comp, d_comp_off, d_comp_size, d_len, K, P, rec, seqcnt, ctx->d_status);
+    uint8_t* tables = (uint8_t*)ctx->dec_tables.p;
+    static bool attr_done = false;
+    if (!attr_done) {
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncSmem)));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WriteSmem)));
+        attr_done = true;
+    }
+    HZ_LAUNCH(ctx, "dec_tables", dec_tables_kernel, K, DT, 0, d_len, P, tables, ctx->d_status);
+    HZ_LAUNCH(ctx, "dec_sync", dec_sync_kernel, (unsigned)max_cta, DT, sizeof(SyncSmem),
+              d_comp, comp_bytes, d_comp_off, d_comp_size, d_len, K, P, tables, rec, seqcnt, ctx->d_status);
     HZ_LAUNCH(ctx, "dec_fix", dec_fix_kernel, K, DT, 0,
-              d_comp, d_comp_off, d_comp_size, d_len, P, rec, seqcnt, ctx->d_status);
-    HZ_LAUNCH(ctx, "dec_write", dec_write_kernel, (unsigned)max_cta, DT, 0,
-              d_comp, d_comp_off, d_comp_size, d_orig_size, d_len, K, P, rec, seqcnt, d_out, out_cap, ctx->d_status);
+              d_comp, d_comp_off, d_comp_size, P, tables, rec, seqcnt, ctx->d_status);
+    HZ_LAUNCH(ctx, "dec_write", dec_write_kernel, (unsigned)max_cta, DT, sizeof(WriteSmem),
+              d_comp, comp_bytes, d_comp_off, d_comp_size, d_orig_size, d_len, K, P, tables, rec, seqcnt, d_out, out_cap,
+              ctx->d_status);
     return HZ_OK;
 }

@@ -20,7 +20,8 @@ chunk = int(float(sys.argv[3]) * (1 << 20)) if len(sys.argv) > 3 else 16 << 20
 reps = int(os.environ.get("REPS", "5"))
 K = (n + chunk - 1) // chunk
 c = hz.Codec(0)
-c.set_stream(torch.cuda.current_stream().cuda_stream)
+_s = torch.cuda.Stream(); torch.cuda.set_stream(_s)
+c.set_stream(_s.cuda_stream)
 src = torch.empty(n, dtype=torch.uint8, device="cuda")
 c.synth_fill(src.data_ptr(), n, 0, 0x5EED0001, datasets.zipf_qtable(H))
 comp = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
