@@ -27,10 +27,12 @@
 //                         with aligned 128-bit stores.
 //
 // Tables (LUTB = 12 bits of look-ahead):
-//   slut u16: l0 | ltot<<4 | n<<8    first codeword length, bits / codewords of all n (<=12)
-//             complete codewords inside the 12 bits (counting pass); 0 = first code longer than
-//             12 bits or no code at all -> canonical first-code walk.
-//   wlut u32: s0 | s1<<8 | s2<<16 | ltot<<24 | n<<28   up to three symbols per lookup.
+//   slut u16: ltot | n<<6 | l0<<10   bits / number of all n (<=12) complete codewords inside the
+//             12 bits and the first codeword's length (counting pass).  A prefix that starts a
+//             code longer than 12 bits has n = 1 and its length when every code under the prefix
+//             has the same length, else n = 0 with ltot = shortest, l0 = longest candidate.
+//   wlut u32: s0 | s1<<8 | s2<<16 | ltot<<24 | n<<28   up to three symbols per lookup;
+//             n = 0: long code, bits 0-5 shortest / bits 6-11 longest candidate length (0 = no code).
 // Codes whose used lengths are all equal never self-synchronise but need no synchronisation
 // either: entries are computed arithmetically.
 #include "hz_common.cuh"
@@ -50,14 +52,13 @@
 // staged bytes per sequence: 16 alignment slack + 16 overlap + sequence + 32 look-ahead
 #define DEC_STAGE_BYTES (16 + DEC_OVERLAP_BYTES + DEC_SEQ_BYTES + 32)
 #define DEC_STAGE_WORDS (DEC_STAGE_BYTES / 4)
-#define DEC_WIN_BYTES 4096                    // per-warp output window of the write kernel
+#define DEC_WIN_BYTES 9216                    // per-warp output window of the write kernel
 #define DEC_NO_TABLE 0xFFFFFFFFu
 #define DEC_TABLE_BYTES (LUTN * 4 + LUTN * 2 + 1024)
 
 struct __align__(16) DecAux {
-    uint32_t first[34];        // first canonical code of each length
-    uint32_t count[34];        // symbols per length
-    uint32_t offs[34];         // offset of each length in `sorted`
+    uint64_t lim[34];          // exclusive upper bound of the left-justified (32-bit) codes of each length
+    int32_t symbase[34];       // sorted[symbase[l] + code] = symbol of a length-l code
     uint8_t sorted[256];       // symbols ordered by (length, symbol)
     uint8_t len[256];          // code length of every symbol
     int maxlen, minlen, uniform, bad;
@@ -67,6 +68,17 @@ static_assert(sizeof(DecAux) <= 1024, "DecAux must fit its 1 KiB slot");
 // ---------------------------------------------------------------------------------------------
 // table construction (all DT threads).  scratch: >= 8 KiB + 2 KiB of shared memory.
 // ---------------------------------------------------------------------------------------------
+#define DEC_BUILD_SCRATCH (LUTN * 2 + 512 + 256 + 8 * 34 * 4 + 3 * 34 * 4)
+
+// length of the (long) code that starts the left-justified 32 stream bits v, searched in
+// [lmin, lmax]; 0 = no code matches
+__device__ __forceinline__ uint32_t long_len(const DecAux& A, uint32_t v, uint32_t lmin, uint32_t lmax) {
+    if (lmin == 0) return 0;
+    uint32_t l = lmin;
+    while (l < lmax && (uint64_t)v >= A.lim[l]) ++l;
+    return (uint64_t)v < A.lim[l] ? l : 0;
+}
+
 template <bool WANT_W, bool WANT_S>
 __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* __restrict__ slut,
                              uint8_t* __restrict__ scratch, const uint8_t* __restrict__ len_k) {
@@ -74,6 +86,9 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
     uint16_t* lj = reinterpret_cast<uint16_t*>(scratch + LUTN * 2);       // [256] left-justified codes (len<=12)
     uint8_t* ljl = scratch + LUTN * 2 + 512;                              // [256] their lengths
     uint32_t* cntw = reinterpret_cast<uint32_t*>(scratch + LUTN * 2 + 768);   // [8][34]
+    uint32_t* first = cntw + 8 * 34;                                      // [34] first canonical code per length
+    uint32_t* count = first + 34;                                         // [34] symbols per length
+    uint32_t* offs = count + 34;                                          // [34] offset of each length in sorted[]
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
     uint32_t l = len_k[t];
     if (l > 32) l = 33;
@@ -87,36 +102,38 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
     if (t < 34) {
         uint32_t c = 0;
         for (int w = 0; w < 8; ++w) c += cntw[w * 34 + t];
-        A.count[t] = t == 0 ? 0 : c;
+        count[t] = t == 0 ? 0 : c;
     }
     __syncthreads();
     if (t == 0) {
         uint32_t c = 0, o = 0;
         int mx = 0, mn = 0;
         uint64_t kraft = 0;                       // in units of 2^-32
-        A.first[0] = 0; A.offs[0] = 0;
+        first[0] = 0; offs[0] = 0; A.lim[0] = 0; A.symbase[0] = 0;
         for (int L = 1; L <= 32; ++L) {
-            c = (c + (L > 1 ? A.count[L - 1] : 0u)) << 1;
-            A.first[L] = c; A.offs[L] = o; o += A.count[L];
-            if (A.count[L]) { mx = L; if (!mn) mn = L; kraft += (uint64_t)A.count[L] << (32 - L); }
+            c = (c + (L > 1 ? count[L - 1] : 0u)) << 1;
+            first[L] = c; offs[L] = o; o += count[L];
+            A.symbase[L] = (int32_t)offs[L] - (int32_t)c;
+            A.lim[L] = ((uint64_t)c + count[L]) << (32 - L);
+            if (count[L]) { mx = L; if (!mn) mn = L; kraft += (uint64_t)count[L] << (32 - L); }
         }
-        A.offs[33] = o; A.first[33] = 0;
+        offs[33] = o; first[33] = 0; A.lim[33] = 0; A.symbase[33] = 0;
         A.maxlen = mx; A.minlen = mn;
         A.uniform = (mx > 0 && mx == mn) ? mx : 0;
-        A.bad = (A.count[33] != 0) || (kraft > (1ull << 32));
+        A.bad = (count[33] != 0) || (kraft > (1ull << 32));
     }
     __syncthreads();
     if (A.bad) return;
     if (l >= 1 && l <= 32) {
         uint32_t rank = rank_w;
         for (uint32_t w = 0; w < wid; ++w) rank += cntw[w * 34 + l];
-        const uint32_t pos = A.offs[l] + rank;
+        const uint32_t pos = offs[l] + rank;
         A.sorted[pos] = (uint8_t)t;
-        if (l <= LUTB) { lj[pos] = (uint16_t)((A.first[l] + rank) << (LUTB - l)); ljl[pos] = (uint8_t)l; }
+        if (l <= LUTB) { lj[pos] = (uint16_t)((first[l] + rank) << (LUTB - l)); ljl[pos] = (uint8_t)l; }
     }
     __syncthreads();
     // single-symbol table: thread t fills entries [16t, 16t+16)
-    const uint32_t n12 = A.offs[LUTB + 1];        // symbols with length <= LUTB, sorted by code value
+    const uint32_t n12 = offs[LUTB + 1];          // symbols with length <= LUTB, sorted by code value
     {
         const uint32_t x0 = t * 16;
         uint32_t i = 0;
@@ -138,6 +155,7 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
     }
     __syncthreads();
     // multi-symbol tables
+    const uint32_t maxlen = (uint32_t)A.maxlen;
     for (uint32_t x = t * 16; x < t * 16 + 16; ++x) {
         const uint32_t e0 = base[x];
         uint32_t we = 0, se = 0;
@@ -154,7 +172,17 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
                 used += le; ++n; lprev = le;
             }
             we = syms | (wtot << 24) | (wn << 28);
-            se = l0 | (used << 4) | (n << 8);
+            se = used | (n << 6) | (l0 << 10);
+        } else if (maxlen > LUTB) {
+            // the prefix starts a code longer than LUTB bits (or no code): candidate lengths at both ends
+            const uint32_t vlo = x << (32 - LUTB), vhi = vlo | ((1u << (32 - LUTB)) - 1);
+            const uint32_t lmin = long_len(A, vlo, LUTB + 1, maxlen);
+            if (lmin) {
+                uint32_t lmax = long_len(A, vhi, lmin, maxlen);
+                if (!lmax) lmax = maxlen;
+                we = lmin | (lmax << 6);
+                se = lmin == lmax ? (lmin | (1u << 6) | (lmin << 10)) : (lmin | (lmax << 10));
+            }
         }
         if (WANT_W) wlut[x] = we;
         if (WANT_S) slut[x] = (uint16_t)se;
@@ -232,7 +260,7 @@ __global__ void __launch_bounds__(DT)
 dec_tables_kernel(const uint8_t* __restrict__ len_tab, DecPlan P, uint8_t* __restrict__ tables, int* status) {
     __shared__ __align__(16) uint32_t wlut[LUTN];
     __shared__ __align__(16) uint16_t slut[LUTN];
-    __shared__ __align__(16) uint8_t scratch[LUTN * 2 + 768 + 8 * 34 * 4];
+    __shared__ __align__(16) uint8_t scratch[DEC_BUILD_SCRATCH];
     __shared__ __align__(16) uint8_t aux_raw[1024];
     const uint32_t k = blockIdx.x;
     const uint32_t ti = P.tab_idx[k];
@@ -331,31 +359,18 @@ __device__ __forceinline__ void stage_fixup(uint8_t* stage, const StageGeom& g) 
 // ---------------------------------------------------------------------------------------------
 struct BitRd {
     const uint32_t* w;     // stage words (raw little-endian loads of the big-endian stream)
-    uint32_t hi, lo, sh, next;
+    uint32_t hi, lo;       // the words holding bits [32*(pos>>5), +64)
 };
-__device__ __forceinline__ uint32_t rd_word(const uint32_t* w, uint32_t i) {
-    return i < DEC_STAGE_WORDS ? bswap32(w[i]) : 0u;
+__device__ __forceinline__ void rd_seek(BitRd& r, uint32_t pos) {
+    const uint32_t i = pos >> 5;
+    r.hi = bswap32(r.w[i]); r.lo = bswap32(r.w[i + 1]);
 }
-__device__ __forceinline__ void rd_seek(BitRd& r, uint32_t bitpos) {
-    const uint32_t i = bitpos >> 5;
-    r.sh = bitpos & 31;
-    r.hi = rd_word(r.w, i); r.lo = rd_word(r.w, i + 1); r.next = i + 2;
-}
-__device__ __forceinline__ uint32_t rd_peek32(const BitRd& r) { return __funnelshift_l(r.lo, r.hi, r.sh); }
-__device__ __forceinline__ void rd_skip(BitRd& r, uint32_t l) {
-    r.sh += l;
-    if (r.sh >= 32) { r.sh -= 32; r.hi = r.lo; r.lo = rd_word(r.w, r.next); ++r.next; }
-}
-
-// canonical first-code walk for codes longer than LUTB bits; returns the length, 0 if no code matches
-__device__ __forceinline__ uint32_t slow_code(const DecAux& A, uint32_t v, int* sym) {
-    for (int l = LUTB + 1; l <= A.maxlen; ++l) {
-        const uint32_t c = v >> (32 - l);
-        const uint32_t d = c - A.first[l];
-        if (c >= A.first[l] && d < A.count[l]) { *sym = A.sorted[A.offs[l] + d]; return (uint32_t)l; }
-    }
-    *sym = -1;
-    return 0;
+// the 32 stream bits that start at pos (the funnel shift takes pos mod 32)
+__device__ __forceinline__ uint32_t rd_peek32(const BitRd& r, uint32_t pos) { return __funnelshift_l(r.lo, r.hi, pos); }
+__device__ __forceinline__ void rd_skip(BitRd& r, uint32_t& pos, uint32_t l) {       // l <= 32
+    const uint32_t np = pos + l;
+    if ((np ^ pos) >= 32) { r.hi = r.lo; r.lo = bswap32(r.w[(np >> 5) + 1]); }
+    pos = np;
 }
 
 // Advance from `pos` to the first codeword boundary >= limit; returns the number of codewords
@@ -364,18 +379,18 @@ __device__ __forceinline__ uint32_t advance(const DecAux& A, const uint16_t* __r
                                             uint32_t& pos, uint32_t limit) {
     uint32_t cnt = 0;
     while (pos + LUTB <= limit) {
-        const uint32_t v = rd_peek32(r);
+        const uint32_t v = rd_peek32(r, pos);
         const uint32_t e = slut[v >> (32 - LUTB)];
-        uint32_t l, n;
-        if (e & 15) { l = (e >> 4) & 15; n = e >> 8; }
-        else { int s; l = slow_code(A, v, &s); n = 1; if (!l) l = 1; }
-        rd_skip(r, l); pos += l; cnt += n;
+        uint32_t l = e & 63, n = (e >> 6) & 15;
+        if (n == 0) { l = long_len(A, v, l, e >> 10); n = 1; if (!l) l = 1; }
+        rd_skip(r, pos, l); cnt += n;
     }
     while (pos < limit) {
-        const uint32_t v = rd_peek32(r);
-        uint32_t l = slut[v >> (32 - LUTB)] & 15;
-        if (!l) { int s; l = slow_code(A, v, &s); if (!l) l = 1; }
-        rd_skip(r, l); pos += l; ++cnt;
+        const uint32_t v = rd_peek32(r, pos);
+        const uint32_t e = slut[v >> (32 - LUTB)];
+        uint32_t l = e >> 10;
+        if (((e >> 6) & 15) == 0) { l = long_len(A, v, e & 63, l); if (!l) l = 1; }
+        rd_skip(r, pos, l); ++cnt;
     }
     return cnt;
 }
@@ -539,8 +554,9 @@ __device__ __forceinline__ void g_scan(const DecAux& A, const uint16_t* __restri
     uint32_t cnt = 0;
     while (pos < end) {
         const uint32_t v = __funnelshift_l(r.lo, r.hi, r.sh);
-        uint32_t l = slut[v >> (32 - LUTB)] & 15;
-        if (!l) { int s; l = slow_code(A, v, &s); if (!l) l = 1; }
+        const uint32_t e = slut[v >> (32 - LUTB)];
+        uint32_t l = e >> 10;
+        if (((e >> 6) & 15) == 0) { l = long_len(A, v, e & 63, l); if (!l) l = 1; }
         g_skip(r, l); pos += l; ++cnt;
     }
     *count = cnt; *exitv = (uint32_t)(pos - end);
@@ -720,7 +736,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         if (active) {
             if (i == nsub - 1) {
                 todo = osize > obase ? osize - obase : 0;
-                if (todo > DEC_SUB_BITS + 32) { err = true; todo = 0; }      // stream holds fewer symbols than orig_size
+                if (todo > count) { err = true; todo = count; }              // stream holds fewer symbols than orig_size
             } else if (obase < osize) {
                 todo = obase + count > osize ? osize - obase : count;
             }
@@ -731,7 +747,8 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
 
         // ---- per-warp windowed decode -------------------------------------------------------
         BitRd r; r.w = reinterpret_cast<const uint32_t*>(S.stage);
-        rd_seek(r, g.bit0 + t * DEC_SUB_BITS + (rv & 0xFF));
+        uint32_t pos = g.bit0 + t * DEC_SUB_BITS + (rv & 0xFF);
+        rd_seek(r, pos);
         uint64_t my_addr = gout + obase;                            // address of this lane's next symbol
         uint64_t ws = todo ? my_addr : ~0ull, we = todo ? my_addr + todo : 0ull;   // the warp's output range
 #pragma unroll
@@ -755,8 +772,8 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                 uint32_t* wp = reinterpret_cast<uint32_t*>(win + (woff & ~3u));
                 uint32_t left = n;
                 while (left) {
-                    const uint32_t v = rd_peek32(r);
-                    uint32_t e = S.wlut[v >> (32 - LUTB)];
+                    const uint32_t v = rd_peek32(r, pos);
+                    const uint32_t e = S.wlut[v >> (32 - LUTB)];
                     uint32_t c = e >> 28, l, syms;
                     if (c) {
                         l = (e >> 24) & 15; syms = e & 0xFFFFFF;
@@ -767,11 +784,12 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                             syms &= 0xFFFFFFu >> (8 * (3 - c));
                         }
                     } else {
-                        int s; l = slow_code(A, v, &s);
-                        if (!l) { l = 1; s = 0; err = true; }
-                        c = 1; syms = (uint32_t)s;
+                        l = long_len(A, v, e & 63, (e >> 6) & 63);
+                        if (l) syms = A.sorted[A.symbase[l] + (int32_t)(v >> (32 - l))];
+                        else { l = 1; syms = 0; err = true; }
+                        c = 1;
                     }
-                    rd_skip(r, l);
+                    rd_skip(r, pos, l);
                     left -= c;
                     acc |= (uint64_t)syms << (8 * fill);
                     fill += c;
