@@ -52,7 +52,8 @@
 // staged bytes per sequence: 16 alignment slack + 16 overlap + sequence + 32 look-ahead
 #define DEC_STAGE_BYTES (16 + DEC_OVERLAP_BYTES + DEC_SEQ_BYTES + 32)
 #define DEC_STAGE_WORDS (DEC_STAGE_BYTES / 4)
-#define DEC_WIN_BYTES 9216                    // per-warp output window of the write kernel
+#define DEC_WIN_MIN 2304                      // per-warp output window of the write kernel (runtime sized)
+#define DEC_WIN_MAX 9216
 #define DEC_NO_TABLE 0xFFFFFFFFu
 #define DEC_TABLE_BYTES (LUTN * 4 + LUTN * 2 + 1024)
 
@@ -357,37 +358,44 @@ __device__ __forceinline__ void stage_fixup(uint8_t* stage, const StageGeom& g) 
 // ---------------------------------------------------------------------------------------------
 // bit reader over the staged bytes: (hi, lo) = 64 upcoming stream bits, sh = consumed bits of hi
 // ---------------------------------------------------------------------------------------------
+// shared-state-space accesses with 32-bit addresses (keeps the hot loops free of generic->shared
+// window arithmetic)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 struct BitRd {
-    const uint32_t* w;     // stage words (raw little-endian loads of the big-endian stream)
+    uint32_t w;            // shared address of the stage (raw little-endian words of the big-endian stream)
     uint32_t hi, lo;       // the words holding bits [32*(pos>>5), +64)
 };
 __device__ __forceinline__ void rd_seek(BitRd& r, uint32_t pos) {
-    const uint32_t i = pos >> 5;
-    r.hi = bswap32(r.w[i]); r.lo = bswap32(r.w[i + 1]);
+    const uint32_t a = r.w + ((pos >> 5) << 2);
+    r.hi = bswap32(lds32(a)); r.lo = bswap32(lds32(a + 4));
 }
 // the 32 stream bits that start at pos (the funnel shift takes pos mod 32)
 __device__ __forceinline__ uint32_t rd_peek32(const BitRd& r, uint32_t pos) { return __funnelshift_l(r.lo, r.hi, pos); }
 __device__ __forceinline__ void rd_skip(BitRd& r, uint32_t& pos, uint32_t l) {       // l <= 32
     const uint32_t np = pos + l;
-    if ((np ^ pos) >= 32) { r.hi = r.lo; r.lo = bswap32(r.w[(np >> 5) + 1]); }
+    if ((np ^ pos) >= 32) { r.hi = r.lo; r.lo = bswap32(lds32(r.w + ((np >> 5) << 2) + 4)); }
     pos = np;
 }
 
 // Advance from `pos` to the first codeword boundary >= limit; returns the number of codewords
 // that began before `limit`.  Unmatched patterns consume one bit.
-__device__ __forceinline__ uint32_t advance(const DecAux& A, const uint16_t* __restrict__ slut, BitRd& r,
-                                            uint32_t& pos, uint32_t limit) {
+__device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitRd& r, uint32_t& pos, uint32_t limit) {
     uint32_t cnt = 0;
     while (pos + LUTB <= limit) {
         const uint32_t v = rd_peek32(r, pos);
-        const uint32_t e = slut[v >> (32 - LUTB)];
+        const uint32_t e = lds16(slut + ((v >> (32 - LUTB)) << 1));
         uint32_t l = e & 63, n = (e >> 6) & 15;
         if (n == 0) { l = long_len(A, v, l, e >> 10); n = 1; if (!l) l = 1; }
         rd_skip(r, pos, l); cnt += n;
     }
     while (pos < limit) {
         const uint32_t v = rd_peek32(r, pos);
-        const uint32_t e = slut[v >> (32 - LUTB)];
+        const uint32_t e = lds16(slut + ((v >> (32 - LUTB)) << 1));
         uint32_t l = e >> 10;
         if (((e >> 6) & 15) == 0) { l = long_len(A, v, e & 63, l); if (!l) l = 1; }
         rd_skip(r, pos, l); ++cnt;
@@ -459,7 +467,8 @@ dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uin
         stage_fixup(S.stage[b], g);
         __syncthreads();
 
-        BitRd r; r.w = reinterpret_cast<const uint32_t*>(S.stage[b]);
+        BitRd r; r.w = smem_u32(S.stage[b]);
+        const uint32_t slut_a = smem_u32(S.slut);
         const uint32_t i = sq * DT + t;
         const bool active = i < nsub;
         const uint32_t nominal = g.bit0 + t * DEC_SUB_BITS;       // stage-relative
@@ -478,10 +487,10 @@ dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uin
                 entry = carry_exit; pos = nominal + entry; rd_seek(r, pos);
             } else {
                 pos = nominal - DEC_OVERLAP_BITS; rd_seek(r, pos);
-                advance(A, S.slut, r, pos, nominal);
+                advance(A, slut_a, r, pos, nominal);
                 entry = pos - nominal;
             }
-            count = advance(A, S.slut, r, pos, end);
+            count = advance(A, slut_a, r, pos, end);
             exitv = pos - end;
         }
         S.s_exit[t] = exitv;
@@ -497,7 +506,7 @@ dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uin
                     entry = want;
                     uint32_t pos = nominal + entry;
                     rd_seek(r, pos);
-                    count = advance(A, S.slut, r, pos, end);
+                    count = advance(A, slut_a, r, pos, end);
                     exitv = pos - end;
                     S.s_exit[t] = exitv;
                 }
@@ -655,22 +664,23 @@ dec_fix_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ co
 // ---------------------------------------------------------------------------------------------
 // write kernel
 // ---------------------------------------------------------------------------------------------
-struct WriteSmem {
+struct WriteSmem {                       // followed by DT/32 output windows of win_bytes each
     __align__(16) uint8_t stage[DEC_STAGE_BYTES];
     __align__(16) uint32_t wlut[LUTN];
     __align__(16) uint8_t aux[1024];
-    __align__(16) uint8_t win[DT / 32][DEC_WIN_BYTES];
+    __align__(16) uint32_t headw[DT];    // a lane's first (partial) word is parked here until the warp is done
     __align__(8) uint64_t bar;
     uint32_t s_warp[DT / 32 + 1];
     uint32_t s_k;
 };
+#define DEC_WRITE_FIXED ((sizeof(WriteSmem) + 15) & ~(size_t)15)
 
 __global__ void __launch_bounds__(DT)
 dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uint64_t* __restrict__ comp_off,
                  const uint32_t* __restrict__ comp_size, const uint32_t* __restrict__ orig_size,
                  const uint8_t* __restrict__ len_tab, uint32_t K, DecPlan P, const uint8_t* __restrict__ tables,
                  const uint32_t* __restrict__ rec, const uint32_t* __restrict__ seqoff,
-                 uint8_t* __restrict__ out, uint64_t out_cap, int* status) {
+                 uint8_t* __restrict__ out, uint64_t out_cap, uint32_t win_bytes, int* status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WriteSmem& S = *reinterpret_cast<WriteSmem*>(smem_raw);
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -705,7 +715,9 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
     const uint32_t sq0 = cta_in_chunk * DEC_SEQ_PER_CTA;
     const uint32_t nq = min((uint32_t)DEC_SEQ_PER_CTA, nseq - sq0);
     const uint64_t gout = reinterpret_cast<uint64_t>(out) + ooff;      // address of the chunk's first output byte
-    uint8_t* win = S.win[wid];
+    uint8_t* win = smem_raw + DEC_WRITE_FIXED + (size_t)wid * win_bytes;
+    const uint32_t win_a = smem_u32(win), wlut_a = smem_u32(S.wlut), aux_a = smem_u32(S.aux);
+    const uint32_t headw_a = smem_u32(&S.headw[t]);
     bool err = false;
 
     for (uint32_t q = 0; q < nq; ++q) {
@@ -746,7 +758,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         __syncthreads();
 
         // ---- per-warp windowed decode -------------------------------------------------------
-        BitRd r; r.w = reinterpret_cast<const uint32_t*>(S.stage);
+        BitRd r; r.w = smem_u32(S.stage);
         uint32_t pos = g.bit0 + t * DEC_SUB_BITS + (rv & 0xFF);
         rd_seek(r, pos);
         uint64_t my_addr = gout + obase;                            // address of this lane's next symbol
@@ -756,65 +768,62 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
             const uint64_t a = __shfl_xor_sync(0xffffffffu, ws, d), b = __shfl_xor_sync(0xffffffffu, we, d);
             ws = a < ws ? a : ws; we = b > we ? b : we;
         }
-        uint64_t acc = 0;
-        uint32_t fill = 0;
-        bool first = true;
-        uint32_t head = 0;
-        for (uint64_t wa = ws & ~(uint64_t)15; wa < we; wa += DEC_WIN_BYTES) {
+        bool lane_first = true;
+        for (uint64_t wa = ws & ~(uint64_t)15; wa < we; wa += win_bytes) {
             uint32_t n = 0;
-            if (todo && my_addr < wa + DEC_WIN_BYTES) {
-                const uint64_t room = wa + DEC_WIN_BYTES - my_addr;
+            if (todo && my_addr < wa + win_bytes) {
+                const uint64_t room = wa + win_bytes - my_addr;
                 n = todo < room ? todo : (uint32_t)room;
             }
             if (n) {
-                uint32_t woff = (uint32_t)(my_addr - wa);           // byte offset of the next symbol in the window
-                if (first) { head = woff & 3; fill = head; }
-                uint32_t* wp = reinterpret_cast<uint32_t*>(win + (woff & ~3u));
-                uint32_t left = n;
-                while (left) {
+                const uint32_t woff = (uint32_t)(my_addr - wa);     // byte offset of the next symbol in the window
+                const uint32_t w0 = win_a + (woff & ~3u);           // the word that holds it
+                // words are assembled in `acc`; the first one (shared with the previous lane) is parked
+                // in headw and merged bytewise once this lane is done
+                uint32_t head = 0, sp = w0, nextw = w0 + 4, acc = 0, fill8 = 0;
+                if (lane_first) { head = woff & 3; fill8 = head * 8; sp = headw_a; lane_first = false; }
+                const bool parked = sp == headw_a;
+                uint32_t left8 = n * 8;
+                while (left8) {
                     const uint32_t v = rd_peek32(r, pos);
-                    const uint32_t e = S.wlut[v >> (32 - LUTB)];
-                    uint32_t c = e >> 28, l, syms;
-                    if (c) {
-                        l = (e >> 24) & 15; syms = e & 0xFFFFFF;
-                        if (c > left) {          // window / subsequence ends inside this entry: take `left` symbols
-                            c = left;
-                            l = A.len[syms & 0xFF];
-                            if (c == 2) l += A.len[(syms >> 8) & 0xFF];
-                            syms &= 0xFFFFFFu >> (8 * (3 - c));
-                        }
-                    } else {
-                        l = long_len(A, v, e & 63, (e >> 6) & 63);
-                        if (l) syms = A.sorted[A.symbase[l] + (int32_t)(v >> (32 - l))];
-                        else { l = 1; syms = 0; err = true; }
-                        c = 1;
+                    const uint32_t e = lds32(wlut_a + ((v >> (32 - LUTB)) << 2));
+                    uint32_t n8 = (e >> 25) & 0x18, l = (e >> 24) & 15, syms = e & 0xFFFFFF;
+                    if (n8 == 0) {                                  // code longer than LUTB bits
+                        const uint32_t lmin = e & 63, lmax = (e >> 6) & 63;
+                        l = lmin == lmax ? lmin : long_len(A, v, lmin, lmax);
+                        if (l) {
+                            const uint32_t sb = lds32(aux_a + (uint32_t)offsetof(DecAux, symbase) + l * 4);
+                            syms = lds8(aux_a + (uint32_t)offsetof(DecAux, sorted) + sb + (v >> (32 - l)));
+                        } else { l = 1; syms = 0; err = true; }
+                        n8 = 8;
+                    } else if (n8 > left8) {                        // window / subsequence ends inside this entry
+                        l = lds8(aux_a + (uint32_t)offsetof(DecAux, len) + (syms & 0xFF));
+                        if (left8 == 16) l += lds8(aux_a + (uint32_t)offsetof(DecAux, len) + ((syms >> 8) & 0xFF));
+                        syms &= 0xFFFFFFu >> (24 - left8);
+                        n8 = left8;
                     }
                     rd_skip(r, pos, l);
-                    left -= c;
-                    acc |= (uint64_t)syms << (8 * fill);
-                    fill += c;
-                    if (fill >= 4) {
-                        if (first) {
-                            uint8_t* bp = reinterpret_cast<uint8_t*>(wp);
-                            for (uint32_t j = head; j < 4; ++j) bp[j] = (uint8_t)(acc >> (8 * j));
-                            first = false;
-                        } else {
-                            *wp = (uint32_t)acc;
-                        }
-                        ++wp; acc >>= 32; fill -= 4;
-                    }
+                    left8 -= n8;
+                    acc |= syms << fill8;
+                    const uint32_t spill = __funnelshift_l(syms, 0u, fill8);     // bytes that do not fit the word
+                    fill8 += n8;
+                    if (fill8 >= 32) { sts32(sp, acc); sp = nextw; nextw += 4; acc = spill; fill8 -= 32; }
                 }
                 todo -= n; my_addr += n;
-                if (todo == 0 && fill) {                             // tail bytes of this lane
-                    uint8_t* bp = reinterpret_cast<uint8_t*>(wp);
-                    for (uint32_t j = first ? head : 0; j < fill; ++j) bp[j] = (uint8_t)(acc >> (8 * j));
-                    fill = 0;
+                const bool stored = !parked || sp != headw_a;       // at least one complete word left this lane
+                if (parked && stored) {
+                    const uint32_t hw = lds32(headw_a);
+                    for (uint32_t j = head; j < 4; ++j) sts8(w0 + j, hw >> (8 * j));
+                }
+                if (fill8) {                                         // tail bytes (the lane is done: todo == 0)
+                    const uint32_t dst = stored ? sp : w0;
+                    for (uint32_t j = stored ? 0 : head; j < fill8 / 8; ++j) sts8(dst + j, acc >> (8 * j));
                 }
             }
             __syncwarp();
             // copy the window out: aligned 16-byte units, bytes at the ragged ends
             const uint64_t lo = ws > wa ? ws : wa;
-            const uint64_t hi = we < wa + DEC_WIN_BYTES ? we : wa + DEC_WIN_BYTES;
+            const uint64_t hi = we < wa + win_bytes ? we : wa + win_bytes;
             const uint32_t u0 = (uint32_t)(lo - wa) >> 4, u1 = (uint32_t)(hi - wa + 15) >> 4;
             for (uint32_t u = u0 + lane; u < u1; u += 32) {
                 const uint64_t ua = wa + (uint64_t)u * 16;
@@ -864,7 +873,8 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     static bool attr_done = false;
     if (!attr_done) {
         HZ_CUDA(ctx, cudaFuncSetAttribute(dec_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncSmem)));
-        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WriteSmem)));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(DEC_WRITE_FIXED + (DT / 32) * DEC_WIN_MAX)));
         attr_done = true;
     }
     HZ_LAUNCH(ctx, "dec_tables", dec_tables_kernel, K, DT, 0, d_len, P, tables, ctx->d_status);
@@ -872,8 +882,13 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
               d_comp, comp_bytes, d_comp_off, d_comp_size, d_len, K, P, tables, rec, seqcnt, ctx->d_status);
     HZ_LAUNCH(ctx, "dec_fix", dec_fix_kernel, K, DT, 0,
               d_comp, d_comp_off, d_comp_size, P, tables, rec, seqcnt, ctx->d_status);
-    HZ_LAUNCH(ctx, "dec_write", dec_write_kernel, (unsigned)max_cta, DT, sizeof(WriteSmem),
+    // per-warp output window: sized so that the symbols of one warp (32 subsequences) normally fit one
+    // window, from the stream's overall expansion ratio; smaller windows -> more CTAs per SM
+    uint64_t est = comp_bytes ? (uint64_t)(32.0 * DEC_SUB_BYTES * 1.1 * (double)out_cap / (double)comp_bytes) + 64 : DEC_WIN_MIN;
+    est = (est + 255) & ~(uint64_t)255;
+    const uint32_t win_bytes = (uint32_t)(est < DEC_WIN_MIN ? DEC_WIN_MIN : (est > DEC_WIN_MAX ? DEC_WIN_MAX : est));
+    HZ_LAUNCH(ctx, "dec_write", dec_write_kernel, (unsigned)max_cta, DT, DEC_WRITE_FIXED + (DT / 32) * (size_t)win_bytes,
               d_comp, comp_bytes, d_comp_off, d_comp_size, d_orig_size, d_len, K, P, tables, rec, seqcnt, d_out, out_cap,
-              ctx->d_status);
+              win_bytes, ctx->d_status);
     return HZ_OK;
 }
