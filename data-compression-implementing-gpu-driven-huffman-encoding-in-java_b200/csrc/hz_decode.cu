@@ -31,7 +31,7 @@
 //             12 bits and the first codeword's length (counting pass).  A prefix that starts a
 //             code longer than 12 bits has n = 1 and its length when every code under the prefix
 //             has the same length, else n = 0 with ltot = shortest, l0 = longest candidate.
-//   wlut u32: s0 | s1<<8 | s2<<16 | ltot<<24 | n<<28   up to three symbols per lookup;
+//   wlut u32: s0 | s1<<8 | s2<<16 | n<<24 | ltot<<28   up to three symbols per lookup;
 //             n = 0: long code, bits 0-5 shortest / bits 6-11 longest candidate length (0 = no code).
 // Codes whose used lengths are all equal never self-synchronise but need no synchronisation
 // either: entries are computed arithmetically.
@@ -172,7 +172,7 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
                 if (n < 3) { syms |= (e & 0xFF) << (8 * n); wtot = used + le; wn = n + 1; }
                 used += le; ++n; lprev = le;
             }
-            we = syms | (wtot << 24) | (wn << 28);
+            we = syms | (wn << 24) | (wtot << 28);
             se = used | (n << 6) | (l0 << 10);
         } else if (maxlen > LUTB) {
             // the prefix starts a code longer than LUTB bits (or no code): candidate lengths at both ends
@@ -366,19 +366,22 @@ __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile(
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+// keep a value in a register: stops the compiler from re-deriving shared-window bases in hot loops
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+
 struct BitRd {
-    uint32_t w;            // shared address of the stage (raw little-endian words of the big-endian stream)
-    uint32_t hi, lo;       // the words holding bits [32*(pos>>5), +64)
+    uint32_t wa;           // shared address of the word held in `lo`
+    uint32_t hi, lo;       // the (byte-swapped) stage words holding bits [32*(pos>>5), +64)
 };
-__device__ __forceinline__ void rd_seek(BitRd& r, uint32_t pos) {
-    const uint32_t a = r.w + ((pos >> 5) << 2);
-    r.hi = bswap32(lds32(a)); r.lo = bswap32(lds32(a + 4));
+__device__ __forceinline__ void rd_seek(BitRd& r, uint32_t stage_a, uint32_t pos) {
+    r.wa = stage_a + ((pos >> 5) << 2) + 4;
+    r.hi = bswap32(lds32(r.wa - 4)); r.lo = bswap32(lds32(r.wa));
 }
 // the 32 stream bits that start at pos (the funnel shift takes pos mod 32)
 __device__ __forceinline__ uint32_t rd_peek32(const BitRd& r, uint32_t pos) { return __funnelshift_l(r.lo, r.hi, pos); }
 __device__ __forceinline__ void rd_skip(BitRd& r, uint32_t& pos, uint32_t l) {       // l <= 32
     const uint32_t np = pos + l;
-    if ((np ^ pos) >= 32) { r.hi = r.lo; r.lo = bswap32(lds32(r.w + ((np >> 5) << 2) + 4)); }
+    if ((np ^ pos) >= 32) { r.hi = r.lo; r.wa += 4; r.lo = bswap32(lds32(r.wa)); }
     pos = np;
 }
 
@@ -388,14 +391,14 @@ __device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitR
     uint32_t cnt = 0;
     while (pos + LUTB <= limit) {
         const uint32_t v = rd_peek32(r, pos);
-        const uint32_t e = lds16(slut + ((v >> (32 - LUTB)) << 1));
+        const uint32_t e = lds16(slut + 2 * (v >> (32 - LUTB)));
         uint32_t l = e & 63, n = (e >> 6) & 15;
         if (n == 0) { l = long_len(A, v, l, e >> 10); n = 1; if (!l) l = 1; }
         rd_skip(r, pos, l); cnt += n;
     }
     while (pos < limit) {
         const uint32_t v = rd_peek32(r, pos);
-        const uint32_t e = lds16(slut + ((v >> (32 - LUTB)) << 1));
+        const uint32_t e = lds16(slut + 2 * (v >> (32 - LUTB)));
         uint32_t l = e >> 10;
         if (((e >> 6) & 15) == 0) { l = long_len(A, v, e & 63, l); if (!l) l = 1; }
         rd_skip(r, pos, l); ++cnt;
@@ -467,8 +470,8 @@ dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uin
         stage_fixup(S.stage[b], g);
         __syncthreads();
 
-        BitRd r; r.w = smem_u32(S.stage[b]);
-        const uint32_t slut_a = smem_u32(S.slut);
+        BitRd r;
+        const uint32_t stage_a = pin_reg(smem_u32(S.stage[b])), slut_a = pin_reg(smem_u32(S.slut));
         const uint32_t i = sq * DT + t;
         const bool active = i < nsub;
         const uint32_t nominal = g.bit0 + t * DEC_SUB_BITS;       // stage-relative
@@ -480,13 +483,13 @@ dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uin
                 const uint64_t nomc = (uint64_t)i * DEC_SUB_BITS;
                 entry = (uint32_t)((U - nomc % U) % U);
                 pos = nominal + entry;
-                rd_seek(r, pos);
+                rd_seek(r, stage_a, pos);
             } else if (i == 0) {
-                pos = nominal; rd_seek(r, pos);
+                pos = nominal; rd_seek(r, stage_a, pos);
             } else if (t == 0 && q > 0) {
-                entry = carry_exit; pos = nominal + entry; rd_seek(r, pos);
+                entry = carry_exit; pos = nominal + entry; rd_seek(r, stage_a, pos);
             } else {
-                pos = nominal - DEC_OVERLAP_BITS; rd_seek(r, pos);
+                pos = nominal - DEC_OVERLAP_BITS; rd_seek(r, stage_a, pos);
                 advance(A, slut_a, r, pos, nominal);
                 entry = pos - nominal;
             }
@@ -505,7 +508,7 @@ dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uin
                 if (fix) {
                     entry = want;
                     uint32_t pos = nominal + entry;
-                    rd_seek(r, pos);
+                    rd_seek(r, stage_a, pos);
                     count = advance(A, slut_a, r, pos, end);
                     exitv = pos - end;
                     S.s_exit[t] = exitv;
@@ -716,9 +719,8 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
     const uint32_t nq = min((uint32_t)DEC_SEQ_PER_CTA, nseq - sq0);
     const uint64_t gout = reinterpret_cast<uint64_t>(out) + ooff;      // address of the chunk's first output byte
     uint8_t* win = smem_raw + DEC_WRITE_FIXED + (size_t)wid * win_bytes;
-    const uint32_t win_a = smem_u32(win), wlut_a = smem_u32(S.wlut), aux_a = smem_u32(S.aux);
-    const uint32_t headw_a = smem_u32(&S.headw[t]);
-    bool err = false;
+    const uint32_t win_a = pin_reg(smem_u32(win)), wlut_a = pin_reg(smem_u32(S.wlut)), aux_a = pin_reg(smem_u32(S.aux));
+    const uint32_t headw_a = pin_reg(smem_u32(&S.headw[t])), stage_a = pin_reg(smem_u32(S.stage));
 
     for (uint32_t q = 0; q < nq; ++q) {
         const uint32_t sq = sq0 + q;
@@ -748,7 +750,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         if (active) {
             if (i == nsub - 1) {
                 todo = osize > obase ? osize - obase : 0;
-                if (todo > count) { err = true; todo = count; }              // stream holds fewer symbols than orig_size
+                if (todo > count) { hz_set_status(status, HZ_ERR_DECODE); todo = count; }   // fewer symbols than orig_size
             } else if (obase < osize) {
                 todo = obase + count > osize ? osize - obase : count;
             }
@@ -758,9 +760,9 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         __syncthreads();
 
         // ---- per-warp windowed decode -------------------------------------------------------
-        BitRd r; r.w = smem_u32(S.stage);
+        BitRd r;
         uint32_t pos = g.bit0 + t * DEC_SUB_BITS + (rv & 0xFF);
-        rd_seek(r, pos);
+        rd_seek(r, stage_a, pos);
         uint64_t my_addr = gout + obase;                            // address of this lane's next symbol
         uint64_t ws = todo ? my_addr : ~0ull, we = todo ? my_addr + todo : 0ull;   // the warp's output range
 #pragma unroll
@@ -786,15 +788,15 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                 uint32_t left8 = n * 8;
                 while (left8) {
                     const uint32_t v = rd_peek32(r, pos);
-                    const uint32_t e = lds32(wlut_a + ((v >> (32 - LUTB)) << 2));
-                    uint32_t n8 = (e >> 25) & 0x18, l = (e >> 24) & 15, syms = e & 0xFFFFFF;
+                    const uint32_t e = lds32(wlut_a + 4 * (v >> (32 - LUTB)));
+                    uint32_t n8 = (e >> 21) & 0x18, l = e >> 28, syms = e & 0xFFFFFF;
                     if (n8 == 0) {                                  // code longer than LUTB bits
                         const uint32_t lmin = e & 63, lmax = (e >> 6) & 63;
                         l = lmin == lmax ? lmin : long_len(A, v, lmin, lmax);
                         if (l) {
                             const uint32_t sb = lds32(aux_a + (uint32_t)offsetof(DecAux, symbase) + l * 4);
                             syms = lds8(aux_a + (uint32_t)offsetof(DecAux, sorted) + sb + (v >> (32 - l)));
-                        } else { l = 1; syms = 0; err = true; }
+                        } else { l = 1; syms = 0; hz_set_status(status, HZ_ERR_DECODE); }
                         n8 = 8;
                     } else if (n8 > left8) {                        // window / subsequence ends inside this entry
                         l = lds8(aux_a + (uint32_t)offsetof(DecAux, len) + (syms & 0xFF));
@@ -838,7 +840,6 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         }
         __syncthreads();            // stage is re-filled by the next iteration
     }
-    if (err) hz_set_status(status, HZ_ERR_DECODE);
 }
 
 // ---------------------------------------------------------------------------------------------
