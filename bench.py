@@ -364,7 +364,9 @@ def run_b200(a):
     roofline = None
     if dom:
         roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": dom["achieved_GBps"] / peak, "traffic": traffic.get(dom["name"]),
+                    "frac": dom["achieved_GBps"] / peak,
+                    "traffic": (traffic.get(dom["name"]) or {}).get("dram_bytes_per_launch") if a.size_mib == 4096 else None,
+                    "traffic_source": "profiles/traffic.json (ncu --set full, default 4 GiB workload)",
                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "ms_per_launch": dom["ms_per_launch"],
                     "peak_source": peak_src}
     stages = {
