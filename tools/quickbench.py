@@ -23,7 +23,7 @@ c = hz.Codec(0)
 _s = torch.cuda.Stream(); torch.cuda.set_stream(_s)
 c.set_stream(_s.cuda_stream)
 src = torch.empty(n, dtype=torch.uint8, device="cuda")
-c.synth_fill(src.data_ptr(), n, 0, 0x5EED0001, datasets.zipf_qtable(H))
+c.synth_fill(src.data_ptr(), n, 0, 0x5EED0001, datasets.zipf_qtable(H) if H else np.full(65536, 0x41, dtype=np.uint8))
 comp = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
 off = torch.zeros(K + 1, dtype=torch.int64, device="cuda")
 lens = torch.zeros((K, 256), dtype=torch.uint8, device="cuda")
