@@ -232,7 +232,7 @@ def run_b200(a):
     n = a.size_mib * MiB
     chunk = a.chunk_kib * 1024
     K = (n + chunk - 1) // chunk
-    spc = (chunk + 61440 - 1) // 61440
+    spc = (chunk + hz.SEG_BYTES - 1) // hz.SEG_BYTES
     q = datasets.zipf_qtable(a.entropy)
     src = torch.empty(n, dtype=torch.uint8, device="cuda")
     codec.synth_fill(src.data_ptr(), n, rank * n, SEED, q)

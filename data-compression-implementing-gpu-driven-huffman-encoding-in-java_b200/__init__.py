@@ -23,7 +23,7 @@ HZ_OK = 0
 HZ_ERR_ARG, HZ_ERR_CUDA, HZ_ERR_NOMEM, HZ_ERR_CODE_TOO_LONG, HZ_ERR_OUT_TOO_SMALL = -1, -2, -3, -4, -5
 HZ_ERR_DECODE, HZ_ERR_BAD_LENGTHS, HZ_ERR_IO, HZ_ERR_FORMAT, HZ_ERR_CHECKSUM, HZ_ERR_UNSUPPORTED = -6, -7, -8, -9, -10, -11
 
-SEG_BYTES = 61440
+SEG_BYTES = 57344
 
 _EXPORTS = [
     "hz_create", "hz_destroy", "hz_last_error", "hz_strerror", "hz_set_stream", "hz_sync", "hz_device_count",

@@ -9,11 +9,12 @@
 // ---------------------------------------------------------------------------------------------
 // Geometry shared by the histogram and encode kernels.
 //   segment = the unit one CTA histograms and later encodes; a chunk is split into
-//   ceil(chunk_bytes / HZ_SEG_BYTES) segments.  15 * 4096: with 256 threads every thread sees at
-//   most 240 bytes of a segment, so the per-thread 8-bit counters of the histogram cannot wrap.
+//   ceil(chunk_bytes / HZ_SEG_BYTES) segments.  7 * 8192: a whole number of encoder tiles, and
+//   with 256 threads every thread sees at most 224 bytes of a segment, so the per-thread 8-bit
+//   counters of the alternative histogram kernel cannot wrap.
 // ---------------------------------------------------------------------------------------------
 #define HZ_THREADS 256
-#define HZ_SEG_BYTES 61440u
+#define HZ_SEG_BYTES 57344u
 
 struct hz_prof_entry { const char* name; double ms; uint64_t launches; };
 

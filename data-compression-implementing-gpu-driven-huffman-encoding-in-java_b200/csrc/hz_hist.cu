@@ -15,8 +15,8 @@
 //  * hist_seg_private  — per-THREAD private 8-bit counters in shared memory (64 KiB per CTA,
 //    column t of a [64][256] word matrix, so lane == bank: conflict-free), plain
 //    LDS.U8/IADD/STS.U8.  Distribution independent (0.61 ms per GiB) but ~7 instructions per
-//    byte; kept as the measured alternative (HZ_HIST=private).  A thread sees at most 240 bytes
-//    per segment (HZ_SEG_BYTES = 15*4096), so a counter cannot wrap.
+//    byte; kept as the measured alternative (HZ_HIST=private).  A thread sees at most 224 bytes
+//    per segment (HZ_SEG_BYTES = 7*8192), so a counter cannot wrap.
 #include "hz_common.cuh"
 
 __device__ __forceinline__ void seg_geometry(uint64_t n, uint32_t chunk_bytes, uint32_t spc,
@@ -67,7 +67,7 @@ hist_seg_private(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_byte
     const uint4* pv = reinterpret_cast<const uint4*>(p + head);
     uint8_t* c8 = reinterpret_cast<uint8_t*>(cnt);
     const uint32_t t4 = t * 4;
-    // nvec <= 3840 -> at most 15 vectors (240 bytes) per thread
+    // nvec <= 3584 -> at most 14 vectors (224 bytes) per thread
     for (uint32_t i = t; i < nvec; i += HZ_THREADS) {
         uint4 v = ld_stream_u4(pv + i);
         uint32_t w[4] = {v.x, v.y, v.z, v.w};

@@ -59,7 +59,7 @@ def test_histogram_known_answers(hz, codec):
     assert fs.is_available() and "B200" in fs.get_service_name()
 
 
-@pytest.mark.parametrize("n,chunk", [(1, 1), (15, 64), (61440, 61440), (61441, 61440), (200_001, 50_000),
+@pytest.mark.parametrize("n,chunk", [(1, 1), (15, 64), (61440, 61440), (61441, 61440), (57344, 57344), (57345, 57344), (200_001, 50_000),
                                       (3 * MiB + 17, MiB), (1_000_003, 333_337)])
 @pytest.mark.parametrize("kind", ["uniform", "zipf", "same"])
 def test_histogram_exact(codec, n, chunk, kind):
@@ -166,7 +166,7 @@ def test_zipf_streams(codec, entropy, chunk):
 
 
 @pytest.mark.parametrize("n,chunk", [(0, 1024), (1, 1024), (7, 3), (1023, 4096), (61439, 1 << 20), (61440, 1 << 20),
-                                      (61441, 1 << 20), (122880, 61440), (1_000_003, 100_003), (300_000, 77)])
+                                      (61441, 1 << 20), (122880, 61440), (57343, 1 << 20), (57344, 1 << 20), (57345, 1 << 20), (114688, 57344), (8191, 8192), (8193, 1 << 20), (1_000_003, 100_003), (300_000, 77)])
 def test_ragged_sizes(codec, n, chunk):
     data = datasets.zipf_stream(n, 4, seed=n + 1) if n else np.zeros(0, np.uint8)
     check_encode(codec, data, chunk)
