@@ -32,7 +32,7 @@
 #define ENC_TILE (HZ_THREADS * ENC_SPT)             // 8192
 #define ENC_STAGE_WORDS (ENC_TILE * 16 / 32 + 16)   // 16 KiB of bits + carry unit + slack
 #define ENC_LUT_BYTES (256 * 32 * 4)                // [sym][lane] uint32: len<<16 | code
-#define ENC_LOW_BYTES (ENC_STAGE_WORDS * 4 + 64)    // staging buffer + scan scratch, below the LUT
+#define ENC_LOW_BYTES (ENC_STAGE_WORDS * 4 + 128)    // staging buffer + scan scratch, below the LUT
 #define ENC_SMEM_BYTES (65536 - 1024)               // the driver reserves the first 1 KiB of the shared window
 
 static_assert(HZ_SEG_BYTES % ENC_TILE == 0, "a segment is a whole number of tiles");
@@ -61,8 +61,9 @@ __device__ __forceinline__ void load_syms32(const uint8_t* q, int nvalid, uint32
     }
 }
 
-// Block-wide exclusive scan of `v`; returns this thread's exclusive prefix, *total = block sum.
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_tot, uint32_t* total) {
+// Block-wide exclusive scan of `v` with ONE barrier: every warp publishes its total, then each
+// warp sums the totals of the warps before it.  warp_tot is double-buffered by the caller (`par`).
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_tot, uint32_t par, uint32_t* total) {
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
     uint32_t inc = v;
 #pragma unroll
@@ -70,22 +71,13 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_t
         uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += o;
     }
-    if (lane == 31) warp_tot[wid] = inc;
+    uint32_t* wt = warp_tot + par * (HZ_THREADS / 32);
+    if (lane == 31) wt[wid] = inc;
     __syncthreads();
-    if (t < 32) {
-        uint32_t x = t < HZ_THREADS / 32 ? warp_tot[t] : 0;
-        uint32_t xi = x;
-#pragma unroll
-        for (int d = 1; d < HZ_THREADS / 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(0xffffffffu, xi, d);
-            if (lane >= d) xi += o;
-        }
-        if (t < HZ_THREADS / 32) warp_tot[t] = xi - x;
-        if (t == HZ_THREADS / 32 - 1) warp_tot[HZ_THREADS / 32] = xi;
-    }
-    __syncthreads();
-    *total = warp_tot[HZ_THREADS / 32];
-    return warp_tot[wid] + inc - v;
+    const uint32_t x = lane < HZ_THREADS / 32 ? wt[lane] : 0;
+    const uint32_t before = __reduce_add_sync(0xffffffffu, lane < wid ? x : 0);
+    *total = __reduce_add_sync(0xffffffffu, x);
+    return before + inc - v;
 }
 
 // Running state of a thread that appends containers to the staging bit buffer.
@@ -178,8 +170,18 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
     if (sbeg >= clen) return;
     const uint32_t slen = (uint32_t)(clen - sbeg < HZ_SEG_BYTES ? clen - sbeg : HZ_SEG_BYTES);
     const bool last_seg = sbeg + slen >= clen;
-    if (comp_off[K] > out_cap) { if (t == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
     const uint8_t* p = in + cbeg + sbeg;
+    // every start-up load is issued before the first use (they are independent)
+    const uint32_t mylen = len_tab[(size_t)k * 256 + t];
+    const uint32_t mycode = code_tab[(size_t)k * 256 + t];
+    const uint64_t total_bytes = comp_off[K], chunk_off = comp_off[k], seg_off = seg_bitoff[seg];
+    uint32_t w[8], wn[8];
+    {
+        const uint32_t first = t * ENC_SPT;
+        const int nvalid = first >= slen ? 0 : (slen - first >= ENC_SPT ? ENC_SPT : (int)(slen - first));
+        load_syms32(p + first, nvalid, wn);
+    }
+    if (total_bytes > out_cap) { if (t == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
 
     // shared memory: [stage | scan scratch] ... [LUT on a 32 KiB boundary of the shared window]
     const uint32_t base_a = enc_smem_u32(smem_raw);
@@ -192,10 +194,9 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
     uint32_t* warp_tot = stage + ENC_STAGE_WORDS;
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (lut_a - base_a));
     const uint32_t stage_a = enc_pin(base_a);
+    uint32_t par = 0;
 
     // codebook of this chunk
-    const uint32_t mylen = len_tab[(size_t)k * 256 + t];
-    const uint32_t mycode = code_tab[(size_t)k * 256 + t];
     const bool wide = __syncthreads_or(mylen > 16);    // block-uniform: codes longer than 16 bits
     uint64_t* lut64 = reinterpret_cast<uint64_t*>(lut);
     if (!wide) {
@@ -211,7 +212,7 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
     __syncthreads();
 
     // absolute bit address of the segment's first bit, and the 16-byte unit it falls in
-    const uint64_t P0 = comp_off[k] * 8 + seg_bitoff[seg];
+    const uint64_t P0 = chunk_off * 8 + seg_off;
     const uint64_t out_addr = reinterpret_cast<uint64_t>(out);
     const uint64_t G0 = out_addr * 8 + P0;
     SegOut O;
@@ -242,12 +243,6 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
     if (!wide) {
         // ---- fast path: 32 symbols per thread per tile, software-pipelined loads ------------------
         const uint32_t lanebase = enc_pin(lut_a | (lane << 2));
-        uint32_t w[8], wn[8];
-        {
-            const uint32_t first = t * ENC_SPT;
-            const int nvalid = first >= slen ? 0 : (slen - first >= ENC_SPT ? ENC_SPT : (int)(slen - first));
-            load_syms32(p + first, nvalid, wn);
-        }
         for (uint32_t tile = 0; tile < slen; tile += ENC_TILE) {
             const uint32_t first = tile + t * ENC_SPT;
             const int nvalid = first >= slen ? 0 : (slen - first >= ENC_SPT ? ENC_SPT : (int)(slen - first));
@@ -261,6 +256,7 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
             // ---- gather + reduce-merge: 8 containers of 4 symbols -------------------------------
             uint32_t ch[8], cl[8], L[8];
             uint32_t tot = 0;
+            const bool ragged = tile + ENC_TILE > slen;         // block-uniform
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const uint32_t x = w[g];
@@ -268,7 +264,7 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
                 uint32_t e1 = enc_lds32(((x >> 1) & 0x7F80u) | lanebase);
                 uint32_t e2 = enc_lds32(((x >> 9) & 0x7F80u) | lanebase);
                 uint32_t e3 = enc_lds32(((x >> 17) & 0x7F80u) | lanebase);
-                if (nvalid != ENC_SPT) {                        // ragged end of the segment
+                if (ragged) {                                   // last tile of a short segment
                     if (g * 4 + 0 >= nvalid) e0 = 0;
                     if (g * 4 + 1 >= nvalid) e1 = 0;
                     if (g * 4 + 2 >= nvalid) e2 = 0;
@@ -285,10 +281,11 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
             }
             // ---- exclusive scan of per-thread bit counts -----------------------------------------
             uint32_t tile_bits;
-            const uint32_t off = O.cur + block_excl_scan(tot, warp_tot, &tile_bits);
+            const uint32_t off = O.cur + block_excl_scan(tot, warp_tot, par, &tile_bits);
+            par ^= 1;
             // ---- every word of this thread's bit range is OR-ed into the staging buffer once -------
             Emit E; E.wp = stage_a + ((off >> 5) << 2); E.f = off & 31; E.a0 = 0;
-            if (nvalid == ENC_SPT) {
+            if (!ragged) {
 #pragma unroll
                 for (int g = 0; g < 8; ++g) emit_put(E, ch[g], cl[g], L[g]);
             } else {
@@ -322,7 +319,8 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
                 c[g] = cc; L[g] = ll; tot += ll;
             }
             uint32_t tile_bits;
-            const uint32_t off = O.cur + block_excl_scan(tot, warp_tot, &tile_bits);
+            const uint32_t off = O.cur + block_excl_scan(tot, warp_tot, par, &tile_bits);
+            par ^= 1;
             Emit E; E.wp = stage_a + ((off >> 5) << 2); E.f = off & 31; E.a0 = 0;
 #pragma unroll
             for (int g = 0; g < 4; ++g) if (L[g]) emit_put(E, (uint32_t)(c[g] >> 32), (uint32_t)c[g], L[g]);
