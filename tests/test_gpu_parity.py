@@ -329,3 +329,39 @@ def test_large_device_resident_roundtrip(codec):
                      lens.data_ptr(), K, back.data_ptr(), n)
     codec.sync()
     assert torch.equal(back, src)
+
+
+# ---- multi-GPU host logic bound to the CUDA codec (world size 1 here; gloo x2 in test_parallel_gloo.py) ----
+@pytest.mark.parametrize("n,chunk", [(1_000_003, 100_000), (3 * MiB + 5, MiB), (0, 4096)])
+def test_sharded_compressor_cuda_binding(hz, codec, n, chunk):
+    import importlib
+    par = importlib.import_module("huffb200.parallel")
+    data = datasets.zipf_stream(n, 4, seed=21) if n else np.zeros(0, np.uint8)
+    sc = par.ShardedCompressor(codec)
+    out = sc.compress(data, n, chunk, "shard.bin", 42)
+    assert out == orc.compress(data, chunk, "shard.bin", 42), "sharded container differs from the reference container"
+    glob = sc.compress(data, n, chunk, "shard.bin", 42, global_codebook=True)
+    assert codec.decompress_buffer(glob) == data.tobytes()          # decoded (and SHA-verified) on the GPU
+    assert orc.decompress(glob) == data.tobytes()                    # and by the reference decoder
+
+
+def test_sharded_two_ranks_one_gpu_equals_reference(hz, codec):
+    """Two chunk ranges coded one after the other on the same GPU and assembled on the host give the
+    reference container (what two ranks on two GPUs produce; ranks never exchange payload data)."""
+    import importlib
+    par = importlib.import_module("huffb200.parallel")
+    n, chunk = 2_500_000, 300_000
+    data = datasets.zipf_stream(n, 5, seed=33)
+    shards = []
+    for r in range(2):
+        lo, hi = par.byte_range(n, chunk, 2, r)
+        payload, off, lens = codec.encode(data[lo:hi], chunk)
+        dig = [bytes(d) for d in codec.sha256_chunks(data[lo:hi], chunk)]
+        K = len(off) - 1
+        shards.append((payload.tobytes(), np.diff(off).astype(np.uint32).tolist(),
+                       [min(chunk, hi - lo - k * chunk) for k in range(K)], dig, lens))
+    sizes = [s for p in shards for s in p[1]]
+    footer = par.write_footer("two.bin", n, 7, chunk, sizes, [o for p in shards for o in p[2]],
+                              [d for p in shards for d in p[3]], np.concatenate([p[4] for p in shards]),
+                              sum(len(p[0]) for p in shards))
+    assert b"".join(p[0] for p in shards) + footer == orc.compress(data, chunk, "two.bin", 7)
