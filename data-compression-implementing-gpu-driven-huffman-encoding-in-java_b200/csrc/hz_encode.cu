@@ -9,41 +9,56 @@
 // offset of the segment is known up front (comp_off[chunk]*8 + seg_bitoff[segment], both derived
 // from the histograms by the codebook kernel), so segments are independent: no look-back chain,
 // no atomics on global memory, no pre-zeroed output.  Per tile of 8192 symbols:
-//   1. one 256-bit coalesced load per thread (32 symbols), issued one tile ahead;
-//   2. codeword gather from a bank-replicated shared-memory LUT (entry [sym][lane]: every lane
-//      reads its own bank, conflict-free for any symbol distribution; the LUT sits on a 32 KiB
-//      boundary of the shared window so that one LOP3 forms the address);
-//   3. reduce-merge: pairs, then quads of codewords are folded into <=64-bit containers in
-//      registers (arXiv 2010.10039 §IV-B);
-//   4. exclusive scan of the per-thread bit counts (warp shuffles + one cross-warp step);
-//   5. shuffle-merge replaced by its shared-memory equivalent: a thread walks its containers
-//      once, assembling the words of its bit range in a register and OR-ing every word into the
-//      staging buffer exactly once (red.shared.or; only the first and last word of a thread are
-//      shared with its neighbours);
-//   6. the completed 16-byte units are byte-swapped to the stream's MSB-first order and written
+//   A. one 256-bit coalesced load per thread (32 symbols), issued one tile ahead; every symbol is
+//      looked up in a bank-replicated shared-memory LUT (entry [sym][lane] = codeword left-aligned
+//      in bits 31.. | length in bits 4..0: every lane reads its own bank, conflict-free for any
+//      symbol distribution) and appended to a 64-bit register accumulator with two funnel shifts
+//      that take both the code bits and the shift amount straight from the LUT entry
+//      (reduce-merge of arXiv 2010.10039 §IV-B, done sequentially in registers).  After every
+//      second symbol the accumulator's completed 32-bit word, if any, goes to the thread's
+//      PRIVATE staging row (17 words, odd stride): the thread's 32 codewords become one
+//      contiguous, word-aligned bit string without knowing where it will land;
+//   S. exclusive scan of the per-thread bit counts (warp shuffles + one cross-warp step, ONE barrier);
+//   B. shuffle-merge: the thread funnel-shifts its private words to its bit offset in the dense
+//      tile buffer.  Interior words are plain stores; the word a thread shares with its
+//      predecessor is completed by a warp shuffle of the predecessor's tail (a thread always owns
+//      >= 32 bits, so at most two threads meet in a word); only the two words at a warp's ends are
+//      OR-ed with red.shared;
+//   F. the completed 16-byte units are byte-swapped to the stream's MSB-first order and written
 //      with aligned 128-bit stores; the trailing partial unit is carried to the next tile.
-// The byte shared by two neighbouring segments is written by the LATER segment, which
-// recomputes the previous segment's last <8 bits from its last 7 symbols.
-// Chunks whose longest code exceeds 16 bits take the "wide" path (2 symbols per container,
-// 8 symbols per thread per tile, unreplicated 64-bit LUT): correct for lengths up to 32, slower.
+// Two barriers per tile.  The byte shared by two neighbouring segments is written by the LATER
+// segment, which recomputes the previous segment's last <8 bits from its last 7 symbols.
+// Chunks whose longest code exceeds 16 bits take the "wide" instantiation (8 symbols per thread
+// per tile, 64-bit LUT entries, a completed-word check after every symbol, every dense word
+// OR-ed): correct for lengths up to 32, slower; it also serves the ragged last tile of a segment.
 #include "hz_common.cuh"
 
 #define ENC_SPT 32                                  // symbols per thread per tile (fast path)
 #define ENC_TILE (HZ_THREADS * ENC_SPT)             // 8192
-#define ENC_STAGE_WORDS (ENC_TILE * 16 / 32 + 16)   // 16 KiB of bits + carry unit + slack
-#define ENC_LUT_BYTES (256 * 32 * 4)                // [sym][lane] uint32: len<<16 | code
-#define ENC_LOW_BYTES (ENC_STAGE_WORDS * 4 + 128)    // staging buffer + scan scratch, below the LUT
-#define ENC_SMEM_BYTES (65536 - 1024)               // the driver reserves the first 1 KiB of the shared window
+#define ENC_WIDE_SPT 8
+#define ENC_WIDE_TILE (HZ_THREADS * ENC_WIDE_SPT)   // 2048
+#define ENC_PRIV_STRIDE 17                          // words per thread: 16 complete + 1 partial / zero pad
+#define ENC_DENSE_WORDS (ENC_TILE * 16 / 32 + 16)   // 16 KiB of bits + carry unit + slack
+#define ENC_LUT_BYTES (256 * 32 * 4)                // [sym][lane] uint32
+#define ENC_OFF_DENSE 0
+#define ENC_OFF_WTOT (ENC_DENSE_WORDS * 4)
+#define ENC_OFF_PRIV (ENC_OFF_WTOT + 64)
+#define ENC_OFF_LUT (ENC_OFF_PRIV + HZ_THREADS * ENC_PRIV_STRIDE * 4)
+#define ENC_SMEM_BYTES (ENC_OFF_LUT + ENC_LUT_BYTES)
 
 static_assert(HZ_SEG_BYTES % ENC_TILE == 0, "a segment is a whole number of tiles");
-static_assert(ENC_LOW_BYTES <= 32768 - 1024, "staging buffer must fit below the LUT");
+static_assert(ENC_WIDE_TILE * 32 / 32 + 16 <= ENC_DENSE_WORDS, "wide tile must fit the dense buffer");
+static_assert(ENC_OFF_LUT % 16 == 0 && ENC_OFF_PRIV % 16 == 0, "alignment");
+static_assert(3 * (ENC_SMEM_BYTES + 1024) <= 228 * 1024, "three CTAs per SM");
 
 __device__ __forceinline__ uint32_t enc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t enc_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 enc_lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void enc_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void enc_or32(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t enc_pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 __device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t s) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s)); return r; }   // s >= 32 -> 0
+__device__ __forceinline__ uint32_t shr_c(uint32_t x, uint32_t s) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s)); return r; }   // s >= 32 -> 0
 
 // 32 symbols (8 little-endian words) starting at q; nvalid of them exist
 __device__ __forceinline__ void load_syms32(const uint8_t* q, int nvalid, uint32_t w[8]) {
@@ -54,10 +69,15 @@ __device__ __forceinline__ void load_syms32(const uint8_t* q, int nvalid, uint32
         const uint32_t* q4 = reinterpret_cast<const uint32_t*>(q);
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = __ldg(q4 + i);
-    } else {
+    } else {                                       // static register indices only: w[] must stay in registers
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = 0;
-        for (int i = 0; i < nvalid; ++i) w[i >> 2] |= (uint32_t)q[i] << (8 * (i & 3));
+        for (int i = 0; i < 8; ++i) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (i * 4 + b < nvalid) v |= (uint32_t)q[i * 4 + b] << (8 * b);
+            w[i] = v;
+        }
     }
 }
 
@@ -80,76 +100,174 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_t
     return before + inc - v;
 }
 
-// Running state of a thread that appends containers to the staging bit buffer.
-struct Emit {
-    uint32_t wp;     // shared address of the current (partially assembled) word
-    uint32_t f;      // bits of that word that precede this thread's next bit
-    uint32_t a0;     // this thread's bits of the current word
-};
-// Append the `len` (1..64) low bits of (ch:cl), MSB first.
-__device__ __forceinline__ void emit_put(Emit& E, uint32_t ch, uint32_t cl, uint32_t len) {
-    // left-align the container in 64 bits
-    const uint32_t s = 64 - len;                               // 0..63
-    uint32_t vh, vl;
-    if (s >= 32) { vh = cl << (s - 32); vl = 0; }
-    else { vh = __funnelshift_l(cl, ch, s); vl = cl << s; }
-    // place it at bit f of the 96-bit window that starts at the current word
-    const uint32_t w0 = vh >> E.f;
-    const uint32_t w1 = __funnelshift_r(vl, vh, E.f);
-    const uint32_t w2 = __funnelshift_r(0u, vl, E.f);
-    E.a0 |= w0;
-    const uint32_t e = E.f + len;
-    if (e >= 32) {
-        enc_or32(E.wp, E.a0); E.a0 = w1;
-        if (e >= 64) { enc_or32(E.wp + 4, w1); E.a0 = w2; }
-    }
-    E.wp += (e >> 5) << 2;
-    E.f = e & 31;
-}
-
 // ---------------------------------------------------------------------------------------------
-// common tail of a tile: flush completed 16-byte units of the staging buffer, carry the rest
+// state of the segment's output: the dense tile buffer holds bits [0, cur); word 0 is the word
+// of the 16-byte unit `unit0` of the output
 // ---------------------------------------------------------------------------------------------
 struct SegOut {
-    uint64_t unit0;      // absolute 16-byte unit index of stage word 0
+    uint64_t unit0;      // absolute 16-byte unit index of dense word 0
     uint64_t own_lo;     // first byte address this CTA writes
-    uint32_t cur;        // bits present in the staging buffer
+    uint32_t cur;        // bits present in the dense buffer
 };
 
-__device__ __forceinline__ void flush_tile(uint32_t* stage, SegOut& O) {
+// phase F: write the completed 16-byte units, clear them, move the partial unit to the front.
+// No barrier inside: the caller's next barrier (the scan of the next tile) orders it against the
+// next phase B.  Thread 0 alone touches unit 0 and the partial unit.
+__device__ __forceinline__ void flush_tile(uint32_t* dense, SegOut& O) {
     const uint32_t t = threadIdx.x;
     const uint32_t full = O.cur >> 7;
     for (uint32_t u = t; u < full; u += HZ_THREADS) {
-        uint4 v = reinterpret_cast<uint4*>(stage)[u];
-        reinterpret_cast<uint4*>(stage)[u] = make_uint4(0, 0, 0, 0);
+        uint4 v = reinterpret_cast<uint4*>(dense)[u];
+        reinterpret_cast<uint4*>(dense)[u] = make_uint4(0, 0, 0, 0);
         v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
         const uint64_t addr = (O.unit0 + u) * 16;
         if (addr >= O.own_lo) {
             *reinterpret_cast<uint4*>(addr) = v;
         } else {                                   // first unit of the segment: the bytes before
-            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};   // own_lo belong to the previous segment
-            for (int b = 0; b < 16; ++b)
-                if (addr + b >= O.own_lo)
-                    *reinterpret_cast<uint8_t*>(addr + b) = (uint8_t)(wv[b >> 2] >> (8 * (b & 3)));
+#pragma unroll                                     // own_lo belong to the previous segment
+            for (int b = 0; b < 16; ++b) {
+                const uint32_t wv = b < 4 ? v.x : (b < 8 ? v.y : (b < 12 ? v.z : v.w));
+                if (addr + b >= O.own_lo) *reinterpret_cast<uint8_t*>(addr + b) = (uint8_t)(wv >> (8 * (b & 3)));
+            }
         }
     }
-    if (full > 0) {                                // move the partial unit to the front
-        __syncthreads();                           // unit 0 has been flushed and cleared
-        if (t < 4) { const uint32_t carry = stage[full * 4 + t]; stage[full * 4 + t] = 0; stage[t] = carry; }
+    if (full > 0) {
+        if (t == 0) {                              // after its own flush of unit 0 (program order)
+            const uint4 c = reinterpret_cast<uint4*>(dense)[full];
+            reinterpret_cast<uint4*>(dense)[full] = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4*>(dense)[0] = c;
+        }
         O.unit0 += full;
         O.cur &= 127;
     }
-    __syncthreads();
 }
 
-__device__ __forceinline__ void flush_tail(const uint32_t* stage, const SegOut& O, bool last_seg) {
+__device__ __forceinline__ void flush_tail(const uint32_t* dense, const SegOut& O, bool last_seg) {
     const uint32_t t = threadIdx.x;
     const uint32_t nb = last_seg ? (O.cur + 7) >> 3 : O.cur >> 3;
     if (t < nb) {
         const uint64_t addr = O.unit0 * 16 + t;
         if (addr >= O.own_lo)
-            *reinterpret_cast<uint8_t*>(addr) = (uint8_t)(stage[t >> 2] >> (24 - 8 * (t & 3)));
+            *reinterpret_cast<uint8_t*>(addr) = (uint8_t)(dense[t >> 2] >> (24 - 8 * (t & 3)));
     }
+}
+
+// phase B, general flavour: OR every non-zero word of the thread's bit string into the dense buffer.
+// priv_a: shared address of the thread's private row (zero word after the last one), n bits.
+__device__ __forceinline__ void merge_or(uint32_t priv_a, uint32_t dense_a, uint32_t off, uint32_t n) {
+    if (n == 0) return;
+    const uint32_t s = off & 31;
+    const uint32_t d = dense_a + ((off >> 5) << 2);
+    const uint32_t nd = (s + n + 31) >> 5;
+    uint32_t prev = 0;
+    for (uint32_t j = 0; j < nd; ++j) {
+        const uint32_t w = enc_lds32(priv_a + 4 * j);
+        const uint32_t o = __funnelshift_r(w, prev, s);
+        prev = w;
+        if (o) enc_or32(d + 4 * j, o);
+    }
+}
+
+// phase B, fast flavour: requires n >= 32 for every thread of the tile (true whenever all 32
+// symbols exist: every present symbol has a code of >= 1 bit), so a dense word holds bits of at
+// most two threads.
+__device__ __forceinline__ void merge_shuffle(uint32_t priv_a, uint32_t dense_a, uint32_t off, uint32_t n, uint32_t lane) {
+    const uint32_t s = off & 31;
+    const uint32_t d = dense_a + ((off >> 5) << 2);
+    const uint32_t e = s + n;
+    const uint32_t nd = (e + 31) >> 5;                   // dense words touched (>= 1)
+    const bool partial = (e & 31) != 0;                  // the last touched word is shared with the successor
+    uint32_t prev = enc_lds32(priv_a);
+    const uint32_t d0 = prev >> s;                       // first word: completed by the predecessor's tail
+    uint32_t tail = 0;
+    if (nd > 1) {
+        const uint32_t jl = nd - 1;
+        uint32_t j = 1;
+#pragma unroll 2
+        for (; j < jl; ++j) {
+            const uint32_t w = enc_lds32(priv_a + 4 * j);
+            enc_sts32(d + 4 * j, __funnelshift_r(w, prev, s));
+            prev = w;
+        }
+        const uint32_t w = enc_lds32(priv_a + 4 * jl);
+        const uint32_t o = __funnelshift_r(w, prev, s);
+        if (partial) tail = o; else enc_sts32(d + 4 * jl, o);
+    } else if (partial) {                                // cannot happen with n >= 32; keeps memory safe
+        tail = d0;
+    }
+    const uint32_t pt = __shfl_up_sync(0xffffffffu, tail, 1);
+    if (nd > 1 || !partial) {
+        if (lane == 0) enc_or32(d, d0); else enc_sts32(d, d0 | pt);
+    }
+    if (lane == 31 && tail) enc_or32(d + 4 * (nd - 1), tail);
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase A, fast path: append the two codewords of LUT entries e0, e1 to (hi:lo); when a 32-bit
+// word completes, store it to the private row.  nb counts bits (low 16 bits exact; the upper
+// bits collect code bits and are never read).
+// ---------------------------------------------------------------------------------------------
+struct Acc { uint32_t hi, lo, nb, ptr; };
+
+__device__ __forceinline__ void acc_pair(Acc& a, uint32_t e0, uint32_t e1) {
+    a.hi = __funnelshift_l(a.lo, a.hi, e0); a.lo = __funnelshift_l(e0, a.lo, e0);
+    a.hi = __funnelshift_l(a.lo, a.hi, e1); a.lo = __funnelshift_l(e1, a.lo, e1);
+    const uint32_t nb2 = a.nb + e0 + e1;
+    if ((a.nb ^ nb2) & 32) {                                 // <= 32 bits were added: at most one word completes
+        enc_sts32(a.ptr, __funnelshift_r(a.lo, a.hi, nb2));  // the 32 bits above the (nb2 & 31) pending ones
+        a.ptr += 4;
+    }
+    a.nb = nb2;
+}
+
+// LUT address of byte j of x: lut[sym][lane]
+template <int J>
+__device__ __forceinline__ uint32_t lut_addr(uint32_t x, uint32_t lanebase) {
+    const uint32_t sym = __byte_perm(x, 0, 0x4440 + J);
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(sym), "r"(lanebase));
+    return a;
+}
+
+template <bool RAGGED>
+__device__ __forceinline__ uint32_t encode_thread32(const uint32_t w[8], int nvalid, uint32_t lanebase, uint32_t priv_a) {
+    Acc a; a.hi = 0; a.lo = 0; a.nb = 0; a.ptr = priv_a;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const uint32_t x = w[g];
+        uint32_t e0 = enc_lds32(lut_addr<0>(x, lanebase));
+        uint32_t e1 = enc_lds32(lut_addr<1>(x, lanebase));
+        uint32_t e2 = enc_lds32(lut_addr<2>(x, lanebase));
+        uint32_t e3 = enc_lds32(lut_addr<3>(x, lanebase));
+        if (RAGGED) {
+            if (g * 4 + 0 >= nvalid) e0 = 0;
+            if (g * 4 + 1 >= nvalid) e1 = 0;
+            if (g * 4 + 2 >= nvalid) e2 = 0;
+            if (g * 4 + 3 >= nvalid) e3 = 0;
+        }
+        acc_pair(a, e0, e1);
+        acc_pair(a, e2, e3);
+    }
+    const uint32_t nbits = a.nb & 0xFFFFu;
+    const uint32_t v = nbits & 31;
+    enc_sts32(a.ptr, shl_c(a.lo, 32 - v));                   // pending bits, left-aligned (0 when v == 0)
+    if (v) enc_sts32(a.ptr + 4, 0);                          // zero word after the last one
+    return nbits;
+}
+
+// phase A, wide path: up to 8 symbols, codes of up to 32 bits
+__device__ __forceinline__ uint32_t encode_thread_wide(const uint8_t* q, int nvalid, const uint2* lut64, uint32_t priv_a) {
+    uint64_t acc = 0;
+    uint32_t v = 0, nbits = 0, ptr = priv_a;
+    for (int i = 0; i < nvalid; ++i) {
+        const uint2 e = lut64[q[i]];                          // {length, right-aligned code}
+        acc = (acc << e.x) | e.y;
+        v += e.x; nbits += e.x;
+        if (v >= 32) { v -= 32; enc_sts32(ptr, (uint32_t)(acc >> v)); ptr += 4; }
+    }
+    enc_sts32(ptr, shl_c((uint32_t)acc, 32 - v));
+    if (v) enc_sts32(ptr + 4, 0);
+    return nbits;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -183,32 +301,27 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
     }
     if (total_bytes > out_cap) { if (t == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
 
-    // shared memory: [stage | scan scratch] ... [LUT on a 32 KiB boundary of the shared window]
+    uint32_t* dense = reinterpret_cast<uint32_t*>(smem_raw + ENC_OFF_DENSE);
+    uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem_raw + ENC_OFF_WTOT);
+    uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + ENC_OFF_LUT);
     const uint32_t base_a = enc_smem_u32(smem_raw);
-    const uint32_t lut_a = (base_a + ENC_LOW_BYTES + 32767u) & ~32767u;
-    if (lut_a + ENC_LUT_BYTES > base_a + ENC_SMEM_BYTES) {      // cannot happen with the 1 KiB driver reservation
-        if (t == 0) hz_set_status(status, HZ_ERR_CUDA);
-        return;
-    }
-    uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* warp_tot = stage + ENC_STAGE_WORDS;
-    uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (lut_a - base_a));
-    const uint32_t stage_a = enc_pin(base_a);
+    const uint32_t dense_a = enc_pin(base_a + ENC_OFF_DENSE);
+    const uint32_t priv_a = enc_pin(base_a + ENC_OFF_PRIV + t * (ENC_PRIV_STRIDE * 4));
     uint32_t par = 0;
 
     // codebook of this chunk
     const bool wide = __syncthreads_or(mylen > 16);    // block-uniform: codes longer than 16 bits
-    uint64_t* lut64 = reinterpret_cast<uint64_t*>(lut);
+    uint2* lut64 = reinterpret_cast<uint2*>(lut);     // wide: [sym] = {length, right-aligned code}
     if (!wide) {
-        const uint32_t e = (mylen << 16) | mycode;
+        const uint32_t e = mylen ? (mycode << (32 - mylen)) | mylen : 0u;
         uint4 e4 = make_uint4(e, e, e, e);
         uint4* row = reinterpret_cast<uint4*>(&lut[t * 32]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) row[i] = e4;
+        for (int i = 0; i < 8; ++i) row[(i + lane) & 7] = e4;   // rotated: a quarter-warp covers all banks
     } else {
-        lut64[t] = ((uint64_t)mylen << 32) | mycode;
+        lut64[t] = make_uint2(mylen, mycode);
     }
-    for (uint32_t i = t; i < ENC_STAGE_WORDS; i += HZ_THREADS) stage[i] = 0;
+    for (uint32_t i = t; i < ENC_DENSE_WORDS / 4; i += HZ_THREADS) reinterpret_cast<uint4*>(dense)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
     // absolute bit address of the segment's first bit, and the 16-byte unit it falls in
@@ -234,15 +347,14 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
                 have += take;
             }
             bits &= (1u << r) - 1;
-            Emit E; E.wp = stage_a + (((O.cur - r) >> 5) << 2); E.f = (O.cur - r) & 31; E.a0 = 0;
-            emit_put(E, 0, bits, r);
-            if (E.a0) enc_or32(E.wp, E.a0);
+            const uint32_t b0 = O.cur - r;                       // r bits inside one byte -> one word
+            enc_or32(dense_a + ((b0 >> 5) << 2), bits << (32 - (b0 & 31) - r));
         }
     }
 
     if (!wide) {
         // ---- fast path: 32 symbols per thread per tile, software-pipelined loads ------------------
-        const uint32_t lanebase = enc_pin(lut_a | (lane << 2));
+        const uint32_t lanebase = enc_pin(base_a + ENC_OFF_LUT + (lane << 2));
         for (uint32_t tile = 0; tile < slen; tile += ENC_TILE) {
             const uint32_t first = tile + t * ENC_SPT;
             const int nvalid = first >= slen ? 0 : (slen - first >= ENC_SPT ? ENC_SPT : (int)(slen - first));
@@ -253,84 +365,40 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
                 const int nv = nf >= slen ? 0 : (slen - nf >= ENC_SPT ? ENC_SPT : (int)(slen - nf));
                 load_syms32(p + nf, nv, wn);
             }
-            // ---- gather + reduce-merge: 8 containers of 4 symbols -------------------------------
-            uint32_t ch[8], cl[8], L[8];
-            uint32_t tot = 0;
             const bool ragged = tile + ENC_TILE > slen;         // block-uniform
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const uint32_t x = w[g];
-                uint32_t e0 = enc_lds32(((x << 7) & 0x7F80u) | lanebase);
-                uint32_t e1 = enc_lds32(((x >> 1) & 0x7F80u) | lanebase);
-                uint32_t e2 = enc_lds32(((x >> 9) & 0x7F80u) | lanebase);
-                uint32_t e3 = enc_lds32(((x >> 17) & 0x7F80u) | lanebase);
-                if (ragged) {                                   // last tile of a short segment
-                    if (g * 4 + 0 >= nvalid) e0 = 0;
-                    if (g * 4 + 1 >= nvalid) e1 = 0;
-                    if (g * 4 + 2 >= nvalid) e2 = 0;
-                    if (g * 4 + 3 >= nvalid) e3 = 0;
-                }
-                const uint32_t l1 = e1 >> 16, l3 = e3 >> 16;
-                const uint32_t p01 = ((e0 & 0xFFFFu) << l1) | (e1 & 0xFFFFu);     // <= 32 bits
-                const uint32_t p23 = ((e2 & 0xFFFFu) << l3) | (e3 & 0xFFFFu);
-                const uint32_t L23 = (e2 >> 16) + l3, L01 = (e0 >> 16) + l1;      // <= 32 each
-                ch[g] = __funnelshift_lc(p01, 0u, L23);                           // (p01 << L23) >> 32
-                cl[g] = shl_c(p01, L23) | p23;
-                L[g] = L01 + L23;
-                tot += L[g];
-            }
-            // ---- exclusive scan of per-thread bit counts -----------------------------------------
+            // A: codewords -> private word-aligned bit string
+            const uint32_t nbits = ragged ? encode_thread32<true>(w, nvalid, lanebase, priv_a)
+                                          : encode_thread32<false>(w, nvalid, lanebase, priv_a);
+            // S: exclusive scan of the per-thread bit counts (one barrier; also orders F of the
+            //    previous tile before B of this one)
             uint32_t tile_bits;
-            const uint32_t off = O.cur + block_excl_scan(tot, warp_tot, par, &tile_bits);
+            const uint32_t off = O.cur + block_excl_scan(nbits, warp_tot, par, &tile_bits);
             par ^= 1;
-            // ---- every word of this thread's bit range is OR-ed into the staging buffer once -------
-            Emit E; E.wp = stage_a + ((off >> 5) << 2); E.f = off & 31; E.a0 = 0;
-            if (!ragged) {
-#pragma unroll
-                for (int g = 0; g < 8; ++g) emit_put(E, ch[g], cl[g], L[g]);
-            } else {
-#pragma unroll
-                for (int g = 0; g < 8; ++g) if (L[g]) emit_put(E, ch[g], cl[g], L[g]);
-            }
-            if (E.a0) enc_or32(E.wp, E.a0);
+            // B: private -> dense
+            if (ragged) merge_or(priv_a, dense_a, off, nbits);
+            else merge_shuffle(priv_a, dense_a, off, nbits, lane);
             __syncthreads();
+            // F: dense -> global
             O.cur += tile_bits;
-            flush_tile(stage, O);
+            flush_tile(dense, O);
         }
     } else {
         // ---- wide path: codes of up to 32 bits, 8 symbols per thread per tile --------------------
-        for (uint32_t tile = 0; tile < slen; tile += HZ_THREADS * 8) {
-            const uint32_t first = tile + t * 8;
-            const int nvalid = first >= slen ? 0 : (slen - first >= 8 ? 8 : (int)(slen - first));
-            uint64_t c[4]; uint32_t L[4];
-            uint32_t tot = 0;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                uint64_t cc = 0; uint32_t ll = 0;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (g * 2 + j < nvalid) {
-                        uint64_t e = lut64[p[first + g * 2 + j]];
-                        uint32_t l = (uint32_t)(e >> 32);
-                        cc = (cc << l) | (uint32_t)e;
-                        ll += l;
-                    }
-                }
-                c[g] = cc; L[g] = ll; tot += ll;
-            }
+        for (uint32_t tile = 0; tile < slen; tile += ENC_WIDE_TILE) {
+            const uint32_t first = tile + t * ENC_WIDE_SPT;
+            const int nvalid = first >= slen ? 0 : (slen - first >= ENC_WIDE_SPT ? ENC_WIDE_SPT : (int)(slen - first));
+            const uint32_t nbits = encode_thread_wide(p + first, nvalid, lut64, priv_a);
             uint32_t tile_bits;
-            const uint32_t off = O.cur + block_excl_scan(tot, warp_tot, par, &tile_bits);
+            const uint32_t off = O.cur + block_excl_scan(nbits, warp_tot, par, &tile_bits);
             par ^= 1;
-            Emit E; E.wp = stage_a + ((off >> 5) << 2); E.f = off & 31; E.a0 = 0;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) if (L[g]) emit_put(E, (uint32_t)(c[g] >> 32), (uint32_t)c[g], L[g]);
-            if (E.a0) enc_or32(E.wp, E.a0);
+            merge_or(priv_a, dense_a, off, nbits);
             __syncthreads();
             O.cur += tile_bits;
-            flush_tile(stage, O);
+            flush_tile(dense, O);
         }
     }
-    flush_tail(stage, O, last_seg);
+    __syncthreads();
+    flush_tail(dense, O, last_seg);
 }
 
 int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
