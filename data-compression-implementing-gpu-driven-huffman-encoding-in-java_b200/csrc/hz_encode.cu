@@ -26,7 +26,9 @@
 //      OR-ed with red.shared;
 //   F. the completed 16-byte units are byte-swapped to the stream's MSB-first order and written
 //      with aligned 128-bit stores; the trailing partial unit is carried to the next tile.
-// Two barriers per tile.  The byte shared by two neighbouring segments is written by the LATER
+// Two barriers per tile.  A CTA is TWO independent 256-thread groups (named barriers), each encoding
+// its own segment of the same chunk; they share only the 32 KiB LUT, which buys 32 resident warps
+// per SM instead of 24.  The byte shared by two neighbouring segments is written by the LATER
 // segment, which recomputes the previous segment's last <8 bits from its last 7 symbols.
 // Chunks whose longest code exceeds 16 bits take the "wide" instantiation (8 symbols per thread
 // per tile, 64-bit LUT entries, a completed-word check after every symbol, every dense word
@@ -37,39 +39,47 @@
 #define ENC_TILE (HZ_THREADS * ENC_SPT)             // 8192
 #define ENC_WIDE_SPT 8
 #define ENC_WIDE_TILE (HZ_THREADS * ENC_WIDE_SPT)   // 2048
+#define ENC_GROUPS 2                                // independent 256-thread groups per CTA
+#define ENC_CTA (ENC_GROUPS * HZ_THREADS)
 #define ENC_PRIV_STRIDE 17                          // words per thread: 16 complete + 1 partial / zero pad
 #define ENC_DENSE_WORDS (ENC_TILE * 16 / 32 + 16)   // 16 KiB of bits + carry unit + slack
 #define ENC_LUT_BYTES (256 * 32 * 4)                // [sym][lane] uint32
-#define ENC_OFF_DENSE 0
-#define ENC_OFF_WTOT (ENC_DENSE_WORDS * 4)
-#define ENC_OFF_PRIV (ENC_OFF_WTOT + 64)
-#define ENC_OFF_LUT (ENC_OFF_PRIV + HZ_THREADS * ENC_PRIV_STRIDE * 4)
-#define ENC_SMEM_BYTES (ENC_OFF_LUT + ENC_LUT_BYTES)
+// per-group region
+#define ENC_G_DENSE 0
+#define ENC_G_WTOT (ENC_DENSE_WORDS * 4)
+#define ENC_G_PRIV (ENC_G_WTOT + 64)
+#define ENC_G_BYTES (ENC_G_PRIV + HZ_THREADS * ENC_PRIV_STRIDE * 4)
+#define ENC_SMEM_BYTES (ENC_LUT_BYTES + ENC_GROUPS * ENC_G_BYTES)
 
 static_assert(HZ_SEG_BYTES % ENC_TILE == 0, "a segment is a whole number of tiles");
 static_assert(ENC_WIDE_TILE * 32 / 32 + 16 <= ENC_DENSE_WORDS, "wide tile must fit the dense buffer");
-static_assert(ENC_OFF_LUT % 16 == 0 && ENC_OFF_PRIV % 16 == 0, "alignment");
-static_assert(3 * (ENC_SMEM_BYTES + 1024) <= 228 * 1024, "three CTAs per SM");
+static_assert(ENC_G_PRIV % 16 == 0 && ENC_G_BYTES % 16 == 0 && ENC_DENSE_WORDS % 4 == 0, "alignment");
+static_assert(2 * (ENC_SMEM_BYTES + 1024) <= 227 * 1024, "two CTAs per SM");
 
 __device__ __forceinline__ uint32_t enc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t enc_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint2 enc_lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void enc_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void enc_or32(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t enc_pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 __device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t s) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s)); return r; }   // s >= 32 -> 0
-__device__ __forceinline__ uint32_t shr_c(uint32_t x, uint32_t s) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s)); return r; }   // s >= 32 -> 0
+// barrier of one 256-thread group (ids 1..ENC_GROUPS; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(uint32_t id) {
+    if (id == 1) asm volatile("bar.sync 1, %0;" ::"n"(HZ_THREADS) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"n"(HZ_THREADS) : "memory");
+}
+static_assert(ENC_GROUPS == 2, "group_sync names two barriers");
 
-// 32 symbols (8 little-endian words) starting at q; nvalid of them exist
-__device__ __forceinline__ void load_syms32(const uint8_t* q, int nvalid, uint32_t w[8]) {
-    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(q) & 31) == 0) {
+// 32 symbols (8 little-endian words) starting at q.  mode: 0 = 32-byte aligned, 1 = 4-byte aligned,
+// 2 = bytes (nvalid of them exist).  Static register indices only: w[] must stay in registers.
+__device__ __forceinline__ void load_syms32(const uint8_t* q, int mode, int nvalid, uint32_t w[8]) {
+    if (mode == 0) {
         asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(q));
-    } else if (nvalid == 32 && (reinterpret_cast<uintptr_t>(q) & 3) == 0) {
+    } else if (mode == 1) {
         const uint32_t* q4 = reinterpret_cast<const uint32_t*>(q);
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = __ldg(q4 + i);
-    } else {                                       // static register indices only: w[] must stay in registers
+    } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             uint32_t v = 0;
@@ -81,10 +91,10 @@ __device__ __forceinline__ void load_syms32(const uint8_t* q, int nvalid, uint32
     }
 }
 
-// Block-wide exclusive scan of `v` with ONE barrier: every warp publishes its total, then each
+// Group-wide exclusive scan of `v` with ONE barrier: every warp publishes its total, then each
 // warp sums the totals of the warps before it.  warp_tot is double-buffered by the caller (`par`).
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_tot, uint32_t par, uint32_t* total) {
-    const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
+__device__ __forceinline__ uint32_t group_excl_scan(uint32_t v, uint32_t* warp_tot, uint32_t par, uint32_t bar_id,
+                                                    uint32_t lane, uint32_t wid, uint32_t* total) {
     uint32_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -93,7 +103,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_t
     }
     uint32_t* wt = warp_tot + par * (HZ_THREADS / 32);
     if (lane == 31) wt[wid] = inc;
-    __syncthreads();
+    group_sync(bar_id);
     const uint32_t x = lane < HZ_THREADS / 32 ? wt[lane] : 0;
     const uint32_t before = __reduce_add_sync(0xffffffffu, lane < wid ? x : 0);
     *total = __reduce_add_sync(0xffffffffu, x);
@@ -101,55 +111,52 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// state of the segment's output: the dense tile buffer holds bits [0, cur); word 0 is the word
-// of the 16-byte unit `unit0` of the output
+// state of the segment's output: the dense tile buffer holds bits [0, cur); dense unit 0 is the
+// 16-byte unit *gptr of the output
 // ---------------------------------------------------------------------------------------------
 struct SegOut {
-    uint64_t unit0;      // absolute 16-byte unit index of dense word 0
-    uint64_t own_lo;     // first byte address this CTA writes
+    uint4* gptr;         // output address of dense unit 0 (16-byte aligned)
+    uint32_t skip;       // leading bytes of that unit owned by the previous segment (first flush only)
     uint32_t cur;        // bits present in the dense buffer
 };
 
 // phase F: write the completed 16-byte units, clear them, move the partial unit to the front.
 // No barrier inside: the caller's next barrier (the scan of the next tile) orders it against the
-// next phase B.  Thread 0 alone touches unit 0 and the partial unit.
-__device__ __forceinline__ void flush_tile(uint32_t* dense, SegOut& O) {
-    const uint32_t t = threadIdx.x;
+// next phase B.  Thread 0 of the group alone touches unit 0 and the partial unit.
+__device__ __forceinline__ void flush_tile(uint32_t* dense, SegOut& O, uint32_t tg) {
     const uint32_t full = O.cur >> 7;
-    for (uint32_t u = t; u < full; u += HZ_THREADS) {
-        uint4 v = reinterpret_cast<uint4*>(dense)[u];
-        reinterpret_cast<uint4*>(dense)[u] = make_uint4(0, 0, 0, 0);
+    uint4* d4 = reinterpret_cast<uint4*>(dense);
+    for (uint32_t u = tg; u < full; u += HZ_THREADS) {
+        uint4 v = d4[u];
+        d4[u] = make_uint4(0, 0, 0, 0);
         v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
-        const uint64_t addr = (O.unit0 + u) * 16;
-        if (addr >= O.own_lo) {
-            *reinterpret_cast<uint4*>(addr) = v;
-        } else {                                   // first unit of the segment: the bytes before
-#pragma unroll                                     // own_lo belong to the previous segment
+        if (u != 0 || O.skip == 0) {
+            O.gptr[u] = v;
+        } else {                                   // first unit of the segment: its first `skip` bytes
+            uint8_t* g = reinterpret_cast<uint8_t*>(O.gptr);   // belong to the previous segment
+#pragma unroll
             for (int b = 0; b < 16; ++b) {
                 const uint32_t wv = b < 4 ? v.x : (b < 8 ? v.y : (b < 12 ? v.z : v.w));
-                if (addr + b >= O.own_lo) *reinterpret_cast<uint8_t*>(addr + b) = (uint8_t)(wv >> (8 * (b & 3)));
+                if (b >= (int)O.skip) g[b] = (uint8_t)(wv >> (8 * (b & 3)));
             }
         }
     }
     if (full > 0) {
-        if (t == 0) {                              // after its own flush of unit 0 (program order)
-            const uint4 c = reinterpret_cast<uint4*>(dense)[full];
-            reinterpret_cast<uint4*>(dense)[full] = make_uint4(0, 0, 0, 0);
-            reinterpret_cast<uint4*>(dense)[0] = c;
+        if (tg == 0) {                             // after its own flush of unit 0 (program order)
+            const uint4 c = d4[full];
+            d4[full] = make_uint4(0, 0, 0, 0);
+            d4[0] = c;
         }
-        O.unit0 += full;
+        O.gptr += full;
         O.cur &= 127;
+        O.skip = 0;
     }
 }
 
-__device__ __forceinline__ void flush_tail(const uint32_t* dense, const SegOut& O, bool last_seg) {
-    const uint32_t t = threadIdx.x;
+__device__ __forceinline__ void flush_tail(const uint32_t* dense, const SegOut& O, bool last_seg, uint32_t tg) {
     const uint32_t nb = last_seg ? (O.cur + 7) >> 3 : O.cur >> 3;
-    if (t < nb) {
-        const uint64_t addr = O.unit0 * 16 + t;
-        if (addr >= O.own_lo)
-            *reinterpret_cast<uint8_t*>(addr) = (uint8_t)(dense[t >> 2] >> (24 - 8 * (t & 3)));
-    }
+    if (tg < nb && tg >= O.skip)
+        reinterpret_cast<uint8_t*>(O.gptr)[tg] = (uint8_t)(dense[tg >> 2] >> (24 - 8 * (tg & 3)));
 }
 
 // phase B, general flavour: OR every non-zero word of the thread's bit string into the dense buffer.
@@ -157,7 +164,7 @@ __device__ __forceinline__ void flush_tail(const uint32_t* dense, const SegOut& 
 __device__ __forceinline__ void merge_or(uint32_t priv_a, uint32_t dense_a, uint32_t off, uint32_t n) {
     if (n == 0) return;
     const uint32_t s = off & 31;
-    const uint32_t d = dense_a + ((off >> 5) << 2);
+    const uint32_t d = dense_a + ((off >> 3) & ~3u);
     const uint32_t nd = (s + n + 31) >> 5;
     uint32_t prev = 0;
     for (uint32_t j = 0; j < nd; ++j) {
@@ -170,35 +177,36 @@ __device__ __forceinline__ void merge_or(uint32_t priv_a, uint32_t dense_a, uint
 
 // phase B, fast flavour: requires n >= 32 for every thread of the tile (true whenever all 32
 // symbols exist: every present symbol has a code of >= 1 bit), so a dense word holds bits of at
-// most two threads.
+// most two threads.  The loop bound is warp-uniform, loads and stores use immediate offsets.
 __device__ __forceinline__ void merge_shuffle(uint32_t priv_a, uint32_t dense_a, uint32_t off, uint32_t n, uint32_t lane) {
     const uint32_t s = off & 31;
-    const uint32_t d = dense_a + ((off >> 5) << 2);
+    const uint32_t d = dense_a + ((off >> 3) & ~3u);
     const uint32_t e = s + n;
-    const uint32_t nd = (e + 31) >> 5;                   // dense words touched (>= 1)
+    const uint32_t nd = (e + 31) >> 5;                   // dense words touched
     const bool partial = (e & 31) != 0;                  // the last touched word is shared with the successor
+    const uint32_t nst = nd - (partial ? 1u : 0u);       // words 0 .. nst-1 are stored by this thread
+    const uint32_t jmax = __reduce_max_sync(0xffffffffu, nst);
     uint32_t prev = enc_lds32(priv_a);
     const uint32_t d0 = prev >> s;                       // first word: completed by the predecessor's tail
-    uint32_t tail = 0;
-    if (nd > 1) {
-        const uint32_t jl = nd - 1;
-        uint32_t j = 1;
-#pragma unroll 2
-        for (; j < jl; ++j) {
-            const uint32_t w = enc_lds32(priv_a + 4 * j);
-            enc_sts32(d + 4 * j, __funnelshift_r(w, prev, s));
-            prev = w;
-        }
-        const uint32_t w = enc_lds32(priv_a + 4 * jl);
+#pragma unroll
+    for (int j = 1; j < ENC_PRIV_STRIDE; ++j) {
+        if (j >= (int)jmax) break;                       // warp-uniform
+        const uint32_t w = enc_lds32(priv_a + 4 * j);    // (lanes past their own row end read stale words: unused)
         const uint32_t o = __funnelshift_r(w, prev, s);
-        if (partial) tail = o; else enc_sts32(d + 4 * jl, o);
-    } else if (partial) {                                // cannot happen with n >= 32; keeps memory safe
-        tail = d0;
+        prev = w;
+        if (j < (int)nst) enc_sts32(d + 4 * j, o);
+    }
+    uint32_t tail = 0;
+    if (partial) {
+        if (nd >= 2) {
+            const uint32_t a = priv_a + 4 * nd;
+            tail = __funnelshift_r(enc_lds32(a - 4), enc_lds32(a - 8), s);
+        } else {
+            tail = d0;                                   // cannot happen with n >= 32; keeps memory safe
+        }
     }
     const uint32_t pt = __shfl_up_sync(0xffffffffu, tail, 1);
-    if (nd > 1 || !partial) {
-        if (lane == 0) enc_or32(d, d0); else enc_sts32(d, d0 | pt);
-    }
+    if (nst) { if (lane == 0) enc_or32(d, d0); else enc_sts32(d, d0 | pt); }
     if (lane == 31 && tail) enc_or32(d + 4 * (nd - 1), tail);
 }
 
@@ -220,7 +228,7 @@ __device__ __forceinline__ void acc_pair(Acc& a, uint32_t e0, uint32_t e1) {
     a.nb = nb2;
 }
 
-// LUT address of byte j of x: lut[sym][lane]
+// LUT address of byte J of x: lut[sym][lane]
 template <int J>
 __device__ __forceinline__ uint32_t lut_addr(uint32_t x, uint32_t lanebase) {
     const uint32_t sym = __byte_perm(x, 0, 0x4440 + J);
@@ -271,70 +279,78 @@ __device__ __forceinline__ uint32_t encode_thread_wide(const uint8_t* q, int nva
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HZ_THREADS, 3)
-encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t spc,
+// grid: K * ceil(spc / ENC_GROUPS) CTAs; CTA b serves chunk b / cpc, its group g the segment
+// (b % cpc) * ENC_GROUPS + g of that chunk
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ENC_CTA, 2)
+encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t spc, uint32_t cpc,
               const uint8_t* __restrict__ len_tab, const uint32_t* __restrict__ code_tab,
               const uint64_t* __restrict__ comp_off, const uint64_t* __restrict__ seg_bitoff,
               uint32_t K, uint8_t* __restrict__ out, uint64_t out_cap, int* status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t t = threadIdx.x, lane = t & 31;
-    const uint32_t seg = blockIdx.x;
-    const uint32_t k = seg / spc, s = seg - k * spc;
+    const uint32_t grp = t / HZ_THREADS, tg = t % HZ_THREADS, wid = tg >> 5;
+    const uint32_t k = blockIdx.x / cpc;
+    const uint32_t s = (blockIdx.x - k * cpc) * ENC_GROUPS + grp;     // segment within the chunk
+    const uint32_t seg = k * spc + s;
 
     // geometry
     const uint64_t cbeg = (uint64_t)k * chunk_bytes;
     const uint64_t clen = n - cbeg < chunk_bytes ? n - cbeg : chunk_bytes;
     const uint64_t sbeg = (uint64_t)s * HZ_SEG_BYTES;
-    if (sbeg >= clen) return;
-    const uint32_t slen = (uint32_t)(clen - sbeg < HZ_SEG_BYTES ? clen - sbeg : HZ_SEG_BYTES);
+    const bool idle = s >= spc || sbeg >= clen;              // group-uniform
+    const uint32_t slen = idle ? 0u : (uint32_t)(clen - sbeg < HZ_SEG_BYTES ? clen - sbeg : HZ_SEG_BYTES);
     const bool last_seg = sbeg + slen >= clen;
     const uint8_t* p = in + cbeg + sbeg;
     // every start-up load is issued before the first use (they are independent)
-    const uint32_t mylen = len_tab[(size_t)k * 256 + t];
-    const uint32_t mycode = code_tab[(size_t)k * 256 + t];
-    const uint64_t total_bytes = comp_off[K], chunk_off = comp_off[k], seg_off = seg_bitoff[seg];
+    const uint32_t mylen = len_tab[(size_t)k * 256 + tg];
+    const uint32_t mycode = code_tab[(size_t)k * 256 + tg];
+    const uint64_t total_bytes = comp_off[K], chunk_off = comp_off[k];
+    const uint64_t seg_off = idle ? 0 : seg_bitoff[seg];
+    const uint8_t* q = p + tg * ENC_SPT;                     // this thread's symbols of tile 0
+    const int lmode = (reinterpret_cast<uintptr_t>(q) & 31) == 0 ? 0 : ((reinterpret_cast<uintptr_t>(q) & 3) == 0 ? 1 : 2);
+    const uint32_t full_tiles = slen / ENC_TILE;
     uint32_t w[8], wn[8];
-    {
-        const uint32_t first = t * ENC_SPT;
-        const int nvalid = first >= slen ? 0 : (slen - first >= ENC_SPT ? ENC_SPT : (int)(slen - first));
-        load_syms32(p + first, nvalid, wn);
-    }
+    if (full_tiles) load_syms32(q, lmode, 32, wn);
     if (total_bytes > out_cap) { if (t == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
 
-    uint32_t* dense = reinterpret_cast<uint32_t*>(smem_raw + ENC_OFF_DENSE);
-    uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem_raw + ENC_OFF_WTOT);
-    uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + ENC_OFF_LUT);
+    uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);
+    uint8_t* gsm = smem_raw + ENC_LUT_BYTES + grp * ENC_G_BYTES;
+    uint32_t* dense = reinterpret_cast<uint32_t*>(gsm + ENC_G_DENSE);
+    uint32_t* warp_tot = reinterpret_cast<uint32_t*>(gsm + ENC_G_WTOT);
     const uint32_t base_a = enc_smem_u32(smem_raw);
-    const uint32_t dense_a = enc_pin(base_a + ENC_OFF_DENSE);
-    const uint32_t priv_a = enc_pin(base_a + ENC_OFF_PRIV + t * (ENC_PRIV_STRIDE * 4));
+    const uint32_t dense_a = enc_pin(base_a + ENC_LUT_BYTES + grp * ENC_G_BYTES + ENC_G_DENSE);
+    const uint32_t priv_a = enc_pin(base_a + ENC_LUT_BYTES + grp * ENC_G_BYTES + ENC_G_PRIV + tg * (ENC_PRIV_STRIDE * 4));
+    const uint32_t bar_id = grp + 1;
     uint32_t par = 0;
 
-    // codebook of this chunk
+    // codebook of this chunk (both groups fill half of every LUT row)
     const bool wide = __syncthreads_or(mylen > 16);    // block-uniform: codes longer than 16 bits
     uint2* lut64 = reinterpret_cast<uint2*>(lut);     // wide: [sym] = {length, right-aligned code}
     if (!wide) {
         const uint32_t e = mylen ? (mycode << (32 - mylen)) | mylen : 0u;
         uint4 e4 = make_uint4(e, e, e, e);
-        uint4* row = reinterpret_cast<uint4*>(&lut[t * 32]);
+        uint4* row = reinterpret_cast<uint4*>(&lut[tg * 32]) + grp * (8 / ENC_GROUPS);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) row[(i + lane) & 7] = e4;   // rotated: a quarter-warp covers all banks
-    } else {
-        lut64[t] = make_uint2(mylen, mycode);
+        for (int i = 0; i < 8 / ENC_GROUPS; ++i) row[(i + lane) & (8 / ENC_GROUPS - 1)] = e4;   // rotated: fewer bank conflicts
+    } else if (grp == 0) {
+        lut64[tg] = make_uint2(mylen, mycode);
     }
-    for (uint32_t i = t; i < ENC_DENSE_WORDS / 4; i += HZ_THREADS) reinterpret_cast<uint4*>(dense)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tg; i < ENC_DENSE_WORDS / 4; i += HZ_THREADS) reinterpret_cast<uint4*>(dense)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    if (idle) return;                                  // from here on only group barriers
 
     // absolute bit address of the segment's first bit, and the 16-byte unit it falls in
     const uint64_t P0 = chunk_off * 8 + seg_off;
     const uint64_t out_addr = reinterpret_cast<uint64_t>(out);
     const uint64_t G0 = out_addr * 8 + P0;
     SegOut O;
-    O.unit0 = G0 >> 7;
+    O.gptr = reinterpret_cast<uint4*>((G0 >> 7) << 4);
     O.cur = (uint32_t)(G0 & 127);
-    O.own_lo = out_addr + (P0 >> 3);
+    O.skip = O.cur >> 3;                                // bytes of the first unit before this segment's first byte
 
     // the leading shared byte: previous segment's last (P0 & 7) bits, from its last 7 symbols
-    if (t == 0) {
+    if (tg == 0) {
         const uint32_t r = (uint32_t)(P0 & 7);
         if (r) {
             uint32_t bits = 0, have = 0;
@@ -354,66 +370,73 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
 
     if (!wide) {
         // ---- fast path: 32 symbols per thread per tile, software-pipelined loads ------------------
-        const uint32_t lanebase = enc_pin(base_a + ENC_OFF_LUT + (lane << 2));
-        for (uint32_t tile = 0; tile < slen; tile += ENC_TILE) {
-            const uint32_t first = tile + t * ENC_SPT;
-            const int nvalid = first >= slen ? 0 : (slen - first >= ENC_SPT ? ENC_SPT : (int)(slen - first));
+        const uint32_t lanebase = enc_pin(base_a + (lane << 2));
+        for (uint32_t i = 0; i < full_tiles; ++i) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = wn[i];
-            if (tile + ENC_TILE < slen) {                       // prefetch the next tile
-                const uint32_t nf = first + ENC_TILE;
-                const int nv = nf >= slen ? 0 : (slen - nf >= ENC_SPT ? ENC_SPT : (int)(slen - nf));
-                load_syms32(p + nf, nv, wn);
-            }
-            const bool ragged = tile + ENC_TILE > slen;         // block-uniform
+            for (int j = 0; j < 8; ++j) w[j] = wn[j];
+            q += ENC_TILE;
+            if (i + 1 < full_tiles) load_syms32(q, lmode, 32, wn);       // prefetch the next tile
             // A: codewords -> private word-aligned bit string
-            const uint32_t nbits = ragged ? encode_thread32<true>(w, nvalid, lanebase, priv_a)
-                                          : encode_thread32<false>(w, nvalid, lanebase, priv_a);
+            const uint32_t nbits = encode_thread32<false>(w, 32, lanebase, priv_a);
             // S: exclusive scan of the per-thread bit counts (one barrier; also orders F of the
             //    previous tile before B of this one)
             uint32_t tile_bits;
-            const uint32_t off = O.cur + block_excl_scan(nbits, warp_tot, par, &tile_bits);
+            const uint32_t off = O.cur + group_excl_scan(nbits, warp_tot, par, bar_id, lane, wid, &tile_bits);
             par ^= 1;
             // B: private -> dense
-            if (ragged) merge_or(priv_a, dense_a, off, nbits);
-            else merge_shuffle(priv_a, dense_a, off, nbits, lane);
-            __syncthreads();
+            merge_shuffle(priv_a, dense_a, off, nbits, lane);
+            group_sync(bar_id);
             // F: dense -> global
             O.cur += tile_bits;
-            flush_tile(dense, O);
+            flush_tile(dense, O, tg);
+        }
+        const uint32_t done = full_tiles * ENC_TILE;
+        if (done < slen) {                                  // ragged last tile (group-uniform)
+            const uint32_t first = done + tg * ENC_SPT;
+            const int nvalid = first >= slen ? 0 : (slen - first >= ENC_SPT ? ENC_SPT : (int)(slen - first));
+            load_syms32(q, nvalid == 32 ? lmode : 2, nvalid, w);
+            const uint32_t nbits = encode_thread32<true>(w, nvalid, lanebase, priv_a);
+            uint32_t tile_bits;
+            const uint32_t off = O.cur + group_excl_scan(nbits, warp_tot, par, bar_id, lane, wid, &tile_bits);
+            par ^= 1;
+            merge_or(priv_a, dense_a, off, nbits);
+            group_sync(bar_id);
+            O.cur += tile_bits;
+            flush_tile(dense, O, tg);
         }
     } else {
         // ---- wide path: codes of up to 32 bits, 8 symbols per thread per tile --------------------
         for (uint32_t tile = 0; tile < slen; tile += ENC_WIDE_TILE) {
-            const uint32_t first = tile + t * ENC_WIDE_SPT;
+            const uint32_t first = tile + tg * ENC_WIDE_SPT;
             const int nvalid = first >= slen ? 0 : (slen - first >= ENC_WIDE_SPT ? ENC_WIDE_SPT : (int)(slen - first));
             const uint32_t nbits = encode_thread_wide(p + first, nvalid, lut64, priv_a);
             uint32_t tile_bits;
-            const uint32_t off = O.cur + block_excl_scan(nbits, warp_tot, par, &tile_bits);
+            const uint32_t off = O.cur + group_excl_scan(nbits, warp_tot, par, bar_id, lane, wid, &tile_bits);
             par ^= 1;
             merge_or(priv_a, dense_a, off, nbits);
-            __syncthreads();
+            group_sync(bar_id);
             O.cur += tile_bits;
-            flush_tile(dense, O);
+            flush_tile(dense, O, tg);
         }
     }
-    __syncthreads();
-    flush_tail(dense, O, last_seg);
+    group_sync(bar_id);
+    flush_tail(dense, O, last_seg, tg);
 }
 
 int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
                const uint8_t* d_len, const uint32_t* d_code, const uint64_t* d_comp_off,
                const uint64_t* d_seg_bitoff, uint8_t* d_out, uint64_t out_cap) {
     if (K == 0) return HZ_OK;
-    uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
-    uint64_t grid = (uint64_t)K * spc;
+    const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
+    const uint32_t cpc = (spc + ENC_GROUPS - 1) / ENC_GROUPS;
+    const uint64_t grid = (uint64_t)K * cpc;
     if (grid > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "too many segments");
     static bool attr_done = false;
     if (!attr_done) {
         HZ_CUDA(ctx, cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
         attr_done = true;
     }
-    HZ_LAUNCH(ctx, "encode", encode_kernel, (unsigned)grid, HZ_THREADS, ENC_SMEM_BYTES,
-              d_in, n, chunk_bytes, spc, d_len, d_code, d_comp_off, d_seg_bitoff, K, d_out, out_cap, ctx->d_status);
+    HZ_LAUNCH(ctx, "encode", encode_kernel, (unsigned)grid, ENC_CTA, ENC_SMEM_BYTES,
+              d_in, n, chunk_bytes, spc, cpc, d_len, d_code, d_comp_off, d_seg_bitoff, K, d_out, out_cap, ctx->d_status);
     return HZ_OK;
 }
