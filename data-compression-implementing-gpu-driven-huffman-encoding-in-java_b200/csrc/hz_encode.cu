@@ -190,24 +190,28 @@ __device__ __forceinline__ void merge_shuffle(uint32_t priv_a, uint32_t dense_a,
     const uint32_t d0 = prev >> s;                       // first word: completed by the predecessor's tail
 #pragma unroll
     for (int j = 1; j < ENC_PRIV_STRIDE; ++j) {
-        if (j >= (int)jmax) break;                       // warp-uniform
+        if ((j & 1) && j >= (int)jmax) break;            // warp-uniform, tested every other word
         const uint32_t w = enc_lds32(priv_a + 4 * j);    // (lanes past their own row end read stale words: unused)
         const uint32_t o = __funnelshift_r(w, prev, s);
         prev = w;
         if (j < (int)nst) enc_sts32(d + 4 * j, o);
     }
-    uint32_t tail = 0;
-    if (partial) {
-        if (nd >= 2) {
-            const uint32_t a = priv_a + 4 * nd;
-            tail = __funnelshift_r(enc_lds32(a - 4), enc_lds32(a - 8), s);
-        } else {
-            tail = d0;                                   // cannot happen with n >= 32; keeps memory safe
-        }
-    }
+    // the word this thread shares with its successor (index nd-1), branch-free; with n >= 32 a
+    // partial last word implies nd >= 2 (otherwise the loads hit a neighbouring row: unused)
+    const uint32_t ta = priv_a + 4 * nd;
+    const uint32_t tw = __funnelshift_r(enc_lds32(ta - 4), enc_lds32(ta - 8), s);
+    const uint32_t tail = partial ? tw : 0u;
     const uint32_t pt = __shfl_up_sync(0xffffffffu, tail, 1);
-    if (nst) { if (lane == 0) enc_or32(d, d0); else enc_sts32(d, d0 | pt); }
-    if (lane == 31 && tail) enc_or32(d + 4 * (nd - 1), tail);
+    // first word: plain store completed with the predecessor's tail; the two words at a warp's
+    // ends are OR-ed (they are shared with another warp)
+    asm volatile("{\n"
+                 ".reg .pred p0, p31;\n"
+                 "setp.eq.u32 p0, %4, 0;\n"
+                 "setp.eq.u32 p31, %4, 31;\n"
+                 "@p0 red.shared.or.b32 [%0], %1;\n"
+                 "@!p0 st.shared.u32 [%0], %2;\n"
+                 "@p31 red.shared.or.b32 [%3], %5;\n"
+                 "}\n" ::"r"(d), "r"(d0), "r"(d0 | pt), "r"(d + 4 * (nd - 1)), "r"(lane), "r"(tail) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -279,11 +283,12 @@ __device__ __forceinline__ uint32_t encode_thread_wide(const uint8_t* q, int nva
 }
 
 // ---------------------------------------------------------------------------------------------
-// grid: K * ceil(spc / ENC_GROUPS) CTAs; CTA b serves chunk b / cpc, its group g the segment
-// (b % cpc) * ENC_GROUPS + g of that chunk
+// grid: K * cpc CTAs; CTA b serves chunk b / cpc, its group g the `mult` consecutive histogram
+// segments starting at ((b % cpc) * ENC_GROUPS + g) * mult of that chunk (the range's first bit
+// offset is seg_bitoff of its first segment)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ENC_CTA, 2)
-encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t spc, uint32_t cpc,
+encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t spc, uint32_t cpc, uint32_t mult,
               const uint8_t* __restrict__ len_tab, const uint32_t* __restrict__ code_tab,
               const uint64_t* __restrict__ comp_off, const uint64_t* __restrict__ seg_bitoff,
               uint32_t K, uint8_t* __restrict__ out, uint64_t out_cap, int* status) {
@@ -291,15 +296,16 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
     const uint32_t t = threadIdx.x, lane = t & 31;
     const uint32_t grp = t / HZ_THREADS, tg = t % HZ_THREADS, wid = tg >> 5;
     const uint32_t k = blockIdx.x / cpc;
-    const uint32_t s = (blockIdx.x - k * cpc) * ENC_GROUPS + grp;     // segment within the chunk
+    const uint32_t s = ((blockIdx.x - k * cpc) * ENC_GROUPS + grp) * mult;   // first histogram segment of this group's range
     const uint32_t seg = k * spc + s;
+    const uint32_t seg_bytes = mult * HZ_SEG_BYTES;                    // this group's range: `mult` histogram segments
 
     // geometry
     const uint64_t cbeg = (uint64_t)k * chunk_bytes;
     const uint64_t clen = n - cbeg < chunk_bytes ? n - cbeg : chunk_bytes;
     const uint64_t sbeg = (uint64_t)s * HZ_SEG_BYTES;
     const bool idle = s >= spc || sbeg >= clen;              // group-uniform
-    const uint32_t slen = idle ? 0u : (uint32_t)(clen - sbeg < HZ_SEG_BYTES ? clen - sbeg : HZ_SEG_BYTES);
+    const uint32_t slen = idle ? 0u : (uint32_t)(clen - sbeg < seg_bytes ? clen - sbeg : seg_bytes);
     const bool last_seg = sbeg + slen >= clen;
     const uint8_t* p = in + cbeg + sbeg;
     // every start-up load is issued before the first use (they are independent)
@@ -371,24 +377,28 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
     if (!wide) {
         // ---- fast path: 32 symbols per thread per tile, software-pipelined loads ------------------
         const uint32_t lanebase = enc_pin(base_a + (lane << 2));
-        for (uint32_t i = 0; i < full_tiles; ++i) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = wn[j];
-            q += ENC_TILE;
-            if (i + 1 < full_tiles) load_syms32(q, lmode, 32, wn);       // prefetch the next tile
-            // A: codewords -> private word-aligned bit string
-            const uint32_t nbits = encode_thread32<false>(w, 32, lanebase, priv_a);
-            // S: exclusive scan of the per-thread bit counts (one barrier; also orders F of the
-            //    previous tile before B of this one)
+        // one full tile: A (codewords -> private word-aligned bit string), S (exclusive scan of the
+        // per-thread bit counts: one barrier, which also orders F of the previous tile before B of
+        // this one), B (private -> dense), barrier, F (dense -> global)
+        auto full_tile = [&](const uint32_t (&x)[8]) {
+            const uint32_t nbits = encode_thread32<false>(x, 32, lanebase, priv_a);
             uint32_t tile_bits;
             const uint32_t off = O.cur + group_excl_scan(nbits, warp_tot, par, bar_id, lane, wid, &tile_bits);
             par ^= 1;
-            // B: private -> dense
             merge_shuffle(priv_a, dense_a, off, nbits, lane);
             group_sync(bar_id);
-            // F: dense -> global
             O.cur += tile_bits;
             flush_tile(dense, O, tg);
+        };
+        // two tiles per iteration: the prefetch registers ping-pong between w and wn
+        for (uint32_t i = 0; i < full_tiles; i += 2) {
+            q += ENC_TILE;
+            if (i + 1 < full_tiles) load_syms32(q, lmode, 32, w);
+            full_tile(wn);
+            if (i + 1 >= full_tiles) break;
+            q += ENC_TILE;
+            if (i + 2 < full_tiles) load_syms32(q, lmode, 32, wn);
+            full_tile(w);
         }
         const uint32_t done = full_tiles * ENC_TILE;
         if (done < slen) {                                  // ragged last tile (group-uniform)
@@ -428,7 +438,11 @@ int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_byte
                const uint64_t* d_seg_bitoff, uint8_t* d_out, uint64_t out_cap) {
     if (K == 0) return HZ_OK;
     const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
-    const uint32_t cpc = (spc + ENC_GROUPS - 1) / ENC_GROUPS;
+    // longer ranges amortise the per-range start-up (LUT build, zeroing, first loads); short
+    // chunks keep them short so that both groups of a CTA have work
+    const uint32_t mult = spc >= 64 ? 4 : (spc >= 16 ? 2 : 1);
+    const uint32_t rpc = (spc + mult - 1) / mult;                      // ranges per chunk
+    const uint32_t cpc = (rpc + ENC_GROUPS - 1) / ENC_GROUPS;
     const uint64_t grid = (uint64_t)K * cpc;
     if (grid > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "too many segments");
     static bool attr_done = false;
@@ -437,6 +451,6 @@ int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_byte
         attr_done = true;
     }
     HZ_LAUNCH(ctx, "encode", encode_kernel, (unsigned)grid, ENC_CTA, ENC_SMEM_BYTES,
-              d_in, n, chunk_bytes, spc, cpc, d_len, d_code, d_comp_off, d_seg_bitoff, K, d_out, out_cap, ctx->d_status);
+              d_in, n, chunk_bytes, spc, cpc, mult, d_len, d_code, d_comp_off, d_seg_bitoff, K, d_out, out_cap, ctx->d_status);
     return HZ_OK;
 }
