@@ -390,14 +390,14 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
             O.cur += tile_bits;
             flush_tile(dense, O, tg);
         };
-        // two tiles per iteration: the prefetch registers ping-pong between w and wn
-        for (uint32_t i = 0; i < full_tiles; i += 2) {
+        // The prefetched words are copied (8 FMA-pipe moves) before the next load is issued: the
+        // copies wait for the previous load, so the new load's scoreboard is not waited on until
+        // the next tile (ping-ponging two register sets made every other tile stall on DRAM).
+        for (uint32_t i = 0; i < full_tiles; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = wn[j];
             q += ENC_TILE;
-            if (i + 1 < full_tiles) load_syms32(q, lmode, 32, w);
-            full_tile(wn);
-            if (i + 1 >= full_tiles) break;
-            q += ENC_TILE;
-            if (i + 2 < full_tiles) load_syms32(q, lmode, 32, wn);
+            if (i + 1 < full_tiles) load_syms32(q, lmode, 32, wn);
             full_tile(w);
         }
         const uint32_t done = full_tiles * ENC_TILE;
