@@ -30,7 +30,7 @@ _EXPORTS = [
     "hz_version", "hz_num_chunks", "hz_histogram", "hz_build_codebooks", "hz_codes_from_lengths", "hz_encode",
     "hz_encode_with_lengths", "hz_decode", "hz_sha256_chunks", "hz_compress_file", "hz_decompress_file",
     "hz_verify_file", "hz_compress_buffer", "hz_decompress_buffer", "hz_free", "hz_prof_enable", "hz_prof_reset",
-    "hz_prof_count", "hz_prof_get", "hz_launch_count",
+    "hz_prof_count", "hz_prof_get", "hz_launch_count", "hz_host_alloc", "hz_host_free",
 ]
 
 

@@ -151,6 +151,18 @@ void hz_destroy(hz_ctx* c) {
     if (c->d_status) cudaFree(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->h_totals) cudaFreeHost(c->h_totals);
+    for (int i = 0; i < hz_ctx::PIPE_SLOTS; ++i) {
+        if (c->pipe_in[i].p) cudaFree(c->pipe_in[i].p);
+        if (c->pipe_out[i].p) cudaFree(c->pipe_out[i].p);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
+    DevBuf* pm[] = {&c->pipe_meta_a, &c->pipe_meta_b, &c->pipe_meta_c, &c->pipe_meta_d};
+    for (DevBuf* b : pm) if (b->p) cudaFree(b->p);
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
     hz_prof_resolve(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -274,6 +286,147 @@ int hz_codes_from_lengths(hz_ctx* ctx, const uint8_t* len, uint32_t K, uint32_t*
     return HZ_OK;
 }
 
+// ---- the pipeline of host buffers -------------------------------------------------------------
+// hz_encode / hz_decode called with HOST input and output move the data in batches of whole chunks
+// through a ring of PIPE_SLOTS device slots: the H2D copy of batch b+1, the kernels of batch b and
+// the D2H copy of batch b-1 run concurrently on three streams (PCIe is full duplex).  Pinned host
+// memory (hz_host_alloc) is needed for the copies to be asynchronous; pageable memory still works,
+// serialised by the driver.
+#define HZ_PIPE_BATCH_BYTES (64ull << 20)
+#define HZ_PIPE_MIN_BYTES (128ull << 20)
+
+static int pipe_init(hz_ctx* ctx) {
+    if (ctx->copy_in) return HZ_OK;
+    HZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    HZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < hz_ctx::PIPE_SLOTS; ++i) {
+        HZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+        HZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+        HZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+    }
+    return HZ_OK;
+}
+static int pipe_totals(hz_ctx* ctx, size_t n) {
+    if (ctx->h_totals_cap >= n) return HZ_OK;
+    if (ctx->h_totals) { cudaFreeHost(ctx->h_totals); ctx->h_totals = nullptr; ctx->h_totals_cap = 0; }
+    cudaError_t e = cudaHostAlloc((void**)&ctx->h_totals, n * sizeof(uint64_t), cudaHostAllocMapped);
+    if (e != cudaSuccess) return hz_cuda_fail(ctx, e, "cudaHostAlloc(totals)");
+    ctx->h_totals_cap = n;
+    return HZ_OK;
+}
+// the batch's payload size, written straight into pinned host memory (no copy-engine queueing)
+__global__ void store_total_kernel(const uint64_t* __restrict__ d_total, uint64_t* __restrict__ h_slot) {
+    *h_slot = *d_total;
+    __threadfence_system();
+}
+
+// histogram -> codebook -> encode of K chunks, everything device-resident
+static int encode_device(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K, const uint8_t* d_fixed,
+                         uint8_t* d_out, uint64_t dcap, uint64_t* d_off, uint8_t* d_len, uint32_t* d_hist) {
+    const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
+    const size_t nseg = (size_t)K * spc;
+    HZ_TRY(hz_reserve(ctx, &ctx->seg_hist, nseg * 1024));
+    HZ_TRY(hz_reserve(ctx, &ctx->code, (size_t)K * 1024));
+    HZ_TRY(hz_reserve(ctx, &ctx->chunk_bits, (size_t)K * 8));
+    HZ_TRY(hz_reserve(ctx, &ctx->comp_size, (size_t)K * 4));
+    HZ_TRY(hz_reserve(ctx, &ctx->seg_bitoff, nseg * 8));
+    HZ_TRY(hzk_histogram(ctx, d_in, n, chunk_bytes, K, (uint32_t*)ctx->seg_hist.p));
+    HZ_TRY(hzk_codebook(ctx, (const uint32_t*)ctx->seg_hist.p, spc, K, d_hist, d_len,
+                        (uint32_t*)ctx->code.p, (uint64_t*)ctx->chunk_bits.p, (uint32_t*)ctx->comp_size.p,
+                        d_off, (uint64_t*)ctx->seg_bitoff.p, d_fixed));
+    HZ_TRY(hzk_encode(ctx, d_in, n, chunk_bytes, K, d_len, (const uint32_t*)ctx->code.p,
+                      d_off, (const uint64_t*)ctx->seg_bitoff.p, d_out, dcap));
+    return HZ_OK;
+}
+
+static int encode_pipelined(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint32_t K, const uint8_t* fixed_len,
+                            uint8_t* out, uint64_t out_cap, uint64_t* comp_off, uint8_t* len_out, uint32_t* hist_out) {
+    const int S = hz_ctx::PIPE_SLOTS;
+    HZ_TRY(pipe_init(ctx));
+    uint64_t per = HZ_PIPE_BATCH_BYTES / chunk_bytes;
+    if (per == 0) per = 1;
+    const uint32_t cpb = (uint32_t)per;                                // chunks per batch
+    const uint32_t nb = (K + cpb - 1) / cpb;
+    const size_t bbytes = (size_t)cpb * chunk_bytes;
+    HZ_TRY(pipe_totals(ctx, nb));
+    for (int i = 0; i < S; ++i) {
+        HZ_TRY(hz_reserve(ctx, &ctx->pipe_in[i], bbytes));
+        HZ_TRY(hz_reserve(ctx, &ctx->pipe_out[i], bbytes + 16));
+    }
+    HZ_TRY(hz_reserve(ctx, &ctx->pipe_meta_a, ((size_t)K + 1) * 8));   // batch-local offsets of every chunk
+    HZ_TRY(hz_reserve(ctx, &ctx->pipe_meta_b, (size_t)K * 256));       // code lengths
+    if (hist_out) HZ_TRY(hz_reserve(ctx, &ctx->pipe_meta_c, (size_t)K * 1024));
+    const void* d_fixed = nullptr;
+    if (fixed_len) {
+        HZ_TRY(hz_reserve(ctx, &ctx->stage_e, 256));
+        HZ_CUDA(ctx, cudaMemcpyAsync(ctx->stage_e.p, fixed_len, 256, cudaMemcpyHostToDevice, ctx->stream));
+        d_fixed = ctx->stage_e.p;
+    }
+    uint64_t* d_off = (uint64_t*)ctx->pipe_meta_a.p;
+    uint8_t* d_len = (uint8_t*)ctx->pipe_meta_b.p;
+    uint32_t* d_hist = hist_out ? (uint32_t*)ctx->pipe_meta_c.p : nullptr;
+    uint64_t* h_tot_dev = nullptr;
+    HZ_CUDA(ctx, cudaHostGetDevicePointer((void**)&h_tot_dev, ctx->h_totals, 0));
+    // make the pipeline streams start after whatever is already queued on the codec's stream
+    HZ_CUDA(ctx, cudaEventRecord(ctx->ev_comp[0], ctx->stream));
+    HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[0], 0));
+    HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[0], 0));
+
+    std::vector<uint64_t> base(nb + 1, 0);
+    uint64_t drained = 0;                      // batches whose payload copy has been issued
+    int rc = HZ_OK;
+    auto drain = [&](uint32_t b) -> int {      // issue the D2H of batch b (its size is known once its kernels ran)
+        const int s = b % S;
+        HZ_CUDA(ctx, cudaEventSynchronize(ctx->ev_comp[s]));
+        const uint64_t tot = ctx->h_totals[b];
+        base[b + 1] = base[b] + tot;
+        if (base[b + 1] > out_cap) return hz_fail(ctx, HZ_ERR_OUT_TOO_SMALL, "payload > capacity %llu", (unsigned long long)out_cap);
+        if (tot) HZ_CUDA(ctx, cudaMemcpyAsync(out + base[b], ctx->pipe_out[s].p, tot, cudaMemcpyDeviceToHost, ctx->copy_out));
+        HZ_CUDA(ctx, cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
+        return HZ_OK;
+    };
+    for (uint32_t b = 0; b < nb && rc == HZ_OK; ++b) {
+        const int s = b % S;
+        const uint32_t k0 = b * cpb, kb = K - k0 < cpb ? K - k0 : cpb;
+        const uint64_t o0 = (uint64_t)k0 * chunk_bytes, nbytes = n - o0 < bbytes ? n - o0 : bbytes;
+        if (b >= (uint32_t)S) {
+            // the slot is reused: its previous batch (b - S) must have been drained
+            while (drained + S <= b && rc == HZ_OK) { rc = drain((uint32_t)drained); ++drained; }
+            if (rc != HZ_OK) break;
+            HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[s], 0));      // kernels of b-S have read the input slot
+            HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0));       // payload of b-S has left the output slot
+        }
+        HZ_CUDA(ctx, cudaMemcpyAsync(ctx->pipe_in[s].p, in + o0, nbytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        HZ_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
+        HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
+        rc = encode_device(ctx, (const uint8_t*)ctx->pipe_in[s].p, nbytes, chunk_bytes, kb, (const uint8_t*)d_fixed,
+                           (uint8_t*)ctx->pipe_out[s].p, bbytes, d_off + k0, d_len + (size_t)k0 * 256,
+                           d_hist ? d_hist + (size_t)k0 * 256 : nullptr);
+        if (rc != HZ_OK) break;
+        HZ_LAUNCH(ctx, "store_total", store_total_kernel, 1, 1, 0, d_off + k0 + kb, h_tot_dev + b);
+        HZ_CUDA(ctx, cudaEventRecord(ctx->ev_comp[s], ctx->stream));
+        // keep one batch of look-ahead: drain batch b-1 while batch b computes
+        while (drained + 1 <= b && rc == HZ_OK) { rc = drain((uint32_t)drained); ++drained; }
+    }
+    while (rc == HZ_OK && drained < nb) { rc = drain((uint32_t)drained); ++drained; }
+    if (rc == HZ_OK) {
+        // metadata: batch-local offsets (rebased on the host), code lengths, histograms
+        std::vector<uint64_t> loc((size_t)K + 1);
+        HZ_CUDA(ctx, cudaMemcpyAsync(loc.data(), d_off, ((size_t)K + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (len_out) HZ_CUDA(ctx, cudaMemcpyAsync(len_out, d_len, (size_t)K * 256, cudaMemcpyDeviceToHost, ctx->stream));
+        if (hist_out) HZ_CUDA(ctx, cudaMemcpyAsync(hist_out, d_hist, (size_t)K * 1024, cudaMemcpyDeviceToHost, ctx->stream));
+        rc = check_status(ctx);
+        if (rc == HZ_OK) {
+            for (uint32_t k = 0; k < K; ++k) comp_off[k] = base[k / cpb] + loc[k];
+            comp_off[K] = base[nb];
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->copy_out);
+    cudaStreamSynchronize(ctx->copy_in);
+    if (rc == HZ_OK && e != cudaSuccess) rc = hz_cuda_fail(ctx, e, "payload copy");
+    return rc;
+}
+
 static int encode_impl(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint8_t* fixed_len,
                        uint8_t* out, uint64_t out_cap, uint64_t* comp_off, uint8_t* len_out, uint32_t* hist_out) {
     if (!ctx || chunk_bytes == 0 || (n && (!in || !out)) || !comp_off)
@@ -288,8 +441,9 @@ static int encode_impl(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chun
         else comp_off[0] = 0;
         return HZ_OK;
     }
-    const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
-    const size_t nseg = (size_t)K * spc;
+    if (n >= HZ_PIPE_MIN_BYTES && !hz_is_device_ptr(in) && !hz_is_device_ptr(out) && !off_dev &&
+        !(len_out && hz_is_device_ptr(len_out)) && !(hist_out && hz_is_device_ptr(hist_out)))
+        return encode_pipelined(ctx, in, n, chunk_bytes, K, fixed_len, out, out_cap, comp_off, len_out, hist_out);
     const void *d_in, *d_fixed = nullptr;
     void *d_out, *d_off, *d_len, *d_hist;
     bool s_out, s_off, s_len, s_hist;
@@ -301,18 +455,8 @@ static int encode_impl(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chun
     HZ_TRY(out_dev(ctx, &ctx->len, len_out, (size_t)K * 256, &d_len, &s_len));
     if (!d_len) { HZ_TRY(hz_reserve(ctx, &ctx->len, (size_t)K * 256)); d_len = ctx->len.p; }
     HZ_TRY(out_dev(ctx, &ctx->chunk_hist, hist_out, (size_t)K * 1024, &d_hist, &s_hist));
-    HZ_TRY(hz_reserve(ctx, &ctx->seg_hist, nseg * 1024));
-    HZ_TRY(hz_reserve(ctx, &ctx->code, (size_t)K * 1024));
-    HZ_TRY(hz_reserve(ctx, &ctx->chunk_bits, (size_t)K * 8));
-    HZ_TRY(hz_reserve(ctx, &ctx->comp_size, (size_t)K * 4));
-    HZ_TRY(hz_reserve(ctx, &ctx->seg_bitoff, nseg * 8));
-
-    HZ_TRY(hzk_histogram(ctx, (const uint8_t*)d_in, n, chunk_bytes, K, (uint32_t*)ctx->seg_hist.p));
-    HZ_TRY(hzk_codebook(ctx, (const uint32_t*)ctx->seg_hist.p, spc, K, (uint32_t*)d_hist, (uint8_t*)d_len,
-                        (uint32_t*)ctx->code.p, (uint64_t*)ctx->chunk_bits.p, (uint32_t*)ctx->comp_size.p,
-                        (uint64_t*)d_off, (uint64_t*)ctx->seg_bitoff.p, (const uint8_t*)d_fixed));
-    HZ_TRY(hzk_encode(ctx, (const uint8_t*)d_in, n, chunk_bytes, K, (const uint8_t*)d_len, (const uint32_t*)ctx->code.p,
-                      (const uint64_t*)d_off, (const uint64_t*)ctx->seg_bitoff.p, (uint8_t*)d_out, dcap));
+    HZ_TRY(encode_device(ctx, (const uint8_t*)d_in, n, chunk_bytes, K, (const uint8_t*)d_fixed, (uint8_t*)d_out, dcap,
+                         (uint64_t*)d_off, (uint8_t*)d_len, (uint32_t*)d_hist));
 
     if (!(s_out || s_off || s_len || s_hist)) return HZ_OK;       // fully device-resident: asynchronous
     // host outputs: offsets first (their total tells how much payload to copy back)
@@ -346,6 +490,73 @@ int hz_encode_with_lengths(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t 
     return encode_impl(ctx, in, n, chunk_bytes, len256, out, out_cap, comp_off, nullptr, nullptr);
 }
 
+static int decode_pipelined(hz_ctx* ctx, const uint8_t* comp, const uint64_t* comp_off, const uint32_t* comp_size,
+                            const uint32_t* orig_size, const uint8_t* len, uint32_t K, uint8_t* out, uint64_t out_cap) {
+    const int S = hz_ctx::PIPE_SLOTS;
+    HZ_TRY(pipe_init(ctx));
+    uint64_t per = HZ_PIPE_BATCH_BYTES / (orig_size[0] ? orig_size[0] : 1);
+    if (per == 0) per = 1;
+    const uint32_t cpb = (uint32_t)(per < K ? per : K);
+    const uint32_t nb = (K + cpb - 1) / cpb;
+    // batch geometry + batch-relative chunk offsets
+    std::vector<uint64_t> rel(K), obase(nb + 1, 0), cbeg(nb), cend(nb);
+    size_t max_in = 0, max_out = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+        const uint32_t k0 = b * cpb, k1 = k0 + cpb < K ? k0 + cpb : K;
+        cbeg[b] = comp_off[k0]; cend[b] = comp_off[k1 - 1] + comp_size[k1 - 1];
+        uint64_t o = 0;
+        for (uint32_t k = k0; k < k1; ++k) { rel[k] = comp_off[k] - cbeg[b]; o += orig_size[k]; }
+        obase[b + 1] = obase[b] + o;
+        if (cend[b] - cbeg[b] > max_in) max_in = cend[b] - cbeg[b];
+        if (o > max_out) max_out = o;
+    }
+    if (obase[nb] > out_cap) return hz_fail(ctx, HZ_ERR_OUT_TOO_SMALL, "decoded size %llu > capacity %llu",
+                                            (unsigned long long)obase[nb], (unsigned long long)out_cap);
+    for (int i = 0; i < S; ++i) {
+        HZ_TRY(hz_reserve(ctx, &ctx->pipe_in[i], max_in + 32));
+        HZ_TRY(hz_reserve(ctx, &ctx->pipe_out[i], max_out + 16));
+    }
+    HZ_TRY(hz_reserve(ctx, &ctx->pipe_meta_a, (size_t)K * 8));
+    HZ_TRY(hz_reserve(ctx, &ctx->pipe_meta_b, (size_t)K * 256));
+    HZ_TRY(hz_reserve(ctx, &ctx->pipe_meta_c, (size_t)K * 4));
+    HZ_TRY(hz_reserve(ctx, &ctx->pipe_meta_d, (size_t)K * 4));
+    uint64_t* d_rel = (uint64_t*)ctx->pipe_meta_a.p;
+    uint8_t* d_len = (uint8_t*)ctx->pipe_meta_b.p;
+    uint32_t* d_csz = (uint32_t*)ctx->pipe_meta_c.p;
+    uint32_t* d_osz = (uint32_t*)ctx->pipe_meta_d.p;
+    HZ_CUDA(ctx, cudaMemcpyAsync(d_rel, rel.data(), (size_t)K * 8, cudaMemcpyHostToDevice, ctx->stream));
+    HZ_CUDA(ctx, cudaMemcpyAsync(d_len, len, (size_t)K * 256, cudaMemcpyHostToDevice, ctx->stream));
+    HZ_CUDA(ctx, cudaMemcpyAsync(d_csz, comp_size, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
+    HZ_CUDA(ctx, cudaMemcpyAsync(d_osz, orig_size, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
+    HZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // `rel` is a local (pageable) vector
+    HZ_CUDA(ctx, cudaEventRecord(ctx->ev_comp[0], ctx->stream));
+    HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[0], 0));
+    HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[0], 0));
+    for (uint32_t b = 0; b < nb; ++b) {
+        const int s = b % S;
+        const uint32_t k0 = b * cpb, kb = K - k0 < cpb ? K - k0 : cpb;
+        const uint64_t cbytes = cend[b] - cbeg[b], obytes = obase[b + 1] - obase[b];
+        if (b >= (uint32_t)S) {
+            HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[s], 0));      // kernels of b-S have read the input slot
+            HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0));       // output of b-S has left its slot
+        }
+        if (cbytes) HZ_CUDA(ctx, cudaMemcpyAsync(ctx->pipe_in[s].p, comp + cbeg[b], cbytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        HZ_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
+        HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
+        HZ_TRY(hzk_decode(ctx, (const uint8_t*)ctx->pipe_in[s].p, cbytes, d_rel + k0, d_csz + k0, d_osz + k0, nullptr,
+                          d_len + (size_t)k0 * 256, kb, (uint8_t*)ctx->pipe_out[s].p, obytes));
+        HZ_CUDA(ctx, cudaEventRecord(ctx->ev_comp[s], ctx->stream));
+        HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[s], 0));
+        if (obytes) HZ_CUDA(ctx, cudaMemcpyAsync(out + obase[b], ctx->pipe_out[s].p, obytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+        HZ_CUDA(ctx, cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
+    }
+    int rc = check_status(ctx);
+    cudaError_t e = cudaStreamSynchronize(ctx->copy_out);
+    cudaStreamSynchronize(ctx->copy_in);
+    if (rc == HZ_OK && e != cudaSuccess) rc = hz_cuda_fail(ctx, e, "output copy");
+    return rc;
+}
+
 int hz_decode(hz_ctx* ctx, const uint8_t* comp, uint64_t comp_bytes, const uint64_t* comp_off,
               const uint32_t* comp_size, const uint32_t* orig_size, const uint64_t* orig_off,
               const uint8_t* len, uint32_t K, uint8_t* out, uint64_t out_cap) {
@@ -353,6 +564,14 @@ int hz_decode(hz_ctx* ctx, const uint8_t* comp, uint64_t comp_bytes, const uint6
         return hz_fail(ctx, HZ_ERR_ARG, "hz_decode: bad argument");
     HZ_CUDA(ctx, cudaSetDevice(ctx->device));
     if (K == 0) return HZ_OK;
+    // host buffers, chunks dense and in order, output back to back: pipeline the copies
+    if (K >= 2 && !orig_off && out_cap >= HZ_PIPE_MIN_BYTES && !hz_is_device_ptr(comp) && !hz_is_device_ptr(out) &&
+        !hz_is_device_ptr(comp_off) && !hz_is_device_ptr(comp_size) && !hz_is_device_ptr(orig_size) && !hz_is_device_ptr(len)) {
+        bool dense = true;
+        for (uint32_t k = 0; k + 1 < K && dense; ++k) dense = comp_off[k + 1] == comp_off[k] + comp_size[k];
+        if (dense && comp_off[K - 1] + comp_size[K - 1] <= comp_bytes)
+            return decode_pipelined(ctx, comp, comp_off, comp_size, orig_size, len, K, out, out_cap);
+    }
     const void *d_comp, *d_coff, *d_csz, *d_osz, *d_ooff = nullptr, *d_len;
     void* d_out; bool s_out;
     HZ_TRY(in_dev(ctx, &ctx->stage_in, comp, comp_bytes, &d_comp));
@@ -370,6 +589,15 @@ int hz_decode(hz_ctx* ctx, const uint8_t* comp, uint64_t comp_bytes, const uint6
     }
     return HZ_OK;
 }
+
+/* pinned host memory for asynchronous (pipelined) transfers */
+int hz_host_alloc(void** p, size_t bytes) {
+    if (!p) return HZ_ERR_ARG;
+    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; return HZ_ERR_NOMEM; }
+    return HZ_OK;
+}
+void hz_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int hz_sha256_chunks(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint8_t* digests) {
     if (!ctx || chunk_bytes == 0 || !digests || (n && !in)) return hz_fail(ctx, HZ_ERR_ARG, "hz_sha256_chunks: bad argument");

@@ -37,6 +37,12 @@ struct hz_ctx {
     DevBuf stage_in, stage_out, stage_a, stage_b, stage_c, stage_d, stage_e;
     DevBuf dec_meta, dec_rec, dec_seqcnt, dec_misc, dec_tables;
     void* h_pin = nullptr; size_t h_pin_cap = 0;
+    // host-buffer pipeline (hz_encode / hz_decode with host pointers): copy streams, ring of device slots
+    static const int PIPE_SLOTS = 3;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[PIPE_SLOTS] = {}, ev_comp[PIPE_SLOTS] = {}, ev_out[PIPE_SLOTS] = {};
+    DevBuf pipe_in[PIPE_SLOTS], pipe_out[PIPE_SLOTS], pipe_meta_a, pipe_meta_b, pipe_meta_c, pipe_meta_d;
+    uint64_t* h_totals = nullptr; size_t h_totals_cap = 0;     // pinned, written by the device (zero-copy)
     // profiling
     // profiling: event pairs are recorded without synchronising and resolved lazily
     bool prof = false;

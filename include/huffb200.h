@@ -112,6 +112,14 @@ int hz_decode(hz_ctx* ctx, const uint8_t* comp, uint64_t comp_bytes, const uint6
               const uint32_t* comp_size, const uint32_t* orig_size, const uint64_t* orig_off,
               const uint8_t* len, uint32_t K, uint8_t* out, uint64_t out_cap);
 
+/* Page-locked host memory.  hz_encode / hz_decode called with HOST input and output of >= 128 MiB
+ * pipeline the transfers in batches of whole chunks (H2D of batch b+1, kernels of batch b and D2H
+ * of batch b-1 overlap on three streams); the copies are only asynchronous from page-locked
+ * memory.  A Java host wraps the returned address in a MemorySegment (replaces the byte[] chunk
+ * buffers of cpu/CpuCompressionService.java:214-224).                                            */
+int hz_host_alloc(void** p, size_t bytes);
+void hz_host_free(void* p);
+
 /* SHA-256 of each chunk: digests is K x 32 bytes.  Replaces ChecksumUtil.computeSha256 per chunk
  * (util/ChecksumUtil.java:11-27; cpu/CpuCompressionService.java:226-228, :536).                 */
 int hz_sha256_chunks(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint8_t* digests);

@@ -365,3 +365,34 @@ def test_sharded_two_ranks_one_gpu_equals_reference(hz, codec):
                               [d for p in shards for d in p[3]], np.concatenate([p[4] for p in shards]),
                               sum(len(p[0]) for p in shards))
     assert b"".join(p[0] for p in shards) + footer == orc.compress(data, chunk, "two.bin", 7)
+
+
+# ---- host-buffer pipeline (batches of chunks over three streams) --------------------------------
+@pytest.mark.parametrize("n,chunk,H", [(160 * MiB + 12345, 4 * MiB, 4), (200 * MiB, 16 * MiB, 6), (130 * MiB + 1, 64 * 1024, 2)])
+def test_pipelined_host_buffers_match_device_path(codec, n, chunk, H):
+    """hz_encode / hz_decode with HOST buffers >= 128 MiB take the pipelined path; the result must be
+    byte-identical to the device-resident single-shot path, and chunks must match the oracle."""
+    import torch
+    data = datasets.zipf_stream(n, H, seed=n & 0xFFFF)
+    K = (n + chunk - 1) // chunk
+    # pipelined: numpy (pageable host) buffers
+    payload, off, lens, hist = codec.encode(data, chunk, want_hist=True)
+    # single shot: device buffers
+    d_in = torch.from_numpy(data).cuda()
+    d_out = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+    d_off = torch.zeros(K + 1, dtype=torch.int64, device="cuda")
+    d_len = torch.zeros((K, 256), dtype=torch.uint8, device="cuda")
+    codec.encode_raw(d_in.data_ptr(), n, chunk, d_out.data_ptr(), n, d_off.data_ptr(), d_len.data_ptr(), None)
+    codec.sync()
+    roff = d_off.cpu().numpy().astype(np.uint64)
+    assert np.array_equal(off, roff), "chunk offsets"
+    assert np.array_equal(lens, d_len.cpu().numpy()), "code lengths"
+    assert np.array_equal(payload, d_out[: int(roff[K])].cpu().numpy()), "payload bytes"
+    for k in (0, K // 2, K - 1):                          # oracle spot checks
+        ref, ln, _ = orc.encode_chunk(data[k * chunk:(k + 1) * chunk])
+        assert np.array_equal(payload[int(off[k]):int(off[k + 1])], ref) and np.array_equal(lens[k], ln.astype(np.uint8))
+        assert np.array_equal(hist[k].astype(np.uint64), orc.histogram(data[k * chunk:(k + 1) * chunk]))
+    sizes = np.diff(off).astype(np.uint32)
+    orig = np.array([min(chunk, n - k * chunk) for k in range(K)], dtype=np.uint32)
+    back = codec.decode(payload, off[:-1], sizes, orig, lens)       # pipelined decode
+    assert np.array_equal(back, data), "round trip"
