@@ -31,10 +31,14 @@
 //             12 bits and the first codeword's length (counting pass).  A prefix that starts a
 //             code longer than 12 bits has n = 1 and its length when every code under the prefix
 //             has the same length, else n = 0 with ltot = shortest, l0 = longest candidate.
-//   wlut u32: s0 | s1<<8 | s2<<16 | n<<24 | ltot<<28   up to three symbols per lookup;
-//             n = 0: long code, bits 0-5 shortest / bits 6-11 longest candidate length (0 = no code).
+//   wlut u32x2: .x = s0 | s1<<8 | s2<<16 | s3<<24 (up to four symbols per lookup), .y = ltot | 8n<<16:
+//             ONE add of .y to the write pass's packed counter (stream bit position | output bits<<16)
+//             advances both.  .y bit 31: long code / no code, .x = shortest | longest<<6 candidate length;
+//             .y bits 31+30: every code under the prefix has length .y & 63 and its symbol is
+//             sorted[.x + (first .y & 63 stream bits)] (the sorted-symbol array is the second level).
 // Codes whose used lengths are all equal never self-synchronise but need no synchronisation
 // either: entries are computed arithmetically.
+#include <cstdlib>
 #include "hz_common.cuh"
 
 #define DT 256
@@ -45,7 +49,7 @@
 #define DEC_SEQ_BITS (DT * DEC_SUB_BITS)
 #define DEC_OVERLAP_BITS 128
 #define DEC_OVERLAP_BYTES 16
-#define DEC_SEQ_PER_CTA 8
+#define DEC_SEQ_PER_CTA 12                    // divisible by 1, 2 and 3 write groups
 #define DEC_SUBS_PER_CTA (DT * DEC_SEQ_PER_CTA)
 #define LUTB 12
 #define LUTN (1 << LUTB)
@@ -55,7 +59,10 @@
 #define DEC_WIN_MIN 2304                      // per-warp output window of the write kernel (runtime sized)
 #define DEC_WIN_MAX 9216
 #define DEC_NO_TABLE 0xFFFFFFFFu
-#define DEC_TABLE_BYTES (LUTN * 4 + LUTN * 2 + 1024)
+#define DEC_TAB_W 0                              // uint2 wlut[LUTN]
+#define DEC_TAB_S (LUTN * 8)                    // uint16 slut[LUTN]
+#define DEC_TAB_AUX (LUTN * 8 + LUTN * 2)       // DecAux
+#define DEC_TABLE_BYTES (DEC_TAB_AUX + 1024)
 
 struct __align__(16) DecAux {
     uint64_t lim[34];          // exclusive upper bound of the left-justified (32-bit) codes of each length
@@ -80,8 +87,11 @@ __device__ __forceinline__ uint32_t long_len(const DecAux& A, uint32_t v, uint32
     return (uint64_t)v < A.lim[l] ? l : 0;
 }
 
+// barrier of the DT threads that build a table (threads 0..DT-1 of the CTA; the write kernel's CTA is larger)
+__device__ __forceinline__ void bt_sync() { asm volatile("bar.sync 1, %0;" ::"n"(DT) : "memory"); }
+
 template <bool WANT_W, bool WANT_S>
-__device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* __restrict__ slut,
+__device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __restrict__ slut,
                              uint8_t* __restrict__ scratch, const uint8_t* __restrict__ len_k) {
     uint16_t* base = reinterpret_cast<uint16_t*>(scratch);                // [LUTN] sym | len<<8
     uint16_t* lj = reinterpret_cast<uint16_t*>(scratch + LUTN * 2);       // [256] left-justified codes (len<=12)
@@ -95,17 +105,17 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
     if (l > 32) l = 33;
     A.len[t] = (uint8_t)l;
     for (uint32_t i = t; i < 8 * 34; i += DT) cntw[i] = 0;
-    __syncthreads();
+    bt_sync();
     const uint32_t same = __match_any_sync(0xffffffffu, l);
     const uint32_t rank_w = __popc(same & ((1u << lane) - 1));
     if (rank_w == 0) cntw[wid * 34 + l] = __popc(same);
-    __syncthreads();
+    bt_sync();
     if (t < 34) {
         uint32_t c = 0;
         for (int w = 0; w < 8; ++w) c += cntw[w * 34 + t];
         count[t] = t == 0 ? 0 : c;
     }
-    __syncthreads();
+    bt_sync();
     if (t == 0) {
         uint32_t c = 0, o = 0;
         int mx = 0, mn = 0;
@@ -123,7 +133,7 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
         A.uniform = (mx > 0 && mx == mn) ? mx : 0;
         A.bad = (count[33] != 0) || (kraft > (1ull << 32));
     }
-    __syncthreads();
+    bt_sync();
     if (A.bad) return;
     if (l >= 1 && l <= 32) {
         uint32_t rank = rank_w;
@@ -132,7 +142,7 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
         A.sorted[pos] = (uint8_t)t;
         if (l <= LUTB) { lj[pos] = (uint16_t)((first[l] + rank) << (LUTB - l)); ljl[pos] = (uint8_t)l; }
     }
-    __syncthreads();
+    bt_sync();
     // single-symbol table: thread t fills entries [16t, 16t+16)
     const uint32_t n12 = offs[LUTB + 1];          // symbols with length <= LUTB, sorted by code value
     {
@@ -154,12 +164,13 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
             base[x] = e;
         }
     }
-    __syncthreads();
+    bt_sync();
     // multi-symbol tables
     const uint32_t maxlen = (uint32_t)A.maxlen;
     for (uint32_t x = t * 16; x < t * 16 + 16; ++x) {
         const uint32_t e0 = base[x];
-        uint32_t we = 0, se = 0;
+        uint2 we = make_uint2(0u, 0x80000000u);
+        uint32_t se = 0;
         if (e0) {
             const uint32_t l0 = e0 >> 8;
             uint32_t syms = e0 & 0xFF, used = l0, n = 1, wtot = l0, wn = 1, cur = x, lprev = l0;
@@ -169,10 +180,10 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
                 if (!e) break;
                 const uint32_t le = e >> 8;
                 if (used + le > LUTB) break;
-                if (n < 3) { syms |= (e & 0xFF) << (8 * n); wtot = used + le; wn = n + 1; }
+                if (n < 4) { syms |= (e & 0xFF) << (8 * n); wtot = used + le; wn = n + 1; }
                 used += le; ++n; lprev = le;
             }
-            we = syms | (wn << 24) | (wtot << 28);
+            we = make_uint2(syms, wtot | (wn << 19));
             se = used | (n << 6) | (l0 << 10);
         } else if (maxlen > LUTB) {
             // the prefix starts a code longer than LUTB bits (or no code): candidate lengths at both ends
@@ -181,21 +192,23 @@ __device__ void build_tables(DecAux& A, uint32_t* __restrict__ wlut, uint16_t* _
             if (lmin) {
                 uint32_t lmax = long_len(A, vhi, lmin, maxlen);
                 if (!lmax) lmax = maxlen;
-                we = lmin | (lmax << 6);
+                we.x = lmin | (lmax << 6);
+                // every code under this prefix has the same length: `sorted` is the second-level table
+                if (lmin == lmax) we = make_uint2((uint32_t)A.symbase[lmin], 0xC0000000u | lmin | (8u << 16));
                 se = lmin == lmax ? (lmin | (1u << 6) | (lmin << 10)) : (lmin | (lmax << 10));
             }
         }
         if (WANT_W) wlut[x] = we;
         if (WANT_S) slut[x] = (uint16_t)se;
     }
-    __syncthreads();
+    bt_sync();
 }
 
-// copy `bytes` (multiple of 16) from global to shared with all DT threads
+// copy `bytes` (multiple of 16) from global to shared with all threads of the CTA
 __device__ __forceinline__ void copy_g2s16(void* dst, const void* src, uint32_t bytes) {
     const uint4* s = reinterpret_cast<const uint4*>(src);
     uint4* d = reinterpret_cast<uint4*>(dst);
-    for (uint32_t i = threadIdx.x; i < bytes / 16; i += DT) d[i] = s[i];
+    for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = s[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -259,7 +272,6 @@ __device__ __forceinline__ uint32_t find_chunk(const uint32_t* __restrict__ cta_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DT)
 dec_tables_kernel(const uint8_t* __restrict__ len_tab, DecPlan P, uint8_t* __restrict__ tables, int* status) {
-    __shared__ __align__(16) uint32_t wlut[LUTN];
     __shared__ __align__(16) uint16_t slut[LUTN];
     __shared__ __align__(16) uint8_t scratch[DEC_BUILD_SCRATCH];
     __shared__ __align__(16) uint8_t aux_raw[1024];
@@ -267,13 +279,12 @@ dec_tables_kernel(const uint8_t* __restrict__ len_tab, DecPlan P, uint8_t* __res
     const uint32_t ti = P.tab_idx[k];
     if (ti == DEC_NO_TABLE) return;
     DecAux& A = *reinterpret_cast<DecAux*>(aux_raw);
-    build_tables<true, true>(A, wlut, slut, scratch, len_tab + (size_t)k * 256);
-    if (A.bad && threadIdx.x == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS);
     uint8_t* dst = tables + (size_t)ti * DEC_TABLE_BYTES;
+    build_tables<true, true>(A, reinterpret_cast<uint2*>(dst + DEC_TAB_W), slut, scratch, len_tab + (size_t)k * 256);
+    if (A.bad && threadIdx.x == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS);
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < LUTN * 4 / 16; i += DT) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<uint4*>(wlut)[i];
-    for (uint32_t i = threadIdx.x; i < LUTN * 2 / 16; i += DT) reinterpret_cast<uint4*>(dst + LUTN * 4)[i] = reinterpret_cast<uint4*>(slut)[i];
-    for (uint32_t i = threadIdx.x; i < 1024 / 16; i += DT) reinterpret_cast<uint4*>(dst + LUTN * 6)[i] = reinterpret_cast<uint4*>(aux_raw)[i];
+    for (uint32_t i = threadIdx.x; i < LUTN * 2 / 16; i += DT) reinterpret_cast<uint4*>(dst + DEC_TAB_S)[i] = reinterpret_cast<uint4*>(slut)[i];
+    for (uint32_t i = threadIdx.x; i < 1024 / 16; i += DT) reinterpret_cast<uint4*>(dst + DEC_TAB_AUX)[i] = reinterpret_cast<uint4*>(aux_raw)[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -340,10 +351,10 @@ __device__ __forceinline__ void stage_issue(uint8_t* stage, uint64_t* bar, const
 
 // after the bulk copy landed: bytes outside the chunk read as zero (TableBasedHuffmanDecoder.java:204-208),
 // chunk bytes the 16-byte aligned copy could not deliver are fetched one by one.  All DT threads.
-__device__ __forceinline__ void stage_fixup(uint8_t* stage, const StageGeom& g) {
+__device__ __forceinline__ void stage_fixup(uint8_t* stage, const StageGeom& g, uint32_t tg) {
     const int64_t glo = g.vlo > g.tlo ? g.vlo : g.tlo, ghi = g.vhi < g.thi ? g.vhi : g.thi;   // good bytes
     if (glo == 0 && ghi == DEC_STAGE_BYTES) return;
-    for (int64_t u = threadIdx.x; u < DEC_STAGE_BYTES / 16; u += DT) {
+    for (int64_t u = tg; u < DEC_STAGE_BYTES / 16; u += DT) {
         const int64_t b0 = u * 16;
         if (b0 >= glo && b0 + 16 <= ghi) continue;
         for (int64_t b = b0; b < b0 + 16; ++b) {
@@ -361,6 +372,7 @@ __device__ __forceinline__ void stage_fixup(uint8_t* stage, const StageGeom& g) 
 // shared-state-space accesses with 32-bit addresses (keeps the hot loops free of generic->shared
 // window arithmetic)
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -443,8 +455,8 @@ dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uin
         build_tables<false, true>(A, nullptr, S.slut, S.stage[0], len_tab + (size_t)k * 256);
     } else {
         const uint8_t* tb = tables + (size_t)ti * DEC_TABLE_BYTES;
-        copy_g2s16(S.slut, tb + LUTN * 4, LUTN * 2);
-        copy_g2s16(S.aux, tb + LUTN * 6, 1024);
+        copy_g2s16(S.slut, tb + DEC_TAB_S, LUTN * 2);
+        copy_g2s16(S.aux, tb + DEC_TAB_AUX, 1024);
     }
     __syncthreads();
     if (A.bad) { if (t == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS); return; }
@@ -467,7 +479,7 @@ dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uin
             stage_issue(S.stage[b ^ 1], &S.bar[b ^ 1], stage_geom(comp, comp_bytes, coff, csize, sq + 1));
         const StageGeom g = stage_geom(comp, comp_bytes, coff, csize, sq);
         mbar_wait(&S.bar[b], (q >> 1) & 1);
-        stage_fixup(S.stage[b], g);
+        stage_fixup(S.stage[b], g, t);
         __syncthreads();
 
         BitRd r;
@@ -597,8 +609,8 @@ dec_fix_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ co
         }
         if (__syncthreads_or(any)) {
             const uint8_t* tb = tables + (size_t)P.tab_idx[k] * DEC_TABLE_BYTES;
-            copy_g2s16(slut, tb + LUTN * 4, LUTN * 2);
-            copy_g2s16(aux_raw, tb + LUTN * 6, 1024);
+            copy_g2s16(slut, tb + DEC_TAB_S, LUTN * 2);
+            copy_g2s16(aux_raw, tb + DEC_TAB_AUX, 1024);
             __syncthreads();
             const DecAux& A = *reinterpret_cast<const DecAux*>(aux_raw);
             if (A.bad) return;
@@ -667,48 +679,65 @@ dec_fix_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ co
 // ---------------------------------------------------------------------------------------------
 // write kernel
 // ---------------------------------------------------------------------------------------------
-struct WriteSmem {                       // followed by DT/32 output windows of win_bytes each
-    __align__(16) uint8_t stage[DEC_STAGE_BYTES];
-    __align__(16) uint32_t wlut[LUTN];
+// The write kernel's CTA is `groups` (1..3) independent 256-thread groups that share the chunk's
+// lookup table (32 KiB) and take the CTA's sequences round-robin; each group has its own staging
+// buffer, mbarrier, named barrier and per-warp output windows.  Sharing the table is what lets
+// 24 warps be resident per SM.
+struct WriteShared {
+    __align__(16) uint2 wlut[LUTN];
     __align__(16) uint8_t aux[1024];
-    __align__(16) uint32_t headw[DT];    // a lane's first (partial) word is parked here until the warp is done
-    __align__(8) uint64_t bar;
-    uint32_t s_warp[DT / 32 + 1];
     uint32_t s_k;
 };
-#define DEC_WRITE_FIXED ((sizeof(WriteSmem) + 15) & ~(size_t)15)
+struct WriteGroup {                      // followed by DT/32 output windows of win_bytes each
+    __align__(16) uint8_t stage[DEC_STAGE_BYTES];
+    __align__(8) uint64_t bar;
+    uint32_t s_warp[DT / 32 + 1];
+};
+#define DEC_WRITE_SHARED ((sizeof(WriteShared) + 15) & ~(size_t)15)
+#define DEC_WRITE_GROUP ((sizeof(WriteGroup) + 15) & ~(size_t)15)
+#define DEC_WRITE_MAX_GROUPS 3
 
-__global__ void __launch_bounds__(DT)
+__device__ __forceinline__ void wgroup_sync(uint32_t grp) {
+    if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(DT) : "memory");
+    else if (grp == 1) asm volatile("bar.sync 2, %0;" ::"n"(DT) : "memory");
+    else asm volatile("bar.sync 3, %0;" ::"n"(DT) : "memory");
+}
+
+__global__ void __launch_bounds__(DT * DEC_WRITE_MAX_GROUPS)
 dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uint64_t* __restrict__ comp_off,
                  const uint32_t* __restrict__ comp_size, const uint32_t* __restrict__ orig_size,
                  const uint8_t* __restrict__ len_tab, uint32_t K, DecPlan P, const uint8_t* __restrict__ tables,
                  const uint32_t* __restrict__ rec, const uint32_t* __restrict__ seqoff,
                  uint8_t* __restrict__ out, uint64_t out_cap, uint32_t win_bytes, int* status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    WriteSmem& S = *reinterpret_cast<WriteSmem*>(smem_raw);
-    const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    WriteShared& W = *reinterpret_cast<WriteShared*>(smem_raw);
+    const uint32_t grp = threadIdx.x / DT, ngrp = blockDim.x / DT;
+    const uint32_t t = threadIdx.x % DT, lane = t & 31, wid = t >> 5;             // thread index within the group
+    const size_t gbytes = DEC_WRITE_GROUP + (DT / 32) * (size_t)win_bytes;
+    uint8_t* gsm = smem_raw + DEC_WRITE_SHARED + grp * gbytes;
+    WriteGroup& S = *reinterpret_cast<WriteGroup*>(gsm);
     if (blockIdx.x >= P.cta_base[K]) return;
     if (t == 0) {
-        S.s_k = find_chunk(P.cta_base, K, blockIdx.x);
+        if (grp == 0) W.s_k = find_chunk(P.cta_base, K, blockIdx.x);
         mbar_init(&S.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint32_t k = S.s_k;
+    const uint32_t k = W.s_k;
     const uint32_t osize = orig_size[k];
     const uint64_t ooff = P.orig_off[k];
-    if (ooff + osize > out_cap) { if (t == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
-    DecAux& A = *reinterpret_cast<DecAux*>(S.aux);
+    if (ooff + osize > out_cap) { if (threadIdx.x == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
+    DecAux& A = *reinterpret_cast<DecAux*>(W.aux);
     const uint32_t ti = P.tab_idx[k];
     if (ti == DEC_NO_TABLE) {
-        build_tables<true, false>(A, S.wlut, nullptr, S.stage, len_tab + (size_t)k * 256);
+        if (grp == 0) build_tables<true, false>(A, W.wlut, nullptr, S.stage, len_tab + (size_t)k * 256);
     } else {
         const uint8_t* tb = tables + (size_t)ti * DEC_TABLE_BYTES;
-        copy_g2s16(S.wlut, tb, LUTN * 4);
-        copy_g2s16(S.aux, tb + LUTN * 6, 1024);
+        copy_g2s16(W.wlut, tb + DEC_TAB_W, LUTN * 8);
+        copy_g2s16(W.aux, tb + DEC_TAB_AUX, 1024);
     }
     __syncthreads();
-    if (A.bad) { if (t == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS); return; }
+    if (A.bad) { if (threadIdx.x == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS); return; }
 
     const uint64_t coff = comp_off[k];
     const uint32_t csize = comp_size[k];
@@ -718,11 +747,12 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
     const uint32_t sq0 = cta_in_chunk * DEC_SEQ_PER_CTA;
     const uint32_t nq = min((uint32_t)DEC_SEQ_PER_CTA, nseq - sq0);
     const uint64_t gout = reinterpret_cast<uint64_t>(out) + ooff;      // address of the chunk's first output byte
-    uint8_t* win = smem_raw + DEC_WRITE_FIXED + (size_t)wid * win_bytes;
-    const uint32_t win_a = pin_reg(smem_u32(win)), wlut_a = pin_reg(smem_u32(S.wlut)), aux_a = pin_reg(smem_u32(S.aux));
-    const uint32_t headw_a = pin_reg(smem_u32(&S.headw[t])), stage_a = pin_reg(smem_u32(S.stage));
+    uint8_t* win = gsm + DEC_WRITE_GROUP + (size_t)wid * win_bytes;
+    const uint32_t win_a = pin_reg(smem_u32(win)), wlut_a = pin_reg(smem_u32(W.wlut)), aux_a = pin_reg(smem_u32(W.aux));
+    const uint32_t stage_a = pin_reg(smem_u32(S.stage));
+    uint32_t phase = 0;                                                // parity of the group's mbarrier
 
-    for (uint32_t q = 0; q < nq; ++q) {
+    for (uint32_t q = grp; q < nq; q += ngrp) {
         const uint32_t sq = sq0 + q;
         const StageGeom g = stage_geom(comp, comp_bytes, coff, csize, sq);
         if (t == 0) stage_issue(S.stage, &S.bar, g);
@@ -738,12 +768,12 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
             if (lane >= d) inc += x;
         }
         if (lane == 31) S.s_warp[wid] = inc;
-        __syncthreads();
+        wgroup_sync(grp);
         if (t == 0) {
             uint32_t a = 0;
             for (int w = 0; w < DT / 32; ++w) { uint32_t x = S.s_warp[w]; S.s_warp[w] = a; a += x; }
         }
-        __syncthreads();
+        wgroup_sync(grp);
         const uint32_t obase = seqoff[P.seq_base[k] + sq] + S.s_warp[wid] + inc - count;
         // the last subsequence of the chunk runs until orig_size symbols exist
         uint32_t todo = 0;
@@ -755,14 +785,20 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                 todo = obase + count > osize ? osize - obase : count;
             }
         }
-        mbar_wait(&S.bar, q & 1);
-        stage_fixup(S.stage, g);
-        __syncthreads();
+        mbar_wait(&S.bar, phase); phase ^= 1;
+        stage_fixup(S.stage, g, t);
+        wgroup_sync(grp);
 
         // ---- per-warp windowed decode -------------------------------------------------------
+        // Packed counter C: bits 0-15 = stream bit position relative to a multiple of 32 at or before
+        // the subsequence's first codeword (so C & 31 is the funnel-shift amount of the bit reader),
+        // bits 16-30 = output bits produced in this pass (8 per symbol, starting at 8 * head).  One
+        // add of the table entry's .y advances both; C2 > Clim catches long codes (bit 31) and
+        // entries with more symbols than the pass may still take.
         BitRd r;
-        uint32_t pos = g.bit0 + t * DEC_SUB_BITS + (rv & 0xFF);
-        rd_seek(r, stage_a, pos);
+        const uint32_t start = g.bit0 + t * DEC_SUB_BITS + (rv & 0xFF);
+        rd_seek(r, stage_a, start);
+        uint32_t rel = start & 31;
         uint64_t my_addr = gout + obase;                            // address of this lane's next symbol
         uint64_t ws = todo ? my_addr : ~0ull, we = todo ? my_addr + todo : 0ull;   // the warp's output range
 #pragma unroll
@@ -770,7 +806,6 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
             const uint64_t a = __shfl_xor_sync(0xffffffffu, ws, d), b = __shfl_xor_sync(0xffffffffu, we, d);
             ws = a < ws ? a : ws; we = b > we ? b : we;
         }
-        bool lane_first = true;
         for (uint64_t wa = ws & ~(uint64_t)15; wa < we; wa += win_bytes) {
             uint32_t n = 0;
             if (todo && my_addr < wa + win_bytes) {
@@ -780,65 +815,101 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
             if (n) {
                 const uint32_t woff = (uint32_t)(my_addr - wa);     // byte offset of the next symbol in the window
                 const uint32_t w0 = win_a + (woff & ~3u);           // the word that holds it
-                // words are assembled in `acc`; the first one (shared with the previous lane) is parked
-                // in headw and merged bytewise once this lane is done
-                uint32_t head = 0, sp = w0, nextw = w0 + 4, acc = 0, fill8 = 0;
-                if (lane_first) { head = woff & 3; fill8 = head * 8; sp = headw_a; lane_first = false; }
-                const bool parked = sp == headw_a;
-                uint32_t left8 = n * 8;
-                while (left8) {
-                    const uint32_t v = rd_peek32(r, pos);
-                    const uint32_t e = lds32(wlut_a + 4 * (v >> (32 - LUTB)));
-                    uint32_t n8 = (e >> 21) & 0x18, l = e >> 28, syms = e & 0xFFFFFF;
-                    if (n8 == 0) {                                  // code longer than LUTB bits
-                        const uint32_t lmin = e & 63, lmax = (e >> 6) & 63;
+                const uint32_t head = woff & 3;
+                const uint32_t T8 = head + n;                       // output bytes of this pass, counted from the word's start
+                uint32_t C = rel | (head << 19);
+                const uint32_t Cend = T8 << 19;
+                const uint32_t Cmain = T8 > 3 ? (T8 - 3) << 19 : 0;   // below it a whole entry (<= 4 symbols) always fits
+                uint32_t sp = w0, acc = 0;
+                // exactly ONE symbol at the reader's position (long codes, and the last <= 3 symbols of a pass)
+                auto one_symbol = [&](uint32_t v, uint2 e, uint32_t& sym) -> uint32_t {
+                    uint32_t l;
+                    if (e.y >> 30 == 3) {                           // code longer than LUTB bits, one candidate length
+                        sym = lds8(aux_a + (uint32_t)offsetof(DecAux, sorted) + e.x + (v >> (32 - (e.y & 63))));
+                        return e.y & 0x3FFFFFFFu;
+                    }
+                    if (e.y >> 31) {                                // several candidate lengths, or no code
+                        const uint32_t lmin = e.x & 63, lmax = (e.x >> 6) & 63;
                         l = lmin == lmax ? lmin : long_len(A, v, lmin, lmax);
                         if (l) {
                             const uint32_t sb = lds32(aux_a + (uint32_t)offsetof(DecAux, symbase) + l * 4);
-                            syms = lds8(aux_a + (uint32_t)offsetof(DecAux, sorted) + sb + (v >> (32 - l)));
-                        } else { l = 1; syms = 0; hz_set_status(status, HZ_ERR_DECODE); }
-                        n8 = 8;
-                    } else if (n8 > left8) {                        // window / subsequence ends inside this entry
-                        l = lds8(aux_a + (uint32_t)offsetof(DecAux, len) + (syms & 0xFF));
-                        if (left8 == 16) l += lds8(aux_a + (uint32_t)offsetof(DecAux, len) + ((syms >> 8) & 0xFF));
-                        syms &= 0xFFFFFFu >> (24 - left8);
-                        n8 = left8;
+                            sym = lds8(aux_a + (uint32_t)offsetof(DecAux, sorted) + sb + (v >> (32 - l)));
+                        } else { l = 1; sym = 0; hz_set_status(status, HZ_ERR_DECODE); }
+                    } else {
+                        sym = e.x & 0xFF;
+                        l = lds8(aux_a + (uint32_t)offsetof(DecAux, len) + sym);
                     }
-                    rd_skip(r, pos, l);
-                    left8 -= n8;
-                    acc |= syms << fill8;
-                    const uint32_t spill = __funnelshift_l(syms, 0u, fill8);     // bytes that do not fit the word
-                    fill8 += n8;
-                    if (fill8 >= 32) { sts32(sp, acc); sp = nextw; nextw += 4; acc = spill; fill8 -= 32; }
+                    return l + (8u << 16);
+                };
+                // one table lookup (up to four symbols): returns the advanced counter, refills the reader
+                auto lookup = [&](uint32_t& syms) -> uint32_t {
+                    const uint32_t v = rd_peek32(r, C);
+                    const uint2 e = lds64(wlut_a + ((v >> 17) & 0x7FF8u));
+                    syms = e.x;
+                    uint32_t C2 = C + e.y;
+                    if ((int32_t)C2 < 0) C2 = C + one_symbol(v, e, syms);
+                    if ((C ^ C2) & 32) { r.hi = r.lo; r.wa += 4; r.lo = bswap32(lds32(r.wa)); }
+                    return C2;
+                };
+                if (head) {
+                    // the first word is shared with the previous lane: its bytes are stored one by one
+                    bool flushed = false;
+                    while (C < Cmain && !flushed) {
+                        uint32_t syms;
+                        const uint32_t C2 = lookup(syms);
+                        const uint32_t F = C >> 16;
+                        acc |= __funnelshift_l(0u, syms, F);
+                        if ((C ^ C2) & (32u << 16)) {
+                            for (uint32_t j = head; j < 4; ++j) sts8(w0 + j, acc >> (8 * j));
+                            acc = __funnelshift_l(syms, 0u, F);
+                            sp = w0 + 4;
+                            flushed = true;
+                        }
+                        C = C2;
+                    }
                 }
+                while (C < Cmain) {
+                    uint32_t syms;
+                    const uint32_t C2 = lookup(syms);
+                    const uint32_t F = C >> 16;
+                    acc |= __funnelshift_l(0u, syms, F);
+                    const uint32_t spill = __funnelshift_l(syms, 0u, F);     // bytes that do not fit the word
+                    if ((C ^ C2) & (32u << 16)) { sts32(sp, acc); sp += 4; acc = spill; }
+                    C = C2;
+                }
+                // bytes still in the accumulator, then the pass's last symbols one at a time
+                const uint32_t pend = (C >> 19) & 3;
+                for (uint32_t j = sp == w0 ? head : 0; j < pend; ++j) sts8(sp + j, acc >> (8 * j));
+                uint32_t bp = sp + pend;
+                while (C < Cend) {
+                    const uint32_t v = rd_peek32(r, C);
+                    const uint2 e = lds64(wlut_a + ((v >> 17) & 0x7FF8u));
+                    uint32_t sym;
+                    const uint32_t C2 = C + one_symbol(v, e, sym);
+                    if ((C ^ C2) & 32) { r.hi = r.lo; r.wa += 4; r.lo = bswap32(lds32(r.wa)); }
+                    sts8(bp, sym); ++bp;
+                    C = C2;
+                }
+                rel = C & 0xFFFFu;
                 todo -= n; my_addr += n;
-                const bool stored = !parked || sp != headw_a;       // at least one complete word left this lane
-                if (parked && stored) {
-                    const uint32_t hw = lds32(headw_a);
-                    for (uint32_t j = head; j < 4; ++j) sts8(w0 + j, hw >> (8 * j));
-                }
-                if (fill8) {                                         // tail bytes (the lane is done: todo == 0)
-                    const uint32_t dst = stored ? sp : w0;
-                    for (uint32_t j = stored ? 0 : head; j < fill8 / 8; ++j) sts8(dst + j, acc >> (8 * j));
-                }
             }
             __syncwarp();
-            // copy the window out: aligned 16-byte units, bytes at the ragged ends
+            // copy the window out: aligned 16-byte units; the ragged first / last unit byte by byte,
+            // one byte per lane (lanes 0-15: first unit, lanes 16-31: last unit)
             const uint64_t lo = ws > wa ? ws : wa;
             const uint64_t hi = we < wa + win_bytes ? we : wa + win_bytes;
-            const uint32_t u0 = (uint32_t)(lo - wa) >> 4, u1 = (uint32_t)(hi - wa + 15) >> 4;
-            for (uint32_t u = u0 + lane; u < u1; u += 32) {
-                const uint64_t ua = wa + (uint64_t)u * 16;
-                if (ua >= lo && ua + 16 <= hi) {
-                    *reinterpret_cast<uint4*>(ua) = *reinterpret_cast<const uint4*>(win + u * 16);
-                } else {
-                    for (uint32_t bb = 0; bb < 16; ++bb)
-                        if (ua + bb >= lo && ua + bb < hi) *reinterpret_cast<uint8_t*>(ua + bb) = win[u * 16 + bb];
-                }
+            const uint32_t b0 = (uint32_t)(lo - wa), b1 = (uint32_t)(hi - wa);          // byte range [b0, b1) of the window
+            const uint32_t f0 = (b0 + 15) >> 4, f1 = b1 >> 4;                              // whole units [f0, f1)
+            for (uint32_t u = f0 + lane; u < f1; u += 32)
+                *reinterpret_cast<uint4*>(wa + (uint64_t)u * 16) = *reinterpret_cast<const uint4*>(win + u * 16);
+            {
+                const uint32_t bb = lane < 16 ? (b0 & ~15u) + lane : (b1 & ~15u) + (lane - 16);
+                const bool edge = lane < 16 ? (b0 & 15) != 0 : (b1 & 15) != 0;
+                if (edge && bb >= b0 && bb < b1) *reinterpret_cast<uint8_t*>(wa + bb) = win[bb];
             }
             __syncwarp();
         }
-        __syncthreads();            // stage is re-filled by the next iteration
+        wgroup_sync(grp);            // stage is re-filled by the next iteration
     }
 }
 
@@ -874,8 +945,7 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     static bool attr_done = false;
     if (!attr_done) {
         HZ_CUDA(ctx, cudaFuncSetAttribute(dec_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncSmem)));
-        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(DEC_WRITE_FIXED + (DT / 32) * DEC_WIN_MAX)));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         attr_done = true;
     }
     HZ_LAUNCH(ctx, "dec_tables", dec_tables_kernel, K, DT, 0, d_len, P, tables, ctx->d_status);
@@ -887,8 +957,15 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     // window, from the stream's overall expansion ratio; smaller windows -> more CTAs per SM
     uint64_t est = comp_bytes ? (uint64_t)(32.0 * DEC_SUB_BYTES * 1.1 * (double)out_cap / (double)comp_bytes) + 64 : DEC_WIN_MIN;
     est = (est + 255) & ~(uint64_t)255;
-    const uint32_t win_bytes = (uint32_t)(est < DEC_WIN_MIN ? DEC_WIN_MIN : (est > DEC_WIN_MAX ? DEC_WIN_MAX : est));
-    HZ_LAUNCH(ctx, "dec_write", dec_write_kernel, (unsigned)max_cta, DT, DEC_WRITE_FIXED + (DT / 32) * (size_t)win_bytes,
+    uint32_t win_bytes = (uint32_t)(est < DEC_WIN_MIN ? DEC_WIN_MIN : (est > DEC_WIN_MAX ? DEC_WIN_MAX : est));
+    if (const char* ev = getenv("HZ_DEC_WIN")) { int v = atoi(ev); if (v >= 256 && v <= DEC_WIN_MAX) win_bytes = (uint32_t)v & ~255u; }   // developer knob
+    // groups per CTA: as many as fit the SM's shared memory next to the shared table (developer knob HZ_DEC_GROUPS)
+    const size_t gbytes = DEC_WRITE_GROUP + (DT / 32) * (size_t)win_bytes;
+    uint32_t groups = (uint32_t)((227 * 1024 - 1024 - DEC_WRITE_SHARED) / gbytes);
+    if (groups > DEC_WRITE_MAX_GROUPS) groups = DEC_WRITE_MAX_GROUPS;
+    if (groups < 1) groups = 1;
+    if (const char* ev = getenv("HZ_DEC_GROUPS")) { int v = atoi(ev); if (v >= 1 && v <= (int)groups) groups = (uint32_t)v; }
+    HZ_LAUNCH(ctx, "dec_write", dec_write_kernel, (unsigned)max_cta, DT * groups, DEC_WRITE_SHARED + groups * gbytes,
               d_comp, comp_bytes, d_comp_off, d_comp_size, d_orig_size, d_len, K, P, tables, rec, seqcnt, d_out, out_cap,
               win_bytes, ctx->d_status);
     return HZ_OK;
