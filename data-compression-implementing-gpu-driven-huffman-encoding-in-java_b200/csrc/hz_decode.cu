@@ -494,8 +494,10 @@ dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uin
             if (U) {                     // equal-length code: boundaries are the multiples of U
                 const uint64_t nomc = (uint64_t)i * DEC_SUB_BITS;
                 entry = (uint32_t)((U - nomc % U) % U);
-                pos = nominal + entry;
-                rd_seek(r, stage_a, pos);
+                // every U-bit pattern counts as one codeword (an unmatched pattern of a one-symbol code
+                // consumes one bit = U), so count and exit follow from arithmetic alone
+                count = (DEC_SUB_BITS - entry + U - 1) / U;
+                exitv = entry + count * U - DEC_SUB_BITS;
             } else if (i == 0) {
                 pos = nominal; rd_seek(r, stage_a, pos);
             } else if (t == 0 && q > 0) {
@@ -505,8 +507,10 @@ dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uin
                 advance(A, slut_a, r, pos, nominal);
                 entry = pos - nominal;
             }
-            count = advance(A, slut_a, r, pos, end);
-            exitv = pos - end;
+            if (!U) {
+                count = advance(A, slut_a, r, pos, end);
+                exitv = pos - end;
+            }
         }
         S.s_exit[t] = exitv;
         __syncthreads();
