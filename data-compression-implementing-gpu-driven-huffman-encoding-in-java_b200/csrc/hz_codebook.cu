@@ -220,6 +220,165 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Many small chunks: ONE WARP per chunk (8 chunks per CTA).  The serial heap replay still runs on
+// one lane, but an SM now keeps ~40 of them in flight instead of 8, which is what bounds the
+// codebook stage when a stream is cut into thousands of chunks (64 KiB chunks: 16 k per GiB).
+// Same results as codebook_kernel; used when spc <= 32 (the segment offsets are scanned by one warp).
+// ---------------------------------------------------------------------------------------------
+#define CBW_WARPS 8
+struct CbWarp {
+    uint64_t heap[256];
+    uint32_t hist[256];
+    uint16_t parent[512];
+    uint16_t leaf_id[256];
+    uint8_t len[256];
+    uint32_t lcount[34];
+    uint32_t first[34];
+};
+
+__global__ void __launch_bounds__(CBW_WARPS * 32)
+codebook_warp_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t K, uint32_t* __restrict__ chunk_hist_out,
+                     uint8_t* __restrict__ len_out, uint32_t* __restrict__ code_out,
+                     uint64_t* __restrict__ chunk_bits, uint32_t* __restrict__ comp_size,
+                     uint64_t* __restrict__ seg_bitoff, const uint8_t* __restrict__ fixed_len,
+                     const uint32_t* __restrict__ direct_hist, int* status) {
+    __shared__ CbWarp S[CBW_WARPS];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t k = blockIdx.x * CBW_WARPS + wid;
+    if (k >= K) return;
+    CbWarp& W = S[wid];
+    const uint32_t FULL = 0xffffffffu;
+
+    // 1. chunk histogram (lane handles symbols lane + 32 j)
+    uint32_t f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t sym = lane + 32 * j;
+        uint32_t a = 0;
+        if (direct_hist) a = direct_hist[(size_t)k * 256 + sym];
+        else for (uint32_t s = 0; s < spc; ++s) a += seg_hist[((size_t)k * spc + s) * 256 + sym];
+        f[j] = a;
+        W.hist[sym] = a;
+        if (chunk_hist_out) chunk_hist_out[(size_t)k * 256 + sym] = a;
+    }
+    if (lane < 34) W.lcount[lane] = 0;
+    if (lane == 0) W.lcount[32] = W.lcount[33] = 0;
+    __syncwarp();
+
+    uint32_t mylen[8];
+    bool bad = false;
+    if (fixed_len) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mylen[j] = fixed_len[lane + 32 * j];
+            if (f[j] > 0 && mylen[j] == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS);
+        }
+    } else {
+        // 2. the serial part: replay java.util.PriorityQueue (CanonicalHuffman.java:55-70)
+        int nsym = 0, root = 0;
+        if (lane == 0) {
+            int size = 0, n = 0;
+            for (int s = 0; s < 256; ++s) {
+                const uint32_t fr = W.hist[s];
+                if (fr > 0) {
+                    W.leaf_id[s] = (uint16_t)n;
+                    heap_offer(W.heap, size, ((uint64_t)fr << 18) | ((uint64_t)(s + 1) << 9) | (uint64_t)n);
+                    ++n;
+                }
+            }
+            nsym = n;
+            while (size > 1) {
+                const uint64_t l = heap_poll(W.heap, size);
+                const uint64_t r = heap_poll(W.heap, size);
+                W.parent[l & 511] = (uint16_t)n;
+                W.parent[r & 511] = (uint16_t)n;
+                heap_offer(W.heap, size, (((l >> 18) + (r >> 18)) << 18) | (uint64_t)n);
+                ++n;
+            }
+            root = n - 1;
+        }
+        nsym = __shfl_sync(FULL, nsym, 0);
+        root = __shfl_sync(FULL, root, 0);
+        __syncwarp();
+        // 3. leaf depth = code length (extractLengths, :85-92); single symbol -> 1 (:35-45)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t d = 0;
+            if (f[j] > 0) {
+                if (nsym == 1) d = 1;
+                else { int id = W.leaf_id[lane + 32 * j]; while (id != root) { id = W.parent[id]; ++d; } }
+            }
+            mylen[j] = d;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bad |= mylen[j] > 32;
+    bad = __any_sync(FULL, bad);
+    if (bad) {                                  // the reference throws here (:107)
+        if (lane == 0) hz_set_status(status, HZ_ERR_CODE_TOO_LONG);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mylen[j] = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        W.len[lane + 32 * j] = (uint8_t)mylen[j];
+        if (mylen[j] > 0) atomicAdd(&W.lcount[mylen[j]], 1u);
+    }
+    __syncwarp();
+    // 4. canonical codes (generateCanonicalCodes, :99-132): first code of every length, then the
+    //    symbols of a length in increasing symbol order (lane 0 walks the alphabet once)
+    if (lane == 0) {
+        uint32_t c = 0;
+        W.first[0] = 0;
+        for (int l = 1; l <= 32; ++l) { c = (c + (l > 1 ? W.lcount[l - 1] : 0u)) << 1; W.first[l] = c; }
+        for (int s = 0; s < 256; ++s) {
+            const uint32_t l = W.len[s];
+            W.hist[s] = l ? W.first[l]++ : 0u;   // hist is no longer needed (f[] holds the counts): reuse for the codes
+        }
+    }
+    __syncwarp();
+    uint64_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t sym = lane + 32 * j;
+        len_out[(size_t)k * 256 + sym] = (uint8_t)mylen[j];
+        if (code_out) code_out[(size_t)k * 256 + sym] = W.hist[sym];
+        bits += (uint64_t)f[j] * mylen[j];
+    }
+    // 5. exact compressed size of the chunk: sum(freq * len) bits
+    if (chunk_bits) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(FULL, bits, d);
+        if (lane == 0) {
+            chunk_bits[k] = bits;
+            uint64_t bytes = (bits + 7) >> 3;
+            if (bytes > 0x7fffffffull) { hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); bytes = 0; }
+            comp_size[k] = (uint32_t)bytes;
+        }
+    }
+    // 6. bit offset of every segment inside the chunk's stream (spc <= 32: one lane per segment)
+    if (seg_bitoff && seg_hist) {
+        uint64_t mine = 0;
+        for (uint32_t s = 0; s < spc; ++s) {
+            const uint32_t* sh = seg_hist + ((size_t)k * spc + s) * 256;
+            uint64_t b = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b += (uint64_t)sh[lane + 32 * j] * mylen[j];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) b += __shfl_xor_sync(FULL, b, d);
+            if (lane == s) mine = b;
+        }
+        uint64_t inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= (uint32_t)d) inc += o;
+        }
+        if (lane < spc) seg_bitoff[(size_t)k * spc + lane] = inc - mine;
+    }
+}
+
 // comp_off[k] = exclusive prefix sum of comp_size (K+1 entries), one CTA of 1024 threads:
 // each thread sums a contiguous slice, the slice totals are scanned, then prefixes are written.
 __global__ void __launch_bounds__(1024)
@@ -291,9 +450,16 @@ int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t spc, uint32_t
     }
     // spc == 0 means d_seg_hist is a caller-supplied K x 256 chunk histogram
     const uint32_t* direct = spc == 0 ? d_seg_hist : nullptr;
-    HZ_LAUNCH(ctx, "codebook", codebook_kernel, K, CB_THREADS, 0,
-              spc == 0 ? nullptr : d_seg_hist, spc, d_chunk_hist, d_len, d_code, d_chunk_bits,
-              d_comp_size, d_seg_bitoff, d_fixed_len256, direct, ctx->d_status);
+    // thousands of small chunks: warp per chunk (more serial heaps in flight per SM)
+    if (K >= 1024 && spc <= 32) {
+        HZ_LAUNCH(ctx, "codebook", codebook_warp_kernel, (K + CBW_WARPS - 1) / CBW_WARPS, CBW_WARPS * 32, 0,
+                  spc == 0 ? nullptr : d_seg_hist, spc, K, d_chunk_hist, d_len, d_code, d_chunk_bits,
+                  d_comp_size, d_seg_bitoff, d_fixed_len256, direct, ctx->d_status);
+    } else {
+        HZ_LAUNCH(ctx, "codebook", codebook_kernel, K, CB_THREADS, 0,
+                  spc == 0 ? nullptr : d_seg_hist, spc, d_chunk_hist, d_len, d_code, d_chunk_bits,
+                  d_comp_size, d_seg_bitoff, d_fixed_len256, direct, ctx->d_status);
+    }
     if (d_comp_off)
         HZ_LAUNCH(ctx, "chunk_offsets", chunk_offsets_kernel, 1, 1024, 0, d_comp_size, K, d_comp_off);
     return HZ_OK;

@@ -396,3 +396,19 @@ def test_pipelined_host_buffers_match_device_path(codec, n, chunk, H):
     orig = np.array([min(chunk, n - k * chunk) for k in range(K)], dtype=np.uint32)
     back = codec.decode(payload, off[:-1], sizes, orig, lens)       # pipelined decode
     assert np.array_equal(back, data), "round trip"
+
+
+def test_many_small_chunks_warp_codebook(codec):
+    """K >= 1024 chunks take the warp-per-chunk codebook kernel: histogram, code lengths, offsets, payload
+    and round trip must still match the oracle chunk by chunk (including one-symbol and ragged chunks)."""
+    n, chunk = 1100 * 4096 + 77, 4096
+    data = datasets.zipf_stream(n, 3, seed=99).copy()
+    data[5 * chunk:6 * chunk] = 0x41                      # a one-symbol chunk
+    data[7 * chunk:8 * chunk] = np.arange(chunk, dtype=np.uint32).astype(np.uint8)   # all 256 symbols, equal counts
+    check_encode(codec, data, chunk)
+    hist = np.zeros((1500, 256), dtype=np.uint32)         # direct histograms: hz_build_codebooks with K >= 1024
+    rng = np.random.default_rng(5)
+    for k in range(1500):
+        m = int(rng.integers(1, 257))
+        hist[k, rng.choice(256, m, replace=False)] = rng.integers(1, 1 << int(rng.integers(1, 20)), m)
+    _check_codebooks(codec, hist)
