@@ -968,6 +968,9 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     uint32_t groups = (uint32_t)((227 * 1024 - 1024 - DEC_WRITE_SHARED) / gbytes);
     if (groups > DEC_WRITE_MAX_GROUPS) groups = DEC_WRITE_MAX_GROUPS;
     if (groups < 1) groups = 1;
+    // chunks of a few sequences each build their table inside the CTA: two independent CTAs per SM
+    // (two table builds in flight) beat one CTA whose extra groups wait for the build
+    if (comp_bytes / K < 4ull * DEC_SEQ_BYTES) groups = 1;
     if (const char* ev = getenv("HZ_DEC_GROUPS")) { int v = atoi(ev); if (v >= 1 && v <= (int)groups) groups = (uint32_t)v; }
     HZ_LAUNCH(ctx, "dec_write", dec_write_kernel, (unsigned)max_cta, DT * groups, DEC_WRITE_SHARED + groups * gbytes,
               d_comp, comp_bytes, d_comp_off, d_comp_size, d_orig_size, d_len, K, P, tables, rec, seqcnt, d_out, out_cap,
