@@ -30,13 +30,17 @@
 // its own segment of the same chunk; they share only the 32 KiB LUT, which buys 32 resident warps
 // per SM instead of 24.  The byte shared by two neighbouring segments is written by the LATER
 // segment, which recomputes the previous segment's last <8 bits from its last 7 symbols.
-// Chunks whose longest code exceeds 16 bits take the "wide" instantiation (8 symbols per thread
+// Chunks whose longest code has 17..27 bits take the "medium" instantiation (16 symbols per thread
+// per tile, the same LUT entry format, a completed-word check after EVERY symbol, OR-ing merge);
+// chunks whose longest code exceeds 27 bits take the "wide" instantiation (8 symbols per thread
 // per tile, 64-bit LUT entries, a completed-word check after every symbol, every dense word
 // OR-ed): correct for lengths up to 32, slower; it also serves the ragged last tile of a segment.
 #include "hz_common.cuh"
 
 #define ENC_SPT 32                                  // symbols per thread per tile (fast path)
 #define ENC_TILE (HZ_THREADS * ENC_SPT)             // 8192
+#define ENC_MED_SPT 16                              // symbols per thread per tile (codes of 17..27 bits)
+#define ENC_MED_TILE (HZ_THREADS * ENC_MED_SPT)     // 4096
 #define ENC_WIDE_SPT 8
 #define ENC_WIDE_TILE (HZ_THREADS * ENC_WIDE_SPT)   // 2048
 #define ENC_GROUPS 2                                // independent 256-thread groups per CTA
@@ -53,6 +57,8 @@
 
 static_assert(HZ_SEG_BYTES % ENC_TILE == 0, "a segment is a whole number of tiles");
 static_assert(ENC_WIDE_TILE * 32 / 32 + 16 <= ENC_DENSE_WORDS, "wide tile must fit the dense buffer");
+static_assert(ENC_MED_TILE * 27 / 32 + 16 <= ENC_DENSE_WORDS, "medium tile must fit the dense buffer");
+static_assert(ENC_MED_SPT * 27 <= (ENC_PRIV_STRIDE - 2) * 32, "medium row must fit the private row");
 static_assert(ENC_G_PRIV % 16 == 0 && ENC_G_BYTES % 16 == 0 && ENC_DENSE_WORDS % 4 == 0, "alignment");
 static_assert(2 * (ENC_SMEM_BYTES + 1024) <= 227 * 1024, "two CTAs per SM");
 
@@ -267,6 +273,51 @@ __device__ __forceinline__ uint32_t encode_thread32(const uint32_t w[8], int nva
     return nbits;
 }
 
+// phase A, medium path: up to 16 symbols (4 words), codes of up to 27 bits.  Same LUT entries
+// (code left-aligned | length in bits 4..0), but the code may reach down to bit 5, so the length is
+// masked before it is counted, and a 32-bit word can complete after every symbol.
+__device__ __forceinline__ uint32_t encode_thread_med(const uint32_t w[4], int nvalid, uint32_t lanebase, uint32_t priv_a) {
+    uint32_t hi = 0, lo = 0, nb = 0, ptr = priv_a;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t x = w[g];
+        uint32_t e[4];
+        e[0] = enc_lds32(lut_addr<0>(x, lanebase));
+        e[1] = enc_lds32(lut_addr<1>(x, lanebase));
+        e[2] = enc_lds32(lut_addr<2>(x, lanebase));
+        e[3] = enc_lds32(lut_addr<3>(x, lanebase));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t ej = g * 4 + j < nvalid ? e[j] : 0u;
+            hi = __funnelshift_l(lo, hi, ej); lo = __funnelshift_l(ej, lo, ej);
+            const uint32_t nb2 = nb + (ej & 31);
+            if ((nb ^ nb2) & 32) { enc_sts32(ptr, __funnelshift_r(lo, hi, nb2)); ptr += 4; }
+            nb = nb2;
+        }
+    }
+    const uint32_t v = nb & 31;
+    enc_sts32(ptr, shl_c(lo, 32 - v));
+    if (v) enc_sts32(ptr + 4, 0);
+    return nb;
+}
+
+// 16 symbols (4 little-endian words) starting at q; nvalid of them exist
+__device__ __forceinline__ void load_syms16(const uint8_t* q, int nvalid, uint32_t w[4]) {
+    if (nvalid == 16 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+        const uint4 v = ld_stream_u4(reinterpret_cast<const uint4*>(q));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (i * 4 + b < nvalid) v |= (uint32_t)q[i * 4 + b] << (8 * b);
+            w[i] = v;
+        }
+    }
+}
+
 // phase A, wide path: up to 8 symbols, codes of up to 32 bits
 __device__ __forceinline__ uint32_t encode_thread_wide(const uint8_t* q, int nvalid, const uint2* lut64, uint32_t priv_a) {
     uint64_t acc = 0;
@@ -331,7 +382,8 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
     uint32_t par = 0;
 
     // codebook of this chunk (both groups fill half of every LUT row)
-    const bool wide = __syncthreads_or(mylen > 16);    // block-uniform: codes longer than 16 bits
+    const bool wide = __syncthreads_or(mylen > 27);    // block-uniform: codes longer than 27 bits
+    const bool medium = __syncthreads_or(mylen > 16) && !wide;
     uint2* lut64 = reinterpret_cast<uint2*>(lut);     // wide: [sym] = {length, right-aligned code}
     if (!wide) {
         const uint32_t e = mylen ? (mycode << (32 - mylen)) | mylen : 0u;
@@ -374,7 +426,29 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
         }
     }
 
-    if (!wide) {
+    if (medium) {
+        // ---- medium path: codes of 17..27 bits, 16 symbols per thread per tile --------------------
+        const uint32_t lanebase = enc_pin(base_a + (lane << 2));
+        uint32_t x[4], xn[4];
+        auto nvalid_of = [&](uint32_t tile) -> int {
+            const uint32_t first = tile + tg * ENC_MED_SPT;
+            return first >= slen ? 0 : (slen - first >= ENC_MED_SPT ? ENC_MED_SPT : (int)(slen - first));
+        };
+        load_syms16(p + tg * ENC_MED_SPT, nvalid_of(0), xn);
+        for (uint32_t tile = 0; tile < slen; tile += ENC_MED_TILE) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = xn[j];
+            if (tile + ENC_MED_TILE < slen) load_syms16(p + tile + ENC_MED_TILE + tg * ENC_MED_SPT, nvalid_of(tile + ENC_MED_TILE), xn);
+            const uint32_t nbits = encode_thread_med(x, nvalid_of(tile), lanebase, priv_a);
+            uint32_t tile_bits;
+            const uint32_t off = O.cur + group_excl_scan(nbits, warp_tot, par, bar_id, lane, wid, &tile_bits);
+            par ^= 1;
+            merge_or(priv_a, dense_a, off, nbits);
+            group_sync(bar_id);
+            O.cur += tile_bits;
+            flush_tile(dense, O, tg);
+        }
+    } else if (!wide) {
         // ---- fast path: 32 symbols per thread per tile, software-pipelined loads ------------------
         const uint32_t lanebase = enc_pin(base_a + (lane << 2));
         // one full tile: A (codewords -> private word-aligned bit string), S (exclusive scan of the

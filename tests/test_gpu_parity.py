@@ -175,7 +175,7 @@ def test_ragged_sizes(codec, n, chunk):
 def test_wide_codes_encode_decode(codec):
     """Chunks whose longest code is > 16 bits (wide encoder path) and > 12 bits (decoder fallback)."""
     rng = np.random.default_rng(11)
-    for nsym in (18, 24, 30):
+    for nsym in (18, 24, 28, 29, 30):       # longest code 17, 23, 27 (medium path) and 28, 29 (wide path)
         f = datasets.fib_like_hist(nsym)[:nsym].astype(np.int64)      # exact Fibonacci counts -> depth nsym-1
         data = np.repeat(np.arange(nsym, dtype=np.uint8), f)
         rng.shuffle(data)
