@@ -755,6 +755,13 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
     const uint32_t win_a = pin_reg(smem_u32(win)), wlut_a = pin_reg(smem_u32(W.wlut)), aux_a = pin_reg(smem_u32(W.aux));
     const uint32_t stage_a = pin_reg(smem_u32(S.stage));
     uint32_t phase = 0;                                                // parity of the group's mbarrier
+    const uint32_t sub0 = P.sub_base[k], seq0 = P.seq_base[k];
+    uint32_t rv_next = 0, sbase_next = 0;
+    if (grp < nq) {
+        const uint32_t i1 = (sq0 + grp) * DT + t;
+        rv_next = i1 < nsub ? rec[sub0 + i1] : 0;
+        sbase_next = seqoff[seq0 + sq0 + grp];
+    }
 
     for (uint32_t q = grp; q < nq; q += ngrp) {
         const uint32_t sq = sq0 + q;
@@ -763,7 +770,13 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         // while the copy is in flight: output offsets of this sequence
         const uint32_t i = sq * DT + t;
         const bool active = i < nsub;
-        const uint32_t rv = active ? rec[P.sub_base[k] + i] : 0;
+        const uint32_t rv = rv_next;
+        const uint32_t sbase = sbase_next;
+        if (q + ngrp < nq) {                                           // next sequence of this group: loads fly during this one
+            const uint32_t i2 = (sq + ngrp) * DT + t;
+            rv_next = i2 < nsub ? rec[sub0 + i2] : 0;
+            sbase_next = seqoff[seq0 + sq + ngrp];
+        }
         const uint32_t count = rv >> 16;
         uint32_t inc = count;
 #pragma unroll
@@ -778,7 +791,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
             for (int w = 0; w < DT / 32; ++w) { uint32_t x = S.s_warp[w]; S.s_warp[w] = a; a += x; }
         }
         wgroup_sync(grp);
-        const uint32_t obase = seqoff[P.seq_base[k] + sq] + S.s_warp[wid] + inc - count;
+        const uint32_t obase = sbase + S.s_warp[wid] + inc - count;
         // the last subsequence of the chunk runs until orig_size symbols exist
         uint32_t todo = 0;
         if (active) {
@@ -802,6 +815,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         BitRd r;
         const uint32_t start = g.bit0 + t * DEC_SUB_BITS + (rv & 0xFF);
         rd_seek(r, stage_a, start);
+        uint32_t nx = bswap32(lds32(r.wa + 4));                     // stage word after (hi, lo): loaded one refill ahead
         uint32_t rel = start & 31;
         uint64_t my_addr = gout + obase;                            // address of this lane's next symbol
         uint64_t ws = todo ? my_addr : ~0ull, we = todo ? my_addr + todo : 0ull;   // the warp's output range
@@ -852,7 +866,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                     syms = e.x;
                     uint32_t C2 = C + e.y;
                     if ((int32_t)C2 < 0) C2 = C + one_symbol(v, e, syms);
-                    if ((C ^ C2) & 32) { r.hi = r.lo; r.wa += 4; r.lo = bswap32(lds32(r.wa)); }
+                    if ((C ^ C2) & 32) { r.hi = r.lo; r.lo = nx; r.wa += 4; nx = bswap32(lds32(r.wa + 4)); }   // the word after next is already in flight
                     return C2;
                 };
                 if (head) {
@@ -890,7 +904,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                     const uint2 e = lds64(wlut_a + ((v >> 17) & 0x7FF8u));
                     uint32_t sym;
                     const uint32_t C2 = C + one_symbol(v, e, sym);
-                    if ((C ^ C2) & 32) { r.hi = r.lo; r.wa += 4; r.lo = bswap32(lds32(r.wa)); }
+                    if ((C ^ C2) & 32) { r.hi = r.lo; r.lo = nx; r.wa += 4; nx = bswap32(lds32(r.wa + 4)); }   // the word after next is already in flight
                     sts8(bp, sym); ++bp;
                     C = C2;
                 }
