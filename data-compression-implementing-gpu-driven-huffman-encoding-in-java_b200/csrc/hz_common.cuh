@@ -29,6 +29,8 @@ struct hz_ctx {
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
+    // kernel attributes (opt-in shared memory) are per device: set once per context, not once per process
+    bool attr_encode = false, attr_decode = false, attr_hist = false;
     // device-side status word (first error latched by kernels) + pinned host mirror
     int* d_status = nullptr;
     int* h_status = nullptr;

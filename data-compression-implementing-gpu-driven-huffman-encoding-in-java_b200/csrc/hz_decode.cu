@@ -960,11 +960,10 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     uint32_t* rec = (uint32_t*)ctx->dec_rec.p;
     uint32_t* seqcnt = (uint32_t*)ctx->dec_seqcnt.p;
     uint8_t* tables = (uint8_t*)ctx->dec_tables.p;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ctx->attr_decode) {
         HZ_CUDA(ctx, cudaFuncSetAttribute(dec_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncSmem)));
         HZ_CUDA(ctx, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        attr_done = true;
+        ctx->attr_decode = true;
     }
     HZ_LAUNCH(ctx, "dec_tables", dec_tables_kernel, K, DT, 0, d_len, P, tables, ctx->d_status);
     HZ_LAUNCH(ctx, "dec_sync", dec_sync_kernel, (unsigned)max_cta, DT, sizeof(SyncSmem),

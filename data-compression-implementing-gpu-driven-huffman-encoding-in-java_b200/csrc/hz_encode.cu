@@ -519,10 +519,9 @@ int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_byte
     const uint32_t cpc = (rpc + ENC_GROUPS - 1) / ENC_GROUPS;
     const uint64_t grid = (uint64_t)K * cpc;
     if (grid > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "too many segments");
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ctx->attr_encode) {
         HZ_CUDA(ctx, cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
-        attr_done = true;
+        ctx->attr_encode = true;
     }
     HZ_LAUNCH(ctx, "encode", encode_kernel, (unsigned)grid, ENC_CTA, ENC_SMEM_BYTES,
               d_in, n, chunk_bytes, spc, cpc, mult, d_len, d_code, d_comp_off, d_seg_bitoff, K, d_out, out_cap, ctx->d_status);

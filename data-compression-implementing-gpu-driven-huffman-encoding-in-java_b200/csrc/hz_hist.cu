@@ -164,10 +164,9 @@ int hzk_histogram(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_b
     }
     if (variant == 0) {
         const size_t smem = (64 * 256 + 256) * sizeof(uint32_t);
-        static bool attr_done = false;
-        if (!attr_done) {
+        if (!ctx->attr_hist) {
             HZ_CUDA(ctx, cudaFuncSetAttribute(hist_seg_private, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
+            ctx->attr_hist = true;
         }
         HZ_LAUNCH(ctx, "hist_seg_private", hist_seg_private, (unsigned)grid, HZ_THREADS, smem,
                   d_in, n, chunk_bytes, spc, d_seg_hist);

@@ -412,3 +412,15 @@ def test_many_small_chunks_warp_codebook(codec):
         m = int(rng.integers(1, 257))
         hist[k, rng.choice(256, m, replace=False)] = rng.integers(1, 1 << int(rng.integers(1, 20)), m)
     _check_codebooks(codec, hist)
+
+
+def test_two_contexts_one_process(hz):
+    """Kernel attributes (opt-in shared memory) are set per context, not once per process."""
+    data = datasets.zipf_stream(700_000, 4, seed=5)
+    with hz.Codec(0) as a, hz.Codec(0) as b:
+        pa, oa, la = a.encode(data, 100_000)
+        pb, ob, lb = b.encode(data, 100_000)
+        assert np.array_equal(pa, pb) and np.array_equal(oa, ob) and np.array_equal(la, lb)
+        K = len(oa) - 1
+        orig = np.array([min(100_000, data.size - k * 100_000) for k in range(K)], dtype=np.uint32)
+        assert np.array_equal(b.decode(pa, oa[:-1], np.diff(oa).astype(np.uint32), orig, la), data)
