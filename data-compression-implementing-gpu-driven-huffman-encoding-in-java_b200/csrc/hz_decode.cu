@@ -27,15 +27,18 @@
 //                         with aligned 128-bit stores.
 //
 // Tables (LUTB = 12 bits of look-ahead):
-//   slut u16: ltot | n<<6 | l0<<10   bits / number of all n (<=12) complete codewords inside the
+//   slut u16: ltot | l0<<6 | n<<12   bits / number of all n (<=12) complete codewords inside the
 //             12 bits and the first codeword's length (counting pass).  A prefix that starts a
 //             code longer than 12 bits has n = 1 and its length when every code under the prefix
 //             has the same length, else n = 0 with ltot = shortest, l0 = longest candidate.
 //   wlut u32x2: .x = s0 | s1<<8 | s2<<16 | s3<<24 (up to four symbols per lookup), .y = ltot | 8n<<16:
 //             ONE add of .y to the write pass's packed counter (stream bit position | output bits<<16)
-//             advances both.  .y bit 31: long code / no code, .x = shortest | longest<<6 candidate length;
-//             .y bits 31+30: every code under the prefix has length .y & 63 and its symbol is
-//             sorted[.x + (first .y & 63 stream bits)] (the sorted-symbol array is the second level).
+//             advances both.  .y bit 31 alone: every code under the prefix has the same length l = .y & 63
+//             (> LUTB) and its symbol is sorted[k + (the l - LUTB stream bits after the prefix)]: the
+//             sorted-symbol array is the second level; .x = (DEC_W_SORTED_REL + k) << 5 | (32 + LUTB - l),
+//             i.e. a wlut-relative shared address and the right-shift that isolates those bits, so the
+//             write loop resolves such codes with five predicated instructions and no branch.
+//             .y bits 31+30: several candidate lengths or no code, .x = shortest | longest<<6.
 // Codes whose used lengths are all equal never self-synchronise but need no synchronisation
 // either: entries are computed arithmetically.
 #include <cstdlib>
@@ -72,6 +75,8 @@ struct __align__(16) DecAux {
     int maxlen, minlen, uniform, bad;
 };
 static_assert(sizeof(DecAux) <= 1024, "DecAux must fit its 1 KiB slot");
+// shared-memory offset of DecAux::sorted relative to the write kernel's wlut (WriteShared: wlut, then aux)
+#define DEC_W_SORTED_REL (LUTN * 8 + (uint32_t)offsetof(DecAux, sorted))
 
 // ---------------------------------------------------------------------------------------------
 // table construction (all DT threads).  scratch: >= 8 KiB + 2 KiB of shared memory.
@@ -169,7 +174,7 @@ __device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __re
     const uint32_t maxlen = (uint32_t)A.maxlen;
     for (uint32_t x = t * 16; x < t * 16 + 16; ++x) {
         const uint32_t e0 = base[x];
-        uint2 we = make_uint2(0u, 0x80000000u);
+        uint2 we = make_uint2(0u, 0xC0000000u);
         uint32_t se = 0;
         if (e0) {
             const uint32_t l0 = e0 >> 8;
@@ -184,7 +189,7 @@ __device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __re
                 used += le; ++n; lprev = le;
             }
             we = make_uint2(syms, wtot | (wn << 19));
-            se = used | (n << 6) | (l0 << 10);
+            se = used | (l0 << 6) | (n << 12);
         } else if (maxlen > LUTB) {
             // the prefix starts a code longer than LUTB bits (or no code): candidate lengths at both ends
             const uint32_t vlo = x << (32 - LUTB), vhi = vlo | ((1u << (32 - LUTB)) - 1);
@@ -194,8 +199,9 @@ __device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __re
                 if (!lmax) lmax = maxlen;
                 we.x = lmin | (lmax << 6);
                 // every code under this prefix has the same length: `sorted` is the second-level table
-                if (lmin == lmax) we = make_uint2((uint32_t)A.symbase[lmin], 0xC0000000u | lmin | (8u << 16));
-                se = lmin == lmax ? (lmin | (1u << 6) | (lmin << 10)) : (lmin | (lmax << 10));
+                if (lmin == lmax && lmin < 32)
+                    we = make_uint2(DEC_W_SORTED_REL + (uint32_t)A.symbase[lmin], 0x80000000u | lmin | (8u << 16));
+                se = lmin == lmax ? (lmin | (lmin << 6) | (1u << 12)) : (lmin | (lmax << 6));
             }
         }
         if (WANT_W) wlut[x] = we;
@@ -397,22 +403,106 @@ __device__ __forceinline__ void rd_skip(BitRd& r, uint32_t& pos, uint32_t l) {  
     pos = np;
 }
 
+struct SyncSmem {
+    __align__(16) uint8_t stage[2][DEC_STAGE_BYTES];
+    __align__(16) uint16_t slut[LUTN];
+    __align__(16) uint8_t aux[1024];
+    __align__(8) uint64_t bar[2];
+    uint32_t s_exit[DT];
+    uint32_t s_red[DT / 32];
+    uint32_t s_k;
+};
+
+// PTX twin of long_len() for the hand-written loops.  Registers of the enclosing asm block: v (32 stream
+// bits), l (in: shortest, out: length found or 0), m (longest candidate), auxb (shared address of DecAux);
+// temporaries a, t, u and predicate pq.  SFX makes the labels unique.
+#define HZ_PTX_LONGLEN(SFX)                         \
+    "setp.eq.u32 pq, l, 0;\n"                       \
+    "@pq bra HZL_END" SFX ";\n"                     \
+    "HZL_TOP" SFX ":\n"                             \
+    "mad.lo.u32 a, l, 8, auxb;\n"                   \
+    "ld.shared.v2.u32 {t, u}, [a];\n"               \
+    "setp.ne.u32 pq, u, 0;\n"                       \
+    "@pq bra HZL_END" SFX ";\n"                     \
+    "setp.lt.u32 pq, v, t;\n"                       \
+    "@pq bra HZL_END" SFX ";\n"                     \
+    "setp.ge.u32 pq, l, m;\n"                       \
+    "@pq mov.u32 l, 0;\n"                           \
+    "@pq bra HZL_END" SFX ";\n"                     \
+    "add.u32 l, l, 1;\n"                            \
+    "bra HZL_TOP" SFX ";\n"                         \
+    "HZL_END" SFX ":\n"
+static_assert(offsetof(DecAux, lim) == 0, "HZ_PTX_LONGLEN reads lim[] at the start of DecAux");
+
 // Advance from `pos` to the first codeword boundary >= limit; returns the number of codewords
 // that began before `limit`.  Unmatched patterns consume one bit.
 __device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitRd& r, uint32_t& pos, uint32_t limit) {
     uint32_t cnt = 0;
-    while (pos + LUTB <= limit) {
-        const uint32_t v = rd_peek32(r, pos);
-        const uint32_t e = lds16(slut + 2 * (v >> (32 - LUTB)));
-        uint32_t l = e & 63, n = (e >> 6) & 15;
-        if (n == 0) { l = long_len(A, v, l, e >> 10); n = 1; if (!l) l = 1; }
-        rd_skip(r, pos, l); cnt += n;
+    if (pos + LUTB <= limit) {
+        // Main loop (hand-written PTX, two lookups per trip so that the position ping-pongs between two
+        // registers): all complete codewords of the 12-bit window per lookup.  The stage word after `lo` is
+        // loaded one refill ahead (raw; byte-swapped when it becomes `lo`), the refill is four predicated
+        // instructions.  Entries with n == 0 (several candidate lengths / no code) branch to an out-of-line
+        // search and come back into the same iteration, so the warp reconverges every lookup.
+        uint32_t nx = lds32(r.wa + 4);
+        const uint32_t lim12 = limit - LUTB;
+#define HZ_ASTEP(PI, PO, SFX)                                                  \
+    "shf.l.wrap.b32 v, %2, %1, " PI ";\n"                                      \
+    "shr.u32 ix, v, 20;\n"                                                     \
+    "mad.lo.u32 ix, ix, 2, %6;\n"                                              \
+    "ld.shared.u16 e, [ix];\n"                                                 \
+    "and.b32 l, e, 63;\n"                                                      \
+    "shr.u32 n, e, 12;\n"                                                      \
+    "setp.lt.u32 pz, e, 4096;\n"                                               \
+    "@pz bra HZA_RARE" SFX ";\n"                                               \
+    "HZA_BACK" SFX ":\n"                                                       \
+    "add.u32 " PO ", " PI ", l;\n"                                             \
+    "add.u32 %5, %5, n;\n"                                                     \
+    "xor.b32 t, " PI ", " PO ";\n"                                             \
+    "and.b32 t, t, 32;\n"                                                      \
+    "setp.ne.u32 p0, t, 0;\n"                                                  \
+    "@p0 mov.u32 %1, %2;\n"                                                    \
+    "@p0 prmt.b32 %2, %4, z, 0x0123;\n"                                        \
+    "@p0 ld.shared.u32 %4, [%3+8];\n"                                          \
+    "@p0 add.u32 %3, %3, 4;\n"                                                 \
+    "setp.gt.u32 pc, " PO ", %7;\n"
+#define HZ_ARARE(SFX)                                                          \
+    "HZA_RARE" SFX ":\n"                                                       \
+    "shr.u32 m, e, 6;\n"                                                       \
+    "and.b32 m, m, 63;\n"                                                      \
+    "mov.u32 auxb, %8;\n"                                                      \
+    HZ_PTX_LONGLEN("A" SFX)                                                    \
+    "max.u32 l, l, 1;\n"                                                       \
+    "mov.u32 n, 1;\n"                                                          \
+    "bra HZA_BACK" SFX ";\n"
+        asm volatile(
+            "{\n"
+            ".reg .pred pz, p0, pc, pq;\n"
+            ".reg .u32 Q, v, ix, e, l, n, m, t, u, a, z, auxb;\n"
+            "mov.u32 z, 0;\n"
+            "HZA_TOP:\n"
+            HZ_ASTEP("%0", "Q", "1")
+            "@pc bra HZA_ENDQ;\n"
+            HZ_ASTEP("Q", "%0", "2")
+            "@!pc bra HZA_TOP;\n"
+            "bra HZA_END;\n"
+            HZ_ARARE("1")
+            HZ_ARARE("2")
+            "HZA_ENDQ:\n"
+            "mov.u32 %0, Q;\n"
+            "HZA_END:\n"
+            "}\n"
+            : "+r"(pos), "+r"(r.hi), "+r"(r.lo), "+r"(r.wa), "+r"(nx), "+r"(cnt)
+            : "r"(slut), "r"(lim12), "r"(slut + (uint32_t)(offsetof(SyncSmem, aux) - offsetof(SyncSmem, slut)))
+            : "memory");
+#undef HZ_ASTEP
+#undef HZ_ARARE
     }
     while (pos < limit) {
         const uint32_t v = rd_peek32(r, pos);
         const uint32_t e = lds16(slut + 2 * (v >> (32 - LUTB)));
-        uint32_t l = e >> 10;
-        if (((e >> 6) & 15) == 0) { l = long_len(A, v, e & 63, l); if (!l) l = 1; }
+        uint32_t l = (e >> 6) & 63;
+        if ((e >> 12) == 0) { l = long_len(A, v, e & 63, l); if (!l) l = 1; }
         rd_skip(r, pos, l); ++cnt;
     }
     return cnt;
@@ -423,15 +513,6 @@ __device__ __forceinline__ uint32_t pack_rec(uint32_t entry, uint32_t exitv, uin
     return entry | (exitv << 8) | (count << 16);
 }
 
-struct SyncSmem {
-    __align__(16) uint8_t stage[2][DEC_STAGE_BYTES];
-    __align__(16) uint16_t slut[LUTN];
-    __align__(16) uint8_t aux[1024];
-    __align__(8) uint64_t bar[2];
-    uint32_t s_exit[DT];
-    uint32_t s_red[DT / 32];
-    uint32_t s_k;
-};
 
 __global__ void __launch_bounds__(DT)
 dec_sync_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const uint64_t* __restrict__ comp_off,
@@ -583,8 +664,8 @@ __device__ __forceinline__ void g_scan(const DecAux& A, const uint16_t* __restri
     while (pos < end) {
         const uint32_t v = __funnelshift_l(r.lo, r.hi, r.sh);
         const uint32_t e = slut[v >> (32 - LUTB)];
-        uint32_t l = e >> 10;
-        if (((e >> 6) & 15) == 0) { l = long_len(A, v, e & 63, l); if (!l) l = 1; }
+        uint32_t l = (e >> 6) & 63;
+        if ((e >> 12) == 0) { l = long_len(A, v, e & 63, l); if (!l) l = 1; }
         g_skip(r, l); pos += l; ++cnt;
     }
     *count = cnt; *exitv = (uint32_t)(pos - end);
@@ -692,6 +773,7 @@ struct WriteShared {
     __align__(16) uint8_t aux[1024];
     uint32_t s_k;
 };
+static_assert(offsetof(WriteShared, aux) + offsetof(DecAux, sorted) == DEC_W_SORTED_REL, "wlut long-code entries address sorted[] relative to wlut");
 struct WriteGroup {                      // followed by DT/32 output windows of win_bytes each
     __align__(16) uint8_t stage[DEC_STAGE_BYTES];
     __align__(8) uint64_t bar;
@@ -815,7 +897,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         BitRd r;
         const uint32_t start = g.bit0 + t * DEC_SUB_BITS + (rv & 0xFF);
         rd_seek(r, stage_a, start);
-        uint32_t nx = bswap32(lds32(r.wa + 4));                     // stage word after (hi, lo): loaded one refill ahead
+        uint32_t nx = lds32(r.wa + 4);                              // stage word after (hi, lo), NOT yet byte-swapped: loaded one refill ahead
         uint32_t rel = start & 31;
         uint64_t my_addr = gout + obase;                            // address of this lane's next symbol
         uint64_t ws = todo ? my_addr : ~0ull, we = todo ? my_addr + todo : 0ull;   // the warp's output range
@@ -842,9 +924,9 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                 // exactly ONE symbol at the reader's position (long codes, and the last <= 3 symbols of a pass)
                 auto one_symbol = [&](uint32_t v, uint2 e, uint32_t& sym) -> uint32_t {
                     uint32_t l;
-                    if (e.y >> 30 == 3) {                           // code longer than LUTB bits, one candidate length
-                        sym = lds8(aux_a + (uint32_t)offsetof(DecAux, sorted) + e.x + (v >> (32 - (e.y & 63))));
-                        return e.y & 0x3FFFFFFFu;
+                    if (e.y >> 30 == 2) {                           // code longer than LUTB bits, one candidate length
+                        sym = lds8(wlut_a + e.x + __funnelshift_l(v, 0u, e.y));   // + first l bits of v (l < 32)
+                        return e.y & 0x7FFFFFFFu;
                     }
                     if (e.y >> 31) {                                // several candidate lengths, or no code
                         const uint32_t lmin = e.x & 63, lmax = (e.x >> 6) & 63;
@@ -866,7 +948,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                     syms = e.x;
                     uint32_t C2 = C + e.y;
                     if ((int32_t)C2 < 0) C2 = C + one_symbol(v, e, syms);
-                    if ((C ^ C2) & 32) { r.hi = r.lo; r.lo = nx; r.wa += 4; nx = bswap32(lds32(r.wa + 4)); }   // the word after next is already in flight
+                    if ((C ^ C2) & 32) { r.hi = r.lo; r.lo = bswap32(nx); r.wa += 4; nx = lds32(r.wa + 4); }   // the word after next is already in flight
                     return C2;
                 };
                 if (head) {
@@ -886,14 +968,101 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                         C = C2;
                     }
                 }
-                while (C < Cmain) {
-                    uint32_t syms;
-                    const uint32_t C2 = lookup(syms);
-                    const uint32_t F = C >> 16;
-                    acc |= __funnelshift_l(0u, syms, F);
-                    const uint32_t spill = __funnelshift_l(syms, 0u, F);     // bytes that do not fit the word
-                    if ((C ^ C2) & (32u << 16)) { sts32(sp, acc); sp += 4; acc = spill; }
-                    C = C2;
+                if (C < Cmain) {
+                    // Main loop (hand-written PTX, two lookups per trip so that the packed counter ping-pongs
+                    // between two registers).  Per lookup: peek, table entry, advanced counter; a single-length
+                    // long code (.y bit 31) is resolved by predicated instructions, no branch; then the predicated
+                    // reader refill and output-word store.  ONE compare catches both the pass's last whole-entry
+                    // lookup and the entries with several candidate lengths / no code (their bit 30 survives):
+                    // those branch out of line, are resolved by the length search and re-enter the same
+                    // iteration, so the warp reconverges every lookup.
+#define HZ_WCOMMIT(CI, CO)                                                    \
+    "xor.b32 t, " CI ", " CO ";\n"                                            \
+    "and.b32 a, t, 32;\n"                                                     \
+    "setp.ne.u32 p0, a, 0;\n"                                                 \
+    "and.b32 a, t, 0x200000;\n"                                               \
+    "setp.ne.u32 p1, a, 0;\n"                                                 \
+    "shr.u32 F, " CI ", 16;\n"                                                \
+    "@p0 mov.u32 %1, %2;\n"                                                   \
+    "@p0 prmt.b32 %2, %3, z, 0x0123;\n"                                       \
+    "@p0 ld.shared.u32 %3, [%4+8];\n"                                         \
+    "@p0 add.u32 %4, %4, 4;\n"                                                \
+    "shf.l.wrap.b32 a, z, ex, F;\n"                                           \
+    "shf.l.wrap.b32 t, ex, z, F;\n"                                           \
+    "add.u32 %5, %5, a;\n"                                                    \
+    "@p1 st.shared.u32 [%6], %5;\n"                                           \
+    "@p1 add.u32 %6, %6, 4;\n"                                                \
+    "selp.b32 %5, t, %5, p1;\n"
+#define HZ_WSTEP(CI, CO, SFX)                                                 \
+    "shf.l.wrap.b32 v, %2, %1, " CI ";\n"                                     \
+    "shr.u32 ix, v, 20;\n"                                                    \
+    "mad.lo.u32 ix, ix, 8, %8;\n"                                             \
+    "ld.shared.v2.u32 {ex, ey}, [ix];\n"                                      \
+    "shf.l.wrap.b32 t, v, z, ey;\n"                                           \
+    "add.u32 a, ex, %8;\n"                                                    \
+    "add.u32 a, a, t;\n"                                                      \
+    "add.u32 " CO ", " CI ", ey;\n"                                           \
+    "setp.lt.s32 pl, ey, 0;\n"                                                \
+    "@pl ld.shared.u8 ex, [a];\n"                                             \
+    "@pl add.u32 " CO ", " CO ", 0x80000000;\n"                               \
+    "setp.ge.u32 px, " CO ", %7;\n"                                           \
+    "@px bra HZW_CHECK" SFX ";\n"                                             \
+    "HZW_BACK" SFX ":\n"                                                      \
+    HZ_WCOMMIT(CI, CO)
+#define HZ_WCHECK(CI, CO, SFX, FIN)                                           \
+    "HZW_CHECK" SFX ":\n"                                                     \
+    "and.b32 t, " CO ", 0x40000000;\n"                                        \
+    "setp.eq.u32 pq, t, 0;\n"                                                 \
+    "@pq bra HZW_LAST" SFX ";\n"                                              \
+    "ld.shared.v2.u32 {ex, ey}, [ix];\n"                                      \
+    "and.b32 l, ex, 63;\n"                                                    \
+    "shr.u32 m, ex, 6;\n"                                                     \
+    "and.b32 m, m, 63;\n"                                                     \
+    "add.u32 auxb, %8, %10;\n"                                                \
+    HZ_PTX_LONGLEN("W" SFX)                                                   \
+    "setp.eq.u32 pq, l, 0;\n"                                                 \
+    "@pq bra HZW_BAD" SFX ";\n"                                               \
+    "mad.lo.u32 a, l, 4, auxb;\n"                                             \
+    "ld.shared.u32 t, [a+%11];\n"                                             \
+    "sub.u32 u, 32, l;\n"                                                     \
+    "shr.u32 u, v, u;\n"                                                      \
+    "add.u32 a, t, u;\n"                                                      \
+    "add.u32 a, a, auxb;\n"                                                   \
+    "ld.shared.u8 ex, [a+%12];\n"                                             \
+    "bra HZW_GOT" SFX ";\n"                                                   \
+    "HZW_BAD" SFX ":\n"                                                       \
+    "mov.u32 l, 1;\n"                                                         \
+    "mov.u32 ex, 0;\n"                                                        \
+    "atom.global.cas.b32 t, [%9], 0, %13;\n"                                  \
+    "HZW_GOT" SFX ":\n"                                                       \
+    "add.u32 " CO ", " CI ", l;\n"                                            \
+    "add.u32 " CO ", " CO ", 0x80000;\n"                                      \
+    "setp.lt.u32 pq, " CO ", %7;\n"                                           \
+    "@pq bra HZW_BACK" SFX ";\n"                                              \
+    "HZW_LAST" SFX ":\n"                                                      \
+    HZ_WCOMMIT(CI, CO)                                                        \
+    FIN                                                                       \
+    "bra HZW_DONE;\n"
+                    asm volatile(
+                        "{\n"
+                        ".reg .pred pl, px, p0, p1, pq;\n"
+                        ".reg .u32 D, v, ix, ex, ey, t, u, a, F, z, l, m, auxb;\n"
+                        "mov.u32 z, 0;\n"
+                        "HZW_TOP:\n"
+                        HZ_WSTEP("%0", "D", "1")
+                        HZ_WSTEP("D", "%0", "2")
+                        "bra HZW_TOP;\n"
+                        HZ_WCHECK("%0", "D", "1", "mov.u32 %0, D;\n")
+                        HZ_WCHECK("D", "%0", "2", "")
+                        "HZW_DONE:\n"
+                        "}\n"
+                        : "+r"(C), "+r"(r.hi), "+r"(r.lo), "+r"(nx), "+r"(r.wa), "+r"(acc), "+r"(sp)
+                        : "r"(Cmain), "r"(smem_u32(W.wlut)), "l"(status),
+                          "n"(LUTN * 8), "n"(offsetof(DecAux, symbase)), "n"(offsetof(DecAux, sorted)), "n"(HZ_ERR_DECODE)
+                        : "memory");
+#undef HZ_WSTEP
+#undef HZ_WCHECK
+#undef HZ_WCOMMIT
                 }
                 // bytes still in the accumulator, then the pass's last symbols one at a time
                 const uint32_t pend = (C >> 19) & 3;
@@ -904,7 +1073,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                     const uint2 e = lds64(wlut_a + ((v >> 17) & 0x7FF8u));
                     uint32_t sym;
                     const uint32_t C2 = C + one_symbol(v, e, sym);
-                    if ((C ^ C2) & 32) { r.hi = r.lo; r.lo = nx; r.wa += 4; nx = bswap32(lds32(r.wa + 4)); }   // the word after next is already in flight
+                    if ((C ^ C2) & 32) { r.hi = r.lo; r.lo = bswap32(nx); r.wa += 4; nx = lds32(r.wa + 4); }   // the word after next is already in flight
                     sts8(bp, sym); ++bp;
                     C = C2;
                 }

@@ -7,8 +7,10 @@
 // per-segment bins lets the encoder derive every segment's exact output bit offset from
 // sum(bins * code length) without a second pass over the data and without a look-back chain.
 //
-// Two kernels:
-//  * hist_seg_atomic   — (default) per-warp private uint32 bins updated with shared-memory atomics;
+// Three kernels:
+//  * hist_seg_lanes    — (default) one counter per (bin, lane): conflict-free shared-memory atomics,
+//    distribution independent: 0.22 ms per GiB (4.8 TB/s) from 1 to 8 bits/symbol on B200.
+//  * hist_seg_atomic   — (HZ_HIST=atomic) per-warp private uint32 bins updated with shared-memory atomics;
 //    one column sum per bin at the end.  Measured on B200, 1 GiB: 0.18 ms for a constant stream
 //    (same-address atomics are combined by the hardware), 0.19 ms at 1 bit/symbol, 0.33 ms at
 //    4 bits/symbol, 0.42 ms for uniform bytes (bank conflicts between different bins).
@@ -151,6 +153,60 @@ hist_seg_atomic(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes
 }
 
 // ---------------------------------------------------------------------------------------------
+// hist_seg_lanes — one uint32 counter per (bin, lane): word bin*32 + lane, so a lane always hits its
+// own bank and every shared-memory atomic of a warp is ONE wavefront whatever the byte distribution
+// (hist_seg_atomic needs ~2.5 for 32 random bins over 32 banks).  32 KiB per CTA, all warps of the
+// CTA share the copy (atomics resolve collisions between warps).  Per symbol: PRMT (byte extract),
+// IMAD (bin*128 + lane address), RED.  The 32 columns of a bin are summed with a rotated,
+// conflict-free read at the end.
+__global__ void __launch_bounds__(HZ_THREADS)
+hist_seg_lanes(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t spc,
+               uint32_t* __restrict__ seg_hist) {
+    __shared__ __align__(16) uint32_t h[256 * 32];
+    const uint32_t t = threadIdx.x, lane = t & 31;
+    uint64_t sbeg; uint32_t slen;
+    seg_geometry(n, chunk_bytes, spc, &sbeg, &slen);
+    uint32_t* dst = seg_hist + (size_t)blockIdx.x * 256;
+    if (slen == 0) { dst[t] = 0; return; }
+    {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* h4 = reinterpret_cast<uint4*>(h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h4[t + i * HZ_THREADS] = z;
+    }
+    __syncthreads();
+    const uint8_t* p = in + sbeg;
+    uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15);
+    if (head > slen) head = slen;
+    const uint32_t nvec = (slen - head) >> 4;
+    const uint32_t tail = slen - head - (nvec << 4);
+    const uint32_t mine = (uint32_t)__cvta_generic_to_shared(h) + lane * 4;      // this lane's column
+    auto bump = [&](uint32_t sym) {
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(sym * 128u + mine) : "memory");
+    };
+    if (t < head) bump(p[t]);
+    if (t < tail) bump(p[head + (nvec << 4) + t]);
+    const uint4* pv = reinterpret_cast<const uint4*>(p + head);
+#pragma unroll 2
+    for (uint32_t i = t; i < nvec; i += HZ_THREADS) {
+        const uint4 v = ld_stream_u4(pv + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            bump(__byte_perm(w[g], 0, 0x4440));
+            bump(__byte_perm(w[g], 0, 0x4441));
+            bump(__byte_perm(w[g], 0, 0x4442));
+            bump(__byte_perm(w[g], 0, 0x4443));
+        }
+    }
+    __syncthreads();
+    uint32_t s = 0;
+#pragma unroll 8
+    for (uint32_t j = 0; j < 32; ++j) s += h[t * 32 + ((j + t) & 31)];
+    dst[t] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
 int hzk_histogram(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
                   uint32_t* d_seg_hist) {
     if (K == 0) return HZ_OK;
@@ -160,7 +216,7 @@ int hzk_histogram(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_b
     static int variant = -1;
     if (variant < 0) {
         const char* e = getenv("HZ_HIST");
-        variant = (e && strcmp(e, "private") == 0) ? 0 : 1;
+        variant = (e && strcmp(e, "private") == 0) ? 0 : (e && strcmp(e, "atomic") == 0) ? 1 : 2;
     }
     if (variant == 0) {
         const size_t smem = (64 * 256 + 256) * sizeof(uint32_t);
@@ -169,6 +225,9 @@ int hzk_histogram(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_b
             ctx->attr_hist = true;
         }
         HZ_LAUNCH(ctx, "hist_seg_private", hist_seg_private, (unsigned)grid, HZ_THREADS, smem,
+                  d_in, n, chunk_bytes, spc, d_seg_hist);
+    } else if (variant == 2) {
+        HZ_LAUNCH(ctx, "hist_seg_lanes", hist_seg_lanes, (unsigned)grid, HZ_THREADS, 0,
                   d_in, n, chunk_bytes, spc, d_seg_hist);
     } else {
         HZ_LAUNCH(ctx, "hist_seg_atomic", hist_seg_atomic, (unsigned)grid, HZ_THREADS, 0,

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 pre = os.path.join(out, "%s_%s_" % (rnd, tag))
-NAMES = {"hist_seg_private": "hist_seg_private", "hist_seg_atomic": "hist_seg_atomic", "encode_kernel": "encode",
+NAMES = {"hist_seg_private": "hist_seg_private", "hist_seg_atomic": "hist_seg_atomic", "hist_seg_lanes": "hist_seg_lanes", "encode_kernel": "encode",
          "dec_sync_kernel": "dec_sync", "dec_write_kernel": "dec_write", "codebook_kernel": "codebook"}
 
 for f in ("bench.json", "bench_ref.json"):
