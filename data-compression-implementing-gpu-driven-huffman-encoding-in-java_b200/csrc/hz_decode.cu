@@ -794,7 +794,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                  const uint32_t* __restrict__ comp_size, const uint32_t* __restrict__ orig_size,
                  const uint8_t* __restrict__ len_tab, uint32_t K, DecPlan P, const uint8_t* __restrict__ tables,
                  const uint32_t* __restrict__ rec, const uint32_t* __restrict__ seqoff,
-                 uint8_t* __restrict__ out, uint64_t out_cap, uint32_t win_bytes, int* status) {
+                 uint8_t* __restrict__ out, uint64_t out_cap, uint32_t win_bytes, uint32_t bulk_out, int* status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WriteShared& W = *reinterpret_cast<WriteShared*>(smem_raw);
     const uint32_t grp = threadIdx.x / DT, ngrp = blockDim.x / DT;
@@ -907,6 +907,10 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
             ws = a < ws ? a : ws; we = b > we ? b : we;
         }
         for (uint64_t wa = ws & ~(uint64_t)15; wa < we; wa += win_bytes) {
+            if (bulk_out) {                      // the previous bulk copy out of this window must have read it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
             uint32_t n = 0;
             if (todo && my_addr < wa + win_bytes) {
                 const uint64_t room = wa + win_bytes - my_addr;
@@ -1087,8 +1091,22 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
             const uint64_t hi = we < wa + win_bytes ? we : wa + win_bytes;
             const uint32_t b0 = (uint32_t)(lo - wa), b1 = (uint32_t)(hi - wa);          // byte range [b0, b1) of the window
             const uint32_t f0 = (b0 + 15) >> 4, f1 = b1 >> 4;                              // whole units [f0, f1)
-            for (uint32_t u = f0 + lane; u < f1; u += 32)
-                *reinterpret_cast<uint4*>(wa + (uint64_t)u * 16) = *reinterpret_cast<const uint4*>(win + u * 16);
+            if (bulk_out) {
+                // whole units leave with ONE asynchronous bulk copy (shared -> global) issued by lane 0: the warp
+                // goes on to its next pass / sequence while the copy drains
+                if (f1 > f0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(wa + (uint64_t)f0 * 16), "r"(win_a + f0 * 16), "r"((f1 - f0) * 16) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else {
+                for (uint32_t u = f0 + lane; u < f1; u += 32)
+                    *reinterpret_cast<uint4*>(wa + (uint64_t)u * 16) = *reinterpret_cast<const uint4*>(win + u * 16);
+            }
             {
                 const uint32_t bb = lane < 16 ? (b0 & ~15u) + lane : (b1 & ~15u) + (lane - 16);
                 const bool edge = lane < 16 ? (b0 & 15) != 0 : (b1 & 15) != 0;
@@ -1098,6 +1116,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         }
         wgroup_sync(grp);            // stage is re-filled by the next iteration
     }
+    if (bulk_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the copies
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1154,8 +1173,10 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     // (two table builds in flight) beat one CTA whose extra groups wait for the build
     if (comp_bytes / K < 4ull * DEC_SEQ_BYTES) groups = 1;
     if (const char* ev = getenv("HZ_DEC_GROUPS")) { int v = atoi(ev); if (v >= 1 && v <= (int)groups) groups = (uint32_t)v; }
+    uint32_t bulk_out = 1;                 // developer knob: HZ_DEC_BULK=0 copies the windows out with 128-bit stores
+    if (const char* ev = getenv("HZ_DEC_BULK")) bulk_out = atoi(ev) != 0;
     HZ_LAUNCH(ctx, "dec_write", dec_write_kernel, (unsigned)max_cta, DT * groups, DEC_WRITE_SHARED + groups * gbytes,
               d_comp, comp_bytes, d_comp_off, d_comp_size, d_orig_size, d_len, K, P, tables, rec, seqcnt, d_out, out_cap,
-              win_bytes, ctx->d_status);
+              win_bytes, bulk_out, ctx->d_status);
     return HZ_OK;
 }
