@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhuffb200.so")
+LIB_PATH = os.environ.get("HZ_LIB") or os.path.join(_HERE, "libhuffb200.so")   # HZ_LIB: developer knob (A/B builds)
 
 # status codes (include/huffb200.h)
 HZ_OK = 0

@@ -845,10 +845,14 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         sbase_next = seqoff[seq0 + sq0 + grp];
     }
 
+    // the compressed bytes of a group's NEXT sequence are requested as soon as every thread of the group
+    // has finished reading the current ones (before the windows are copied out), so the bulk copy flies
+    // during the copy-out and the next sequence's offset scan
+    if (t == 0 && grp < nq) stage_issue(S.stage, &S.bar, stage_geom(comp, comp_bytes, coff, csize, sq0 + grp));
     for (uint32_t q = grp; q < nq; q += ngrp) {
         const uint32_t sq = sq0 + q;
         const StageGeom g = stage_geom(comp, comp_bytes, coff, csize, sq);
-        if (t == 0) stage_issue(S.stage, &S.bar, g);
+        bool released = false;                                         // this warp has passed the "stage is free" barrier
         // while the copy is in flight: output offsets of this sequence
         const uint32_t i = sq * DT + t;
         const bool active = i < nsub;
@@ -1085,6 +1089,11 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                 todo -= n; my_addr += n;
             }
             __syncwarp();
+            if (wa + win_bytes >= we) {          // this warp's last pass: it no longer reads the staged bytes
+                wgroup_sync(grp);
+                released = true;
+                if (t == 0 && q + ngrp < nq) stage_issue(S.stage, &S.bar, stage_geom(comp, comp_bytes, coff, csize, sq + ngrp));
+            }
             // copy the window out: aligned 16-byte units; the ragged first / last unit byte by byte,
             // one byte per lane (lanes 0-15: first unit, lanes 16-31: last unit)
             const uint64_t lo = ws > wa ? ws : wa;
@@ -1114,7 +1123,10 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
             }
             __syncwarp();
         }
-        wgroup_sync(grp);            // stage is re-filled by the next iteration
+        if (!released) {                         // a warp without output still takes part in the hand-over
+            wgroup_sync(grp);
+            if (t == 0 && q + ngrp < nq) stage_issue(S.stage, &S.bar, stage_geom(comp, comp_bytes, coff, csize, sq + ngrp));
+        }
     }
     if (bulk_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the copies
 }
