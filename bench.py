@@ -227,6 +227,8 @@ def run_b200(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hz = ge.load_package()
+    import importlib
+    numa_cpus = importlib.import_module(hz.__name__ + ".parallel").bind_to_gpu_numa(local)   # pinned buffers on the GPU's socket
     codec = hz.Codec(local)
     stream = torch.cuda.Stream()          # a real (non-default) stream: the codec, torch and the events share it
     torch.cuda.set_stream(stream)
@@ -362,7 +364,9 @@ def run_b200(a):
         meta = (K + 1) * 8 + K * 256
         e2e = {"value": 2.0 * n * world / e2e_s / 1e9, "unit": UNIT, "ms_per_step": 1e3 * e2e_s, "steps": a.e2e_steps,
                "h2d_bytes_per_step": n + C + 2 * meta + 8 * K, "d2h_bytes_per_step": C + n + meta,
-               "api": "hz_encode + hz_decode with pinned host buffers"}
+               "api": "hz_encode + hz_decode with pinned host buffers",
+               "host_numa_binding": ("rank pinned to the %d CPUs NVML reports local to its GPU before the pinned buffers are allocated"
+                                     % len(numa_cpus)) if numa_cpus else "none (NVML affinity unavailable)"}
         del h_src, h_comp, h_back
 
     if rank != 0:
@@ -431,6 +435,12 @@ def run_b200(a):
 
 def main():
     a = parse_args()
+    # stdout carries exactly ONE JSON line: everything else written to fd 1 (NCCL prints its version banner
+    # there) is sent to stderr; the JSON goes to the saved descriptor
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
     if a.impl == "reference":
         return run_reference(a)
     return run_b200(a)

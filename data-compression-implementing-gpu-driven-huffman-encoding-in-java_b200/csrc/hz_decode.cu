@@ -872,12 +872,15 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         }
         if (lane == 31) S.s_warp[wid] = inc;
         wgroup_sync(grp);
-        if (t == 0) {
-            uint32_t a = 0;
-            for (int w = 0; w < DT / 32; ++w) { uint32_t x = S.s_warp[w]; S.s_warp[w] = a; a += x; }
+        // symbols of the warps before this one: every warp scans the DT/32 warp totals itself (one barrier)
+        uint32_t wsum = lane < DT / 32 ? S.s_warp[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < DT / 32; d <<= 1) {
+            uint32_t x = __shfl_up_sync(0xffffffffu, wsum, d);
+            if (lane >= d) wsum += x;
         }
-        wgroup_sync(grp);
-        const uint32_t obase = sbase + S.s_warp[wid] + inc - count;
+        const uint32_t wbase = __shfl_sync(0xffffffffu, wsum, wid) - __shfl_sync(0xffffffffu, lane < DT / 32 ? S.s_warp[lane] : 0, wid);
+        const uint32_t obase = sbase + wbase + inc - count;
         // the last subsequence of the chunk runs until orig_size symbols exist
         uint32_t todo = 0;
         if (active) {
@@ -904,11 +907,14 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
         uint32_t nx = lds32(r.wa + 4);                              // stage word after (hi, lo), NOT yet byte-swapped: loaded one refill ahead
         uint32_t rel = start & 31;
         uint64_t my_addr = gout + obase;                            // address of this lane's next symbol
-        uint64_t ws = todo ? my_addr : ~0ull, we = todo ? my_addr + todo : 0ull;   // the warp's output range
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const uint64_t a = __shfl_xor_sync(0xffffffffu, ws, d), b = __shfl_xor_sync(0xffffffffu, we, d);
-            ws = a < ws ? a : ws; we = b > we ? b : we;
+        // the warp's output range: the lanes' runs are consecutive, so it is [first active lane's start, last active lane's end)
+        uint64_t ws = ~0ull, we = 0ull;
+        {
+            const uint32_t am = __ballot_sync(0xffffffffu, todo != 0);
+            if (am) {
+                ws = __shfl_sync(0xffffffffu, my_addr, __ffs(am) - 1);
+                we = __shfl_sync(0xffffffffu, my_addr + todo, 31 - __clz(am));
+            }
         }
         for (uint64_t wa = ws & ~(uint64_t)15; wa < we; wa += win_bytes) {
             if (bulk_out) {                      // the previous bulk copy out of this window must have read it

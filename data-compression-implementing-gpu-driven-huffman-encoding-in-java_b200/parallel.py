@@ -26,6 +26,29 @@ MAGIC = 0x44435A46          # core/CompressionHeader.java:15
 VERSION = 1                 # :16
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device_index`, so that pinned host
+    buffers allocated afterwards (hz_host_alloc = cudaHostAlloc, first touch) land on that GPU's NUMA node.
+    With one process per GPU this keeps every rank's H2D/D2H traffic on its own socket instead of funnelling
+    all ranks through the node the launcher happened to start on.  Returns the CPU set, or None when NVML or
+    the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def chunk_range(K, world, rank):
     """Contiguous chunk range of `rank`: [rank*K//world, (rank+1)*K//world)."""
     return (rank * K) // world, ((rank + 1) * K) // world
