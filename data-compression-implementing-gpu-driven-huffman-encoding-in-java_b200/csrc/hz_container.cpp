@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 #include <thread>
+#include <future>
 #include <atomic>
 #include <algorithm>
 #include <fcntl.h>
@@ -213,10 +214,30 @@ int read_header(Rd& r, Header& h, std::string& why) {
 }
 
 // ---- byte sources ----------------------------------------------------------------------------
+// Large transfers are cut into slices handled by a few threads: one thread copying out of / into the page
+// cache moves 1.5-4 GB/s, which is what used to bound the file pipeline.
+static const uint64_t IO_SLICE_MIN = 8ull << 20;
+template <class F>
+bool io_parallel(uint64_t n, F&& piece) {              // piece(offset, bytes) -> bool, on up to 8 threads
+    unsigned hw = std::thread::hardware_concurrency();
+    uint64_t T = std::min<uint64_t>(std::min<uint64_t>(hw ? hw : 4, 8), (n + IO_SLICE_MIN - 1) / IO_SLICE_MIN);
+    if (T <= 1) return piece(0, n);
+    const uint64_t per = ((n + T - 1) / T + 4095) & ~4095ull;
+    std::atomic<bool> ok{true};
+    std::vector<std::thread> pool;
+    for (uint64_t i = 0; i < T; ++i) {
+        const uint64_t lo = i * per;
+        if (lo >= n) break;
+        const uint64_t len = std::min<uint64_t>(per, n - lo);
+        pool.emplace_back([&, lo, len] { if (!piece(lo, len)) ok = false; });
+    }
+    for (auto& th : pool) th.join();
+    return ok;
+}
+
 struct Source {                     // random-access reader over a file or a memory buffer
     int fd = -1; const uint8_t* mem = nullptr; uint64_t size = 0;
-    bool read(uint64_t off, void* dst, uint64_t n) const {
-        if (off + n > size) return false;
+    bool read_serial(uint64_t off, void* dst, uint64_t n) const {
         if (mem) { memcpy(dst, mem + off, n); return true; }
         uint8_t* d = (uint8_t*)dst;
         while (n) {
@@ -226,18 +247,30 @@ struct Source {                     // random-access reader over a file or a mem
         }
         return true;
     }
+    bool read(uint64_t off, void* dst, uint64_t n) const {
+        if (off + n > size) return false;
+        return io_parallel(n, [&](uint64_t lo, uint64_t len) { return read_serial(off + lo, (uint8_t*)dst + lo, len); });
+    }
 };
-struct Sink {                       // sequential writer to a file or a growing memory buffer
-    int fd = -1; std::vector<uint8_t>* mem = nullptr;
-    bool write(const void* src, uint64_t n) {
-        if (mem) { mem->insert(mem->end(), (const uint8_t*)src, (const uint8_t*)src + n); return true; }
-        const uint8_t* s = (const uint8_t*)src;
+struct Sink {                       // in-order writer to a file or a growing memory buffer
+    int fd = -1; std::vector<uint8_t>* mem = nullptr; uint64_t pos = 0;
+    bool write_serial(uint64_t off, const uint8_t* s, uint64_t n) {
         while (n) {
-            ssize_t w = ::write(fd, s, n > (1u << 30) ? (1u << 30) : n);
+            ssize_t w = ::pwrite(fd, s, n > (1u << 30) ? (1u << 30) : n, (off_t)off);
             if (w <= 0) { if (w < 0 && errno == EINTR) continue; return false; }
-            s += w; n -= (uint64_t)w;
+            s += w; off += (uint64_t)w; n -= (uint64_t)w;
         }
         return true;
+    }
+    bool write(const void* src, uint64_t n) {
+        const uint64_t at = pos;
+        pos += n;
+        if (mem) {
+            mem->resize((size_t)(at + n));
+            uint8_t* d = mem->data() + at;
+            return io_parallel(n, [&](uint64_t lo, uint64_t len) { memcpy(d + lo, (const uint8_t*)src + lo, len); return true; });
+        }
+        return io_parallel(n, [&](uint64_t lo, uint64_t len) { return write_serial(at + lo, (const uint8_t*)src + lo, len); });
     }
 };
 
@@ -252,7 +285,7 @@ int pin_reserve(hz_ctx* ctx, size_t bytes) {
 
 // bytes of input handled per GPU batch (>= one chunk)
 uint64_t batch_bytes_for(uint32_t chunk_bytes) {
-    const uint64_t target = 256ull << 20;
+    const uint64_t target = 128ull << 20;      // two pinned slots of this size are in flight
     if (chunk_bytes >= target) return chunk_bytes;
     return (target / chunk_bytes) * chunk_bytes;
 }
@@ -270,12 +303,15 @@ int compress_core(hz_ctx* ctx, const Source& src, Sink& dst, uint32_t chunk_byte
     const uint64_t bb = batch_bytes_for(chunk_bytes);
     const uint64_t max_batch = std::min<uint64_t>(bb, n);
     const size_t kb_max = (size_t)(bb / chunk_bytes);
-    // pinned staging: [input batch][payload batch][comp_off][len]
+    // Two pinned slots, each [input batch][payload batch][comp_off][len]: while the GPU encodes batch b and the
+    // host hashes it, a reader task fills the other slot with batch b+1 and a writer task drains batch b-1.
     const size_t off_in = 0, off_out = (size_t)((max_batch + 255) & ~255ull);
     const size_t off_coff = off_out + (size_t)((max_batch + 16 + 255) & ~255ull);
     const size_t off_len = off_coff + (((kb_max + 1) * 8 + 255) & ~(size_t)255);
-    HZ_TRY(pin_reserve(ctx, off_len + kb_max * 256 + 256));
-    uint8_t* pin = (uint8_t*)ctx->h_pin;
+    const size_t slot_bytes = (off_len + kb_max * 256 + 256 + 4095) & ~(size_t)4095;
+    const uint64_t nbatch = (n + bb - 1) / bb;
+    HZ_TRY(pin_reserve(ctx, slot_bytes * (nbatch > 1 ? 2 : 1)));
+    uint8_t* pin_base = (uint8_t*)ctx->h_pin;
     DevBuf& d_in = ctx->stage_in; DevBuf& d_out = ctx->stage_out;
     DevBuf& d_off = ctx->stage_d; DevBuf& d_len = ctx->stage_e;
     HZ_TRY(hz_reserve(ctx, &d_in, max_batch));
@@ -284,10 +320,20 @@ int compress_core(hz_ctx* ctx, const Source& src, Sink& dst, uint32_t chunk_byte
     HZ_TRY(hz_reserve(ctx, &d_len, kb_max * 256));
 
     uint64_t comp_total = 0, done = 0;
-    for (uint64_t pos = 0, k0 = 0; pos < n; ) {
+    std::future<bool> fut_rd, fut_wr;                 // std::async futures join in their destructor on every exit path
+    if (n) fut_rd = std::async(std::launch::async, [&src, pin_base, off_in, bb, n] {
+        return src.read(0, pin_base + off_in, std::min<uint64_t>(bb, n)); });
+    uint64_t b = 0;
+    for (uint64_t pos = 0, k0 = 0; pos < n; ++b) {
+        uint8_t* pin = pin_base + (b & 1) * slot_bytes;
         const uint64_t bn = std::min<uint64_t>(bb, n - pos);
         const size_t kb = (size_t)hz_num_chunks(bn, chunk_bytes);
-        if (!src.read(pos, pin + off_in, bn)) return hz_fail(ctx, HZ_ERR_IO, "read failed at offset %llu", (unsigned long long)pos);
+        if (!fut_rd.get()) return hz_fail(ctx, HZ_ERR_IO, "read failed at offset %llu", (unsigned long long)pos);
+        if (pos + bn < n) {                           // the other slot's input was consumed (copied, hashed) a batch ago
+            uint8_t* nxt = pin_base + ((b + 1) & 1) * slot_bytes + off_in;
+            const uint64_t npos = pos + bn, nn = std::min<uint64_t>(bb, n - npos);
+            fut_rd = std::async(std::launch::async, [&src, nxt, npos, nn] { return src.read(npos, nxt, nn); });
+        }
         HZ_CUDA(ctx, cudaMemcpyAsync(d_in.p, pin + off_in, bn, cudaMemcpyHostToDevice, ctx->stream));
         HZ_TRY(hz_encode(ctx, (const uint8_t*)d_in.p, bn, chunk_bytes, (uint8_t*)d_out.p, bn + 16,
                          (uint64_t*)d_off.p, (uint8_t*)d_len.p, nullptr));
@@ -300,9 +346,11 @@ int compress_core(hz_ctx* ctx, const Source& src, Sink& dst, uint32_t chunk_byte
         HZ_TRY(hz_sync(ctx));
         const uint64_t* coff = (const uint64_t*)(pin + off_coff);
         const uint64_t btotal = coff[kb];
+        // this slot's payload region was handed to the writer two batches ago; that write was joined last batch
         HZ_CUDA(ctx, cudaMemcpyAsync(pin + off_out, d_out.p, btotal, cudaMemcpyDeviceToHost, ctx->stream));
         HZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (!dst.write(pin + off_out, btotal)) return hz_fail(ctx, HZ_ERR_IO, "write failed");
+        if (fut_wr.valid() && !fut_wr.get()) return hz_fail(ctx, HZ_ERR_IO, "write failed");
+        fut_wr = std::async(std::launch::async, [&dst, pin, off_out, btotal] { return dst.write(pin + off_out, btotal); });
         for (size_t i = 0; i < kb; ++i) {
             ChunkMeta& c = h.chunks[(size_t)k0 + i];
             c.index = (uint32_t)(k0 + i);
@@ -316,6 +364,7 @@ int compress_core(hz_ctx* ctx, const Source& src, Sink& dst, uint32_t chunk_byte
         }
         comp_total += btotal; pos += bn; k0 += kb;
     }
+    if (fut_wr.valid() && !fut_wr.get()) return hz_fail(ctx, HZ_ERR_IO, "write failed");
     // global checksum = SHA-256 over the chunk digests in index order (:106-109,126)
     std::vector<uint8_t> cat(32 * (size_t)K);
     for (size_t i = 0; i < (size_t)K; ++i) memcpy(&cat[32 * i], h.chunks[i].sha, 32);
@@ -367,29 +416,60 @@ int decompress_core(hz_ctx* ctx, const Source& src, Sink* dst, hz_progress_fn pr
     Header h; uint64_t data_start = 0;
     HZ_TRY(parse_container(ctx, src, h, &data_start));
     const size_t K = h.chunks.size();
-    // batches of consecutive chunks, up to ~256 MiB of output each
-    size_t k0 = 0, done = 0;
-    while (k0 < K) {
+    // batches of consecutive chunks, up to ~128 MiB of output each; two pinned slots [compressed][output]:
+    // a reader task fetches batch b+1 while batch b is decoded and verified, a writer task drains batch b-1
+    struct Batch { size_t k0, k1; uint64_t ob, cb; };
+    std::vector<Batch> batches;
+    uint64_t max_ob = 0, max_cb = 0;
+    for (size_t k0 = 0; k0 < K; ) {
         size_t k1 = k0; uint64_t ob = 0, cb = 0;
-        while (k1 < K && (k1 == k0 || ob + h.chunks[k1].origSize <= (256ull << 20))) {
+        while (k1 < K && (k1 == k0 || ob + h.chunks[k1].origSize <= (128ull << 20))) {
             ob += h.chunks[k1].origSize; cb += h.chunks[k1].compSize; ++k1;
         }
-        const size_t kb = k1 - k0;
-        const size_t o_comp = 0, o_out = (size_t)((cb + 255) & ~255ull);
-        HZ_TRY(pin_reserve(ctx, o_out + ob + 256));
-        uint8_t* pin = (uint8_t*)ctx->h_pin;
+        batches.push_back({k0, k1, ob, cb});
+        max_ob = std::max(max_ob, ob); max_cb = std::max(max_cb, cb);
+        k0 = k1;
+    }
+    const size_t o_comp = 0, o_out = (size_t)((max_cb + 255) & ~255ull);
+    const size_t slot_bytes = (o_out + max_ob + 256 + 4095) & ~(size_t)4095;
+    if (!batches.empty()) HZ_TRY(pin_reserve(ctx, slot_bytes * (batches.size() > 1 ? 2 : 1)));
+    uint8_t* pin_base = (uint8_t*)ctx->h_pin;
+    // the chunks of a batch are gathered back to back; consecutive chunks of a well-formed file are one extent
+    auto read_batch = [&src, &h, data_start](const Batch& B, uint8_t* dstp) -> long {
+        uint64_t ca = 0;
+        size_t i = B.k0;
+        while (i < B.k1) {
+            size_t j = i; uint64_t ext = 0;
+            const uint64_t start = h.chunks[i].compOff;
+            while (j < B.k1 && h.chunks[j].compOff == start + ext) { ext += h.chunks[j].compSize; ++j; }
+            if (!src.read(data_start + start, dstp + ca, ext)) return (long)i;          // :429-436
+            ca += ext; i = j;
+        }
+        return -1;
+    };
+    std::future<long> fut_rd;
+    std::future<bool> fut_wr;
+    if (!batches.empty()) fut_rd = std::async(std::launch::async, read_batch, batches[0], pin_base + o_comp);
+    size_t done = 0;
+    for (size_t b = 0; b < batches.size(); ++b) {
+        const Batch& B = batches[b];
+        const size_t k0 = B.k0, k1 = B.k1, kb = k1 - k0;
+        uint8_t* pin = pin_base + (b & 1) * slot_bytes;
+        const long bad = fut_rd.get();
+        if (bad >= 0) return hz_fail(ctx, HZ_ERR_IO, "chunk %ld: compressed data out of file bounds", bad);
+        if (b + 1 < batches.size())
+            fut_rd = std::async(std::launch::async, read_batch, batches[b + 1], pin_base + ((b + 1) & 1) * slot_bytes + o_comp);
         std::vector<uint64_t> coff(kb), ooff(kb); std::vector<uint32_t> csz(kb), osz(kb); std::vector<uint8_t> lens(kb * 256);
         uint64_t ca = 0, oa = 0;
         for (size_t i = 0; i < kb; ++i) {
             const ChunkMeta& c = h.chunks[k0 + i];
-            if (!src.read(data_start + c.compOff, pin + o_comp + ca, c.compSize))      // :429-436
-                return hz_fail(ctx, HZ_ERR_IO, "chunk %zu: compressed data out of file bounds", k0 + i);
             coff[i] = ca; csz[i] = c.compSize; ooff[i] = oa; osz[i] = c.origSize;
             memcpy(&lens[256 * i], c.len, 256);
             ca += c.compSize; oa += c.origSize;
         }
-        int rc = hz_decode(ctx, pin + o_comp, cb, coff.data(), csz.data(), osz.data(), ooff.data(), lens.data(),
-                           (uint32_t)kb, pin + o_out, ob);
+        // this slot's output region was handed to the writer two batches ago; that write was joined last batch
+        int rc = hz_decode(ctx, pin + o_comp, B.cb, coff.data(), csz.data(), osz.data(), ooff.data(), lens.data(),
+                           (uint32_t)kb, pin + o_out, B.ob);
         if (rc != HZ_OK) {
             if (rc == HZ_ERR_DECODE || rc == HZ_ERR_BAD_LENGTHS)
                 return hz_fail(ctx, rc, "Chunk decompression failed: %s (chunks %zu..%zu)", hz_strerror(rc), k0, k1 - 1);
@@ -400,11 +480,15 @@ int decompress_core(hz_ctx* ctx, const Source& src, Sink* dst, hz_progress_fn pr
         for (size_t i = 0; i < kb; ++i)
             if (memcmp(&dig[32 * i], h.chunks[k0 + i].sha, 32) != 0)
                 return hz_fail(ctx, HZ_ERR_CHECKSUM, "Checksum mismatch in chunk %zu", k0 + i);
-        if (dst && !dst->write(pin + o_out, ob)) return hz_fail(ctx, HZ_ERR_IO, "write failed");
+        if (dst) {
+            if (fut_wr.valid() && !fut_wr.get()) return hz_fail(ctx, HZ_ERR_IO, "write failed");
+            const uint64_t ob = B.ob;
+            fut_wr = std::async(std::launch::async, [dst, pin, o_out, ob] { return dst->write(pin + o_out, ob); });
+        }
         for (size_t i = 0; i < kb; ++i)
             if (progress) progress((double)(++done) / (double)K, user);                  // :464-467
-        k0 = k1;
     }
+    if (fut_wr.valid() && !fut_wr.get()) return hz_fail(ctx, HZ_ERR_IO, "write failed");
     return HZ_OK;
 }
 

@@ -285,6 +285,25 @@ def test_service_files(hz, tmp_path):
         assert e.value.status == hz.HZ_ERR_FORMAT
 
 
+@pytest.mark.parametrize("n,chunk_mib", [(300 * MiB + 7, 16), (260 * MiB, 1)])
+def test_service_files_multi_batch(hz, tmp_path, n, chunk_mib):
+    """Files larger than one 128 MiB batch go through the double-buffered file pipeline (reader task, GPU +
+    SHA-256, writer task over two pinned slots): the .dcz must still be byte-identical to the oracle's."""
+    data = datasets.zipf_stream(n, 4, seed=77).tobytes()
+    src = tmp_path / "big.bin"; src.write_bytes(data)
+    with hz.B200CompressionService(chunk_mib) as svc:
+        svc.compress(str(src), str(tmp_path / "big.dcz"), None)
+        z = (tmp_path / "big.dcz").read_bytes()
+        mtime = int.from_bytes(z[int.from_bytes(z[-8:], "big") + 12 + 7 + 8:][:8], "big")
+        assert z == orc.compress(data, chunk_mib * MiB, "big.bin", mtime)
+        assert svc.verify_integrity(str(tmp_path / "big.dcz"))
+        svc.decompress(str(tmp_path / "big.dcz"), str(tmp_path / "back.bin"))
+        assert (tmp_path / "back.bin").read_bytes() == data
+        bad = bytearray(z); bad[200 * MiB // 2] ^= 0x5A              # a payload byte of a later batch
+        (tmp_path / "bad.dcz").write_bytes(bytes(bad))
+        assert not svc.verify_integrity(str(tmp_path / "bad.dcz"))
+
+
 def test_legacy_header_first_layout(codec):
     data = b"Hello World! " * 100
     z = orc.compress(data, MiB, "t.txt", 5)
