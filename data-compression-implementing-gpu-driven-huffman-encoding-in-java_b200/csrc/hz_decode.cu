@@ -446,13 +446,10 @@ __device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitR
         // search and come back into the same iteration, so the warp reconverges every lookup.
         uint32_t nx = lds32(r.wa + 4);
         const uint32_t lim12 = limit - LUTB;
-        // 1 that the compiler cannot fold (grids are one-dimensional): multiplies by it keep moves and adds on the
-        // FMA pipe (IMAD) instead of the integer ALU pipe, which is the busier one in this loop
-        const uint32_t one = gridDim.y;
 #define HZ_ASTEP(PI, PO, SFX)                                                  \
     "shf.l.wrap.b32 v, %2, %1, " PI ";\n"                                      \
     "shr.u32 ix, v, 20;\n"                                                     \
-    "mad.lo.u32 ix, ix, %9, %6;\n"                                             \
+    "mad.lo.u32 ix, ix, 2, %6;\n"                                              \
     "ld.shared.u16 e, [ix];\n"                                                 \
     "and.b32 l, e, 63;\n"                                                      \
     "shr.u32 n, e, 12;\n"                                                      \
@@ -464,10 +461,10 @@ __device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitR
     "xor.b32 t, " PI ", " PO ";\n"                                             \
     "and.b32 t, t, 32;\n"                                                      \
     "setp.ne.u32 p0, t, 0;\n"                                                  \
-    "@p0 mad.lo.u32 %1, %2, %10, z;\n"                                         \
+    "@p0 mov.u32 %1, %2;\n"                                                    \
     "@p0 prmt.b32 %2, %4, z, 0x0123;\n"                                        \
     "@p0 ld.shared.u32 %4, [%3+8];\n"                                          \
-    "@p0 mad.lo.u32 %3, %10, %11, %3;\n"                                       \
+    "@p0 add.u32 %3, %3, 4;\n"                                                 \
     "setp.gt.u32 pc, " PO ", %7;\n"
 #define HZ_ARARE(SFX)                                                          \
     "HZA_RARE" SFX ":\n"                                                       \
@@ -496,8 +493,7 @@ __device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitR
             "HZA_END:\n"
             "}\n"
             : "+r"(pos), "+r"(r.hi), "+r"(r.lo), "+r"(r.wa), "+r"(nx), "+r"(cnt)
-            : "r"(slut), "r"(lim12), "r"(slut + (uint32_t)(offsetof(SyncSmem, aux) - offsetof(SyncSmem, slut))),
-              "r"(2u * one), "r"(one), "r"(4u * one)
+            : "r"(slut), "r"(lim12), "r"(slut + (uint32_t)(offsetof(SyncSmem, aux) - offsetof(SyncSmem, slut)))
             : "memory");
 #undef HZ_ASTEP
 #undef HZ_ARARE
@@ -840,7 +836,6 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
     uint8_t* win = gsm + DEC_WRITE_GROUP + (size_t)wid * win_bytes;
     const uint32_t win_a = pin_reg(smem_u32(win)), wlut_a = pin_reg(smem_u32(W.wlut)), aux_a = pin_reg(smem_u32(W.aux));
     const uint32_t stage_a = pin_reg(smem_u32(S.stage));
-    const uint32_t one = gridDim.y;       // 1 the compiler cannot fold: see advance()
     uint32_t phase = 0;                                                // parity of the group's mbarrier
     const uint32_t sub0 = P.sub_base[k], seq0 = P.seq_base[k];
     uint32_t rv_next = 0, sbase_next = 0;
@@ -1002,16 +997,16 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
     "and.b32 a, t, 0x200000;\n"                                               \
     "setp.ne.u32 p1, a, 0;\n"                                                 \
     "shr.u32 F, " CI ", 16;\n"                                                \
-    "@p0 mad.lo.u32 %1, %2, %14, z;\n"                                        \
+    "@p0 mov.u32 %1, %2;\n"                                                   \
     "@p0 prmt.b32 %2, %3, z, 0x0123;\n"                                       \
     "@p0 ld.shared.u32 %3, [%4+8];\n"                                         \
-    "@p0 mad.lo.u32 %4, %14, %15, %4;\n"                                      \
+    "@p0 add.u32 %4, %4, 4;\n"                                                \
     "shf.l.wrap.b32 a, z, ex, F;\n"                                           \
     "shf.l.wrap.b32 t, ex, z, F;\n"                                           \
     "add.u32 %5, %5, a;\n"                                                    \
     "@p1 st.shared.u32 [%6], %5;\n"                                           \
-    "@p1 mad.lo.u32 %6, %14, %15, %6;\n"                                      \
-    "@p1 mad.lo.u32 %5, t, %14, z;\n"
+    "@p1 add.u32 %6, %6, 4;\n"                                                \
+    "selp.b32 %5, t, %5, p1;\n"
 #define HZ_WSTEP(CI, CO, SFX)                                                 \
     "shf.l.wrap.b32 v, %2, %1, " CI ";\n"                                     \
     "shr.u32 ix, v, 20;\n"                                                    \
@@ -1077,8 +1072,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                         "}\n"
                         : "+r"(C), "+r"(r.hi), "+r"(r.lo), "+r"(nx), "+r"(r.wa), "+r"(acc), "+r"(sp)
                         : "r"(Cmain), "r"(smem_u32(W.wlut)), "l"(status),
-                          "n"(LUTN * 8), "n"(offsetof(DecAux, symbase)), "n"(offsetof(DecAux, sorted)), "n"(HZ_ERR_DECODE),
-                          "r"(one), "r"(4u * one)
+                          "n"(LUTN * 8), "n"(offsetof(DecAux, symbase)), "n"(offsetof(DecAux, sorted)), "n"(HZ_ERR_DECODE)
                         : "memory");
 #undef HZ_WSTEP
 #undef HZ_WCHECK
