@@ -15,13 +15,17 @@
 
 #define CB_THREADS 256
 
+// compareTo on heap entries: key(a) > key(b) with key = entry >> 9  <=>  a > (b | 511) (the low 9 bits, the node
+// id, are saturated away) - one 64-bit compare instead of two 64-bit shifts and a compare
+__device__ __forceinline__ bool key_gt(uint64_t a, uint64_t b) { return a > (b | 511ull); }
+
 __device__ __forceinline__ void heap_offer(uint64_t* q, int& size, uint64_t x) {
     int k = size++;
-    const uint64_t xk = x >> 9;
+    const uint64_t xs = x | 511ull;
     while (k > 0) {
         int parent = (k - 1) >> 1;
         uint64_t e = q[parent];
-        if (xk >= (e >> 9)) break;
+        if (!(e > xs)) break;                       // cmp(x, parent) >= 0
         q[k] = e;
         k = parent;
     }
@@ -33,7 +37,6 @@ __device__ __forceinline__ uint64_t heap_poll(uint64_t* q, int& size) {
     int n = --size;
     if (n > 0) {
         uint64_t x = q[n];
-        const uint64_t xk = x >> 9;
         int k = 0;
         const int half = n >> 1;
         while (k < half) {
@@ -42,9 +45,9 @@ __device__ __forceinline__ uint64_t heap_poll(uint64_t* q, int& size) {
             int right = child + 1;
             if (right < n) {
                 uint64_t r = q[right];
-                if ((c >> 9) > (r >> 9)) { c = r; child = right; }
+                if (key_gt(c, r)) { c = r; child = right; }     // cmp(left, right) > 0
             }
-            if (xk <= (c >> 9)) break;
+            if (!key_gt(x, c)) break;                           // cmp(x, child) <= 0
             q[k] = c;
             k = child;
         }
