@@ -446,10 +446,13 @@ __device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitR
         // search and come back into the same iteration, so the warp reconverges every lookup.
         uint32_t nx = lds32(r.wa + 4);
         const uint32_t lim12 = limit - LUTB;
+        // 2 that the compiler cannot fold (grids are one-dimensional): the table address is then an IMAD (FMA pipe)
+        // instead of an LEA on the integer ALU pipe, the busiest pipe of this loop
+        const uint32_t two = 2u * gridDim.y;
 #define HZ_ASTEP(PI, PO, SFX)                                                  \
     "shf.l.wrap.b32 v, %2, %1, " PI ";\n"                                      \
     "shr.u32 ix, v, 20;\n"                                                     \
-    "mad.lo.u32 ix, ix, 2, %6;\n"                                              \
+    "mad.lo.u32 ix, ix, %9, %6;\n"                                             \
     "ld.shared.u16 e, [ix];\n"                                                 \
     "and.b32 l, e, 63;\n"                                                      \
     "shr.u32 n, e, 12;\n"                                                      \
@@ -493,7 +496,7 @@ __device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitR
             "HZA_END:\n"
             "}\n"
             : "+r"(pos), "+r"(r.hi), "+r"(r.lo), "+r"(r.wa), "+r"(nx), "+r"(cnt)
-            : "r"(slut), "r"(lim12), "r"(slut + (uint32_t)(offsetof(SyncSmem, aux) - offsetof(SyncSmem, slut)))
+            : "r"(slut), "r"(lim12), "r"(slut + (uint32_t)(offsetof(SyncSmem, aux) - offsetof(SyncSmem, slut))), "r"(two)
             : "memory");
 #undef HZ_ASTEP
 #undef HZ_ARARE
