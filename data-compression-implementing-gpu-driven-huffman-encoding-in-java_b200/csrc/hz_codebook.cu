@@ -11,6 +11,8 @@
 // Everything around the serial heap (summing segment histograms, leaf depths by parent chasing,
 // canonical code assignment, exact compressed sizes and per-segment output bit offsets) is
 // parallel over the CTA's 256 threads.
+#include <cstdlib>
+#include <cstring>
 #include "hz_common.cuh"
 
 #define CB_THREADS 256
@@ -242,10 +244,10 @@ struct CbWarp {
 
 __global__ void __launch_bounds__(CBW_WARPS * 32)
 codebook_warp_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t K, uint32_t* __restrict__ chunk_hist_out,
-                     uint8_t* __restrict__ len_out, uint32_t* __restrict__ code_out,
+                     uint8_t* len_out, uint32_t* __restrict__ code_out,
                      uint64_t* __restrict__ chunk_bits, uint32_t* __restrict__ comp_size,
                      uint64_t* __restrict__ seg_bitoff, const uint8_t* __restrict__ fixed_len,
-                     const uint32_t* __restrict__ direct_hist, int* status) {
+                     const uint32_t* __restrict__ direct_hist, int lens_ready, int* status) {
     __shared__ CbWarp S[CBW_WARPS];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t k = blockIdx.x * CBW_WARPS + wid;
@@ -277,6 +279,10 @@ codebook_warp_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32
             mylen[j] = fixed_len[lane + 32 * j];
             if (f[j] > 0 && mylen[j] == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS);
         }
+    } else if (lens_ready) {
+        // the heap replay was done by codebook_lane_kernel (32 chunks per warp): leaf depths are in len_out
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mylen[j] = len_out[(size_t)k * 256 + lane + 32 * j];
     } else {
         // 2. the serial part: replay java.util.PriorityQueue (CanonicalHuffman.java:55-70)
         int nsym = 0, root = 0;
@@ -382,6 +388,145 @@ codebook_warp_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Thousands of chunks: ONE LANE per chunk for the serial heap replay.  With one active lane per warp the
+// replay (about 10^5 issue slots per chunk) costs as many issue slots as 32 chunks in lock step do, and it
+// bounded the encode stage of 64 KiB chunks (1.7 ms of 2.7 ms per GiB).  Here every lane of a warp replays
+// the JDK heap of its own chunk; the lanes diverge only in the sift depths.  Heap entries are the same
+// uint64 keys as above, stored [slot][lane] (a lane always stays in its own pair of banks: no conflicts
+// whatever the slots); leaves have node id = symbol, internal nodes 256...; the histogram columns
+// ([sym][lane], stride 33) are consumed by the leaf inserts and their memory then holds the parent
+// links, the heap's memory later holds the node depths (filled top-down: a parent's id is larger than
+// its children's).  Output: the code LENGTHS (leaf depths; a single symbol gets 1) in len_out;
+// codebook_warp_kernel(lens_ready) derives codes, sizes and segment offsets from them.
+// ---------------------------------------------------------------------------------------------
+#define CBL_HS 33
+#define CBL_HEAP_BYTES (256 * 32 * 8)
+#define CBL_SMEM (CBL_HEAP_BYTES + 256 * CBL_HS * 4)
+static_assert(512 * 32 * 2 <= 256 * CBL_HS * 4, "parent links reuse the histogram columns");
+static_assert(2 * (CBL_SMEM + 1024) <= 227 * 1024, "two warps per SM");
+
+__global__ void __launch_bounds__(32)
+codebook_lane_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t K,
+                     const uint32_t* __restrict__ direct_hist, uint8_t* __restrict__ len_out) {
+    extern __shared__ __align__(16) uint8_t cbl_smem[];
+    uint64_t* heap = reinterpret_cast<uint64_t*>(cbl_smem) + threadIdx.x;              // slot i at heap[i * 32]
+    uint32_t* hs = reinterpret_cast<uint32_t*>(cbl_smem + CBL_HEAP_BYTES);               // [sym * CBL_HS + chunk]
+    uint16_t* par = reinterpret_cast<uint16_t*>(cbl_smem + CBL_HEAP_BYTES) + threadIdx.x;   // node i at par[i * 32]
+    uint8_t* dep = cbl_smem + threadIdx.x;                                               // node i at dep[i * 32]
+    const uint32_t lane = threadIdx.x;
+    const uint32_t k0 = blockIdx.x * 32;
+
+    // 1. chunk histograms of the warp's 32 chunks (coalesced: lane = symbol lane + 32 j)
+    for (uint32_t c = 0; c < 32; ++c) {
+        const uint32_t k = k0 + c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t sym = lane + 32 * j;
+            uint32_t a = 0;
+            if (k < K) {
+                if (direct_hist) a = direct_hist[(size_t)k * 256 + sym];
+                else for (uint32_t s = 0; s < spc; ++s) a += seg_hist[((size_t)k * spc + s) * 256 + sym];
+            }
+            hs[sym * CBL_HS + c] = a;
+        }
+    }
+    __syncwarp();
+
+    // 2. leaves in ascending symbol order (CanonicalHuffman.java:56-62): offer = siftUp
+    int size = 0, n = 0, only = 0;
+    for (int s = 0; s < 256; ++s) {
+        const uint32_t fr = hs[s * CBL_HS + lane];
+        if (fr > 0) {
+            const uint64_t x = ((uint64_t)fr << 18) | ((uint64_t)(s + 1) << 9) | (uint64_t)s;
+            const uint64_t xs = x | 511ull;
+            int i = size++;
+            while (i > 0) {
+                const int p = (i - 1) >> 1;
+                const uint64_t e = heap[p * 32];
+                if (!(e > xs)) break;
+                heap[i * 32] = e;
+                i = p;
+            }
+            heap[i * 32] = x;
+            ++n; only = s;
+        }
+    }
+    __syncwarp();                                   // every lane has consumed its histogram column
+    for (int s = 0; s < 256; ++s) par[s * 32] = 0xFFFFu;      // absent symbols keep this
+    // 3. merge loop (CanonicalHuffman.java:64-70): two polls, one offer
+    int next = 256;
+    while (size > 1) {
+        uint64_t lr[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            lr[h] = heap[0];
+            const int m = --size;
+            if (m > 0) {
+                const uint64_t x = heap[m * 32];
+                int i = 0;
+                const int half = m >> 1;
+                while (i < half) {
+                    int child = 2 * i + 1;
+                    uint64_t c = heap[child * 32];
+                    const int right = child + 1;
+                    if (right < m) {
+                        const uint64_t r = heap[right * 32];
+                        if (key_gt(c, r)) { c = r; child = right; }
+                    }
+                    if (!key_gt(x, c)) break;
+                    heap[i * 32] = c;
+                    i = child;
+                }
+                heap[i * 32] = x;
+            }
+        }
+        par[(uint32_t)(lr[0] & 511) * 32] = (uint16_t)next;
+        par[(uint32_t)(lr[1] & 511) * 32] = (uint16_t)next;
+        const uint64_t x = (((lr[0] >> 18) + (lr[1] >> 18)) << 18) | (uint64_t)next;
+        const uint64_t xs = x | 511ull;
+        int i = size++;
+        while (i > 0) {
+            const int p = (i - 1) >> 1;
+            const uint64_t e = heap[p * 32];
+            if (!(e > xs)) break;
+            heap[i * 32] = e;
+            i = p;
+        }
+        heap[i * 32] = x;
+        ++next;
+    }
+    __syncwarp();                                   // the heaps are dead: their memory now holds node depths
+    // 4. depths top-down (extractLengths, :85-92), saturated at 255 (anything > 32 is an error downstream)
+    const int root = next - 1;
+    if (n >= 2) {
+        dep[root * 32] = 0;
+        for (int id = root - 1; id >= 256; --id) {
+            const uint32_t d = dep[(uint32_t)par[id * 32] * 32] + 1u;
+            dep[id * 32] = (uint8_t)(d > 255u ? 255u : d);
+        }
+    }
+    const uint32_t k = k0 + lane;
+    if (k < K) {
+        uint32_t* lo = reinterpret_cast<uint32_t*>(len_out + (size_t)k * 256);
+        for (int s4 = 0; s4 < 64; ++s4) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int s = s4 * 4 + b;
+                uint32_t l = 0;
+                if (n == 1) l = (s == only) ? 1u : 0u;
+                else if (n >= 2) {
+                    const uint32_t p = par[s * 32];
+                    if (p != 0xFFFFu) { l = dep[p * 32] + 1u; if (l > 255u) l = 255u; }
+                }
+                w |= l << (8 * b);
+            }
+            lo[s4] = w;
+        }
+    }
+}
+
 // comp_off[k] = exclusive prefix sum of comp_size (K+1 entries), one CTA of 1024 threads:
 // each thread sums a contiguous slice, the slice totals are scanned, then prefixes are written.
 __global__ void __launch_bounds__(1024)
@@ -455,9 +600,21 @@ int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t spc, uint32_t
     const uint32_t* direct = spc == 0 ? d_seg_hist : nullptr;
     // thousands of small chunks: warp per chunk (more serial heaps in flight per SM)
     if (K >= 1024 && spc <= 32) {
+        int lens_ready = 0;
+        bool lanes = !d_fixed_len256;              // developer knob HZ_CODEBOOK=warp: serial replay on one lane per warp
+        if (const char* ev = getenv("HZ_CODEBOOK")) lanes = lanes && strcmp(ev, "warp") != 0;
+        if (lanes) {
+            if (!ctx->attr_codebook) {
+                HZ_CUDA(ctx, cudaFuncSetAttribute(codebook_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CBL_SMEM));
+                ctx->attr_codebook = true;
+            }
+            HZ_LAUNCH(ctx, "codebook_heap", codebook_lane_kernel, (K + 31) / 32, 32, CBL_SMEM,
+                      spc == 0 ? nullptr : d_seg_hist, spc, K, direct, d_len);
+            lens_ready = 1;
+        }
         HZ_LAUNCH(ctx, "codebook", codebook_warp_kernel, (K + CBW_WARPS - 1) / CBW_WARPS, CBW_WARPS * 32, 0,
                   spc == 0 ? nullptr : d_seg_hist, spc, K, d_chunk_hist, d_len, d_code, d_chunk_bits,
-                  d_comp_size, d_seg_bitoff, d_fixed_len256, direct, ctx->d_status);
+                  d_comp_size, d_seg_bitoff, d_fixed_len256, direct, lens_ready, ctx->d_status);
     } else {
         HZ_LAUNCH(ctx, "codebook", codebook_kernel, K, CB_THREADS, 0,
                   spc == 0 ? nullptr : d_seg_hist, spc, d_chunk_hist, d_len, d_code, d_chunk_bits,

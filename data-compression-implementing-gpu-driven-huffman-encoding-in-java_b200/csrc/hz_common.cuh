@@ -30,7 +30,7 @@ struct hz_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     // kernel attributes (opt-in shared memory) are per device: set once per context, not once per process
-    bool attr_encode = false, attr_decode = false, attr_hist = false;
+    bool attr_encode = false, attr_decode = false, attr_hist = false, attr_codebook = false;
     // device-side status word (first error latched by kernels) + pinned host mirror
     int* d_status = nullptr;
     int* h_status = nullptr;

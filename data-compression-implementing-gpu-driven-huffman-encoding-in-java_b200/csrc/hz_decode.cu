@@ -66,6 +66,7 @@
 #define DEC_TAB_S (LUTN * 8)                    // uint16 slut[LUTN]
 #define DEC_TAB_AUX (LUTN * 8 + LUTN * 2)       // DecAux
 #define DEC_TABLE_BYTES (DEC_TAB_AUX + 1024)
+#define DEC_TAB_PREBUILD_CAP (2ull << 30)        // scratch the prebuilt tables of single-CTA chunks may take
 
 struct __align__(16) DecAux {
     uint64_t lim[34];          // exclusive upper bound of the left-justified (32-bit) codes of each length
@@ -228,7 +229,7 @@ __device__ __forceinline__ uint32_t ceil_div_u64(uint64_t a, uint32_t b) { retur
 
 __global__ void __launch_bounds__(1024)
 dec_plan_kernel(const uint32_t* __restrict__ comp_size, const uint32_t* __restrict__ orig_size,
-                const uint64_t* __restrict__ orig_off_in, uint32_t K, DecPlan P) {
+                const uint64_t* __restrict__ orig_off_in, uint32_t K, DecPlan P, uint32_t tab_min_seq) {
     __shared__ uint64_t part[5][1024];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (K + 1023) / 1024;
@@ -238,7 +239,7 @@ dec_plan_kernel(const uint32_t* __restrict__ comp_size, const uint32_t* __restri
         uint32_t ns = orig_size[i] ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, DEC_SUB_BITS)) : 0;
         uint32_t nq = (ns + DT - 1) / DT;
         s0 += ns; s1 += nq; s2 += (nq + DEC_SEQ_PER_CTA - 1) / DEC_SEQ_PER_CTA; s3 += orig_size[i];
-        s4 += nq > DEC_SEQ_PER_CTA;
+        s4 += nq > tab_min_seq;
     }
     part[0][t] = s0; part[1][t] = s1; part[2][t] = s2; part[3][t] = s3; part[4][t] = s4;
     __syncthreads();
@@ -257,9 +258,9 @@ dec_plan_kernel(const uint32_t* __restrict__ comp_size, const uint32_t* __restri
         uint32_t nq = (ns + DT - 1) / DT;
         P.nsub[i] = ns; P.sub_base[i] = (uint32_t)s0; P.seq_base[i] = (uint32_t)s1; P.cta_base[i] = (uint32_t)s2;
         P.orig_off[i] = orig_off_in ? orig_off_in[i] : s3;
-        P.tab_idx[i] = nq > DEC_SEQ_PER_CTA ? (uint32_t)s4 : DEC_NO_TABLE;
+        P.tab_idx[i] = nq > tab_min_seq ? (uint32_t)s4 : DEC_NO_TABLE;
         s0 += ns; s1 += nq; s2 += (nq + DEC_SEQ_PER_CTA - 1) / DEC_SEQ_PER_CTA; s3 += orig_size[i];
-        s4 += nq > DEC_SEQ_PER_CTA;
+        s4 += nq > tab_min_seq;
     }
 }
 
@@ -1155,13 +1156,20 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     P.seq_base = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
     P.cta_base = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
     P.tab_idx = (uint32_t*)m;
-    HZ_LAUNCH(ctx, "dec_plan", dec_plan_kernel, 1, 1024, 0, d_comp_size, d_orig_size, d_orig_off, K, P);
+    // Chunks decoded by a single CTA used to build their lookup tables inside the sync AND the write kernel
+    // (two builds per chunk, each on a CTA that holds the decode kernels' shared memory): with thousands of
+    // small chunks that was 60 % of the decode time.  While K tables fit DEC_TAB_PREBUILD_CAP bytes of scratch
+    // every chunk's tables are built once by dec_tables_kernel (a small CTA, many per SM) and copied in.
+    uint32_t tab_min_seq = DEC_SEQ_PER_CTA;
+    if ((uint64_t)K * DEC_TABLE_BYTES <= DEC_TAB_PREBUILD_CAP) tab_min_seq = 0;
+    if (const char* ev = getenv("HZ_DEC_PREBUILD")) tab_min_seq = atoi(ev) ? 0 : DEC_SEQ_PER_CTA;   // developer knob
+    HZ_LAUNCH(ctx, "dec_plan", dec_plan_kernel, 1, 1024, 0, d_comp_size, d_orig_size, d_orig_off, K, P, tab_min_seq);
     // upper bounds (no host sync): every chunk has at most ceil(comp_size*8/SUB_BITS)+1 subsequences
     const uint64_t max_sub = comp_bytes * 8 / DEC_SUB_BITS + 2ull * K + 2;
     const uint64_t max_seq = max_sub / DT + K + 1;
     const uint64_t max_cta = max_seq / DEC_SEQ_PER_CTA + K + 1;
     uint64_t max_tab = comp_bytes / ((uint64_t)DEC_SEQ_PER_CTA * DEC_SEQ_BYTES) + 1;
-    if (max_tab > K) max_tab = K;
+    if (max_tab > K || tab_min_seq == 0) max_tab = K;
     if (max_cta > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "decode grid too large");
     HZ_TRY(hz_reserve(ctx, &ctx->dec_rec, max_sub * sizeof(uint32_t)));
     HZ_TRY(hz_reserve(ctx, &ctx->dec_seqcnt, max_seq * sizeof(uint32_t)));
@@ -1192,8 +1200,9 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     if (groups < 1) groups = 1;
     // chunks of a few sequences each build their table inside the CTA: two independent CTAs per SM
     // (two table builds in flight) beat one CTA whose extra groups wait for the build
+    const uint32_t fit = groups;
     if (comp_bytes / K < 4ull * DEC_SEQ_BYTES) groups = 1;
-    if (const char* ev = getenv("HZ_DEC_GROUPS")) { int v = atoi(ev); if (v >= 1 && v <= (int)groups) groups = (uint32_t)v; }
+    if (const char* ev = getenv("HZ_DEC_GROUPS")) { int v = atoi(ev); if (v >= 1 && v <= (int)fit) groups = (uint32_t)v; }
     uint32_t bulk_out = 1;                 // developer knob: HZ_DEC_BULK=0 copies the windows out with 128-bit stores
     if (const char* ev = getenv("HZ_DEC_BULK")) bulk_out = atoi(ev) != 0;
     HZ_LAUNCH(ctx, "dec_write", dec_write_kernel, (unsigned)max_cta, DT * groups, DEC_WRITE_SHARED + groups * gbytes,

@@ -433,6 +433,36 @@ def test_many_small_chunks_warp_codebook(codec):
     _check_codebooks(codec, hist)
 
 
+def test_lane_codebook_ties_and_long_codes(codec, hz):
+    """K >= 1024 histograms take the lane-per-chunk heap replay (codebook_lane_kernel): tie-heavy, sparse,
+    one-symbol, empty and long-code histograms, mixed inside the same warps, must give the oracle's lengths."""
+    rng = np.random.default_rng(11)
+    hs = np.zeros((1400, 256), dtype=np.uint32)
+    for k in range(1400):
+        kind = k % 8
+        if kind == 0:
+            hs[k] = rng.choice([1, 2, 3], 256)
+        elif kind == 1:
+            m = int(rng.integers(1, 257)); hs[k, rng.choice(256, m, replace=False)] = 1
+        elif kind == 2:
+            hs[k] = 2 ** rng.integers(0, 12, 256)
+        elif kind == 3:
+            hs[k, int(rng.integers(0, 256))] = int(rng.integers(1, 70000))       # one symbol
+        elif kind == 4:
+            pass                                                                   # empty chunk
+        elif kind == 5:
+            hs[k] = datasets.fib_like_hist(int(rng.integers(2, 34))).astype(np.uint32)   # max length up to 32
+        elif kind == 6:
+            hs[k] = rng.integers(0, 4, 256)
+        else:
+            hs[k] = rng.integers(1, 1 << 16, 256)
+    _check_codebooks(codec, hs)
+    hs[777] = datasets.fib_like_hist(34).astype(np.uint32)                         # depth 33: reference throws
+    with pytest.raises(hz.HzError) as e:
+        codec.build_codebooks(hs)
+    assert e.value.status == hz.HZ_ERR_CODE_TOO_LONG
+
+
 def test_two_contexts_one_process(hz):
     """Kernel attributes (opt-in shared memory) are set per context, not once per process."""
     data = datasets.zipf_stream(700_000, 4, seed=5)
