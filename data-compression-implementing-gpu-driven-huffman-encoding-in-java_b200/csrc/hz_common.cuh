@@ -116,4 +116,36 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 
 __device__ __forceinline__ void hz_set_status(int* status, int code) {
     if (code != 0) atomicCAS(status, 0, code);
 }
+
+// Copies n bytes src -> dst with the nthr threads of a group (tid = 0 .. nthr-1), any alignment of either
+// pointer: dst-aligned 128-bit stores; a source that is not 16-byte aligned is read as 4-byte aligned words
+// and funnel-shifted into place (an aligned word that holds one valid byte never leaves the allocation).
+// Used where a chunk's code is the identity (all 256 symbols with 8-bit codes: canonical code == symbol),
+// so that encoding / decoding it is a byte copy.
+__device__ __forceinline__ void hz_group_copy(uint8_t* dst, const uint8_t* src, uint64_t n, uint32_t tid, uint32_t nthr) {
+    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (head > n) head = n;
+    if (tid < head) dst[tid] = src[tid];
+    const uint8_t* s = src + head;
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    const uint64_t units = (n - head) >> 4;
+    if ((reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(s);
+#pragma unroll 4
+        for (uint64_t u = tid; u < units; u += nthr) d4[u] = ld_stream_u4(s4 + u);
+    } else {
+        const uint32_t r = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3), sh = r * 8;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s - r);
+#pragma unroll 4
+        for (uint64_t u = tid; u < units; u += nthr) {
+            const uint32_t* w = sw + u * 4;
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+            const uint32_t w4 = r ? __ldg(w + 4) : 0u;
+            d4[u] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                               __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        }
+    }
+    const uint64_t done = head + (units << 4);
+    if (tid < n - done) dst[done + tid] = src[done + tid];
+}
 #endif

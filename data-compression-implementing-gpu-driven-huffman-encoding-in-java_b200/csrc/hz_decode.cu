@@ -223,44 +223,95 @@ __device__ __forceinline__ void copy_g2s16(void* dst, const void* src, uint32_t 
 // ---------------------------------------------------------------------------------------------
 struct DecPlan {
     uint32_t* nsub; uint32_t* sub_base; uint32_t* seq_base; uint32_t* cta_base; uint32_t* tab_idx; uint64_t* orig_off;
+    uint32_t* islice;          // [K+1] copy slices of the identity chunks before chunk k
 };
+#define DEC_IDENT_SLICE 65536u
 
 __device__ __forceinline__ uint32_t ceil_div_u64(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
 __global__ void __launch_bounds__(1024)
 dec_plan_kernel(const uint32_t* __restrict__ comp_size, const uint32_t* __restrict__ orig_size,
-                const uint64_t* __restrict__ orig_off_in, uint32_t K, DecPlan P, uint32_t tab_min_seq) {
-    __shared__ uint64_t part[5][1024];
+                const uint64_t* __restrict__ orig_off_in, uint32_t K, DecPlan P, uint32_t tab_min_seq,
+                const uint8_t* __restrict__ ident) {
+    __shared__ uint64_t part[6][1024];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (K + 1023) / 1024;
     const uint32_t lo = min(K, t * per), hi = min(K, lo + per);
-    uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+    uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
     for (uint32_t i = lo; i < hi; ++i) {
-        uint32_t ns = orig_size[i] ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, DEC_SUB_BITS)) : 0;
+        s5 += ident[i] ? (orig_size[i] + DEC_IDENT_SLICE - 1) / DEC_IDENT_SLICE : 0u;
+        uint32_t ns = (orig_size[i] && !ident[i]) ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, DEC_SUB_BITS)) : 0;
         uint32_t nq = (ns + DT - 1) / DT;
         s0 += ns; s1 += nq; s2 += (nq + DEC_SEQ_PER_CTA - 1) / DEC_SEQ_PER_CTA; s3 += orig_size[i];
         s4 += nq > tab_min_seq;
     }
-    part[0][t] = s0; part[1][t] = s1; part[2][t] = s2; part[3][t] = s3; part[4][t] = s4;
+    part[0][t] = s0; part[1][t] = s1; part[2][t] = s2; part[3][t] = s3; part[4][t] = s4; part[5][t] = s5;
     __syncthreads();
-    if (t < 5) {
+    if (t < 6) {
         uint64_t a = 0;
         for (int j = 0; j < 1024; ++j) { uint64_t x = part[t][j]; part[t][j] = a; a += x; }
         if (t == 0) P.sub_base[K] = (uint32_t)a;
         if (t == 1) P.seq_base[K] = (uint32_t)a;
         if (t == 2) P.cta_base[K] = (uint32_t)a;
         if (t == 3) P.orig_off[K] = a;
+        if (t == 5) P.islice[K] = (uint32_t)a;
     }
     __syncthreads();
-    s0 = part[0][t]; s1 = part[1][t]; s2 = part[2][t]; s3 = part[3][t]; s4 = part[4][t];
+    s0 = part[0][t]; s1 = part[1][t]; s2 = part[2][t]; s3 = part[3][t]; s4 = part[4][t]; s5 = part[5][t];
     for (uint32_t i = lo; i < hi; ++i) {
-        uint32_t ns = orig_size[i] ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, DEC_SUB_BITS)) : 0;
+        P.islice[i] = (uint32_t)s5;
+        s5 += ident[i] ? (orig_size[i] + DEC_IDENT_SLICE - 1) / DEC_IDENT_SLICE : 0u;
+        uint32_t ns = (orig_size[i] && !ident[i]) ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, DEC_SUB_BITS)) : 0;
         uint32_t nq = (ns + DT - 1) / DT;
         P.nsub[i] = ns; P.sub_base[i] = (uint32_t)s0; P.seq_base[i] = (uint32_t)s1; P.cta_base[i] = (uint32_t)s2;
         P.orig_off[i] = orig_off_in ? orig_off_in[i] : s3;
         P.tab_idx[i] = nq > tab_min_seq ? (uint32_t)s4 : DEC_NO_TABLE;
         s0 += ns; s1 += nq; s2 += (nq + DEC_SEQ_PER_CTA - 1) / DEC_SEQ_PER_CTA; s3 += orig_size[i];
         s4 += nq > tab_min_seq;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Identity chunks.  When all 256 symbols of a chunk have 8-bit codes (incompressible data: every byte value
+// about equally frequent), generateCanonicalCodesFromLengths assigns code[s] == s (CanonicalHuffman.java:
+// 99-132: codes of one length are consecutive in symbol order), so the chunk's payload IS its plaintext and
+// decoding it is a byte copy at HBM speed instead of a table walk.  The flags kernel marks such chunks (one
+// warp per chunk); the plan gives them no subsequences, so the sync / fix / write kernels never see them;
+// the copy kernel (persistent grid over 64 KiB slices, located through the plan's slice prefix sums) moves them.  Bytes the stream lacks
+// (comp_size < orig_size) decode as symbol 0, like zero bits past the end (TableBasedHuffmanDecoder.java:204-208).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DT)
+dec_ident_flags_kernel(const uint8_t* __restrict__ len_tab, const uint32_t* __restrict__ orig_size, uint32_t K,
+                       uint8_t* __restrict__ ident, uint32_t enable) {
+    const uint32_t k = blockIdx.x * (DT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= K) return;
+    const uint2 v = reinterpret_cast<const uint2*>(len_tab + (size_t)k * 256)[lane];
+    const bool all8 = __all_sync(0xffffffffu, v.x == 0x08080808u && v.y == 0x08080808u);
+    if (lane == 0) ident[k] = enable && all8 && orig_size[k] != 0;
+}
+
+__global__ void __launch_bounds__(DT)
+dec_ident_copy_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ comp_off,
+                      const uint32_t* __restrict__ comp_size, const uint32_t* __restrict__ orig_size,
+                      const uint64_t* __restrict__ orig_off, const uint32_t* __restrict__ islice, uint32_t K,
+                      uint8_t* __restrict__ out, uint64_t out_cap, int* status) {
+    const uint32_t total = islice[K];
+    for (uint32_t j = blockIdx.x; j < total; j += gridDim.x) {
+        uint32_t lo = 0, hi = K;                       // largest k with islice[k] <= j (identity chunks have >= 1 slice)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (islice[mid] <= j) lo = mid; else hi = mid;
+        }
+        const uint32_t k = lo;
+        const uint32_t osize = orig_size[k], csize = comp_size[k];
+        const uint64_t ooff = orig_off[k];
+        if (ooff + osize > out_cap) { if (threadIdx.x == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
+        const uint32_t have = csize < osize ? csize : osize;
+        const uint32_t b0 = (j - islice[k]) * DEC_IDENT_SLICE;
+        const uint32_t b1 = min(osize, b0 + DEC_IDENT_SLICE);
+        const uint32_t c1 = min(have, b1);
+        if (c1 > b0) hz_group_copy(out + ooff + b0, comp + comp_off[k] + b0, c1 - b0, threadIdx.x, DT);
+        for (uint32_t b = max(b0, c1) + threadIdx.x; b < b1; b += DT) out[ooff + b] = 0;
     }
 }
 
@@ -1147,7 +1198,7 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
                const uint8_t* d_len, uint32_t K, uint8_t* d_out, uint64_t out_cap) {
     if (K == 0) return HZ_OK;
     // plan arrays
-    HZ_TRY(hz_reserve(ctx, &ctx->dec_meta, ((size_t)K + 1) * (5 * sizeof(uint32_t) + sizeof(uint64_t)) + 64));
+    HZ_TRY(hz_reserve(ctx, &ctx->dec_meta, ((size_t)K + 1) * (6 * sizeof(uint32_t) + sizeof(uint64_t)) + 64));
     DecPlan P;
     uint8_t* m = (uint8_t*)ctx->dec_meta.p;
     P.orig_off = (uint64_t*)m; m += ((size_t)K + 1) * sizeof(uint64_t);
@@ -1155,7 +1206,8 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     P.sub_base = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
     P.seq_base = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
     P.cta_base = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
-    P.tab_idx = (uint32_t*)m;
+    P.tab_idx = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
+    P.islice = (uint32_t*)m;
     // Chunks decoded by a single CTA used to build their lookup tables inside the sync AND the write kernel
     // (two builds per chunk, each on a CTA that holds the decode kernels' shared memory): with thousands of
     // small chunks that was 60 % of the decode time.  While K tables fit DEC_TAB_PREBUILD_CAP bytes of scratch
@@ -1163,7 +1215,12 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     uint32_t tab_min_seq = DEC_SEQ_PER_CTA;
     if ((uint64_t)K * DEC_TABLE_BYTES <= DEC_TAB_PREBUILD_CAP) tab_min_seq = 0;
     if (const char* ev = getenv("HZ_DEC_PREBUILD")) tab_min_seq = atoi(ev) ? 0 : DEC_SEQ_PER_CTA;   // developer knob
-    HZ_LAUNCH(ctx, "dec_plan", dec_plan_kernel, 1, 1024, 0, d_comp_size, d_orig_size, d_orig_off, K, P, tab_min_seq);
+    HZ_TRY(hz_reserve(ctx, &ctx->dec_misc, (size_t)K + 64));
+    uint8_t* ident = (uint8_t*)ctx->dec_misc.p;
+    uint32_t ident_on = 1;                 // developer knob: HZ_IDENT=0 sends identity chunks through the table walk
+    if (const char* ev = getenv("HZ_IDENT")) ident_on = atoi(ev) != 0;
+    HZ_LAUNCH(ctx, "dec_ident", dec_ident_flags_kernel, (K + DT / 32 - 1) / (DT / 32), DT, 0, d_len, d_orig_size, K, ident, ident_on);
+    HZ_LAUNCH(ctx, "dec_plan", dec_plan_kernel, 1, 1024, 0, d_comp_size, d_orig_size, d_orig_off, K, P, tab_min_seq, ident);
     // upper bounds (no host sync): every chunk has at most ceil(comp_size*8/SUB_BITS)+1 subsequences
     const uint64_t max_sub = comp_bytes * 8 / DEC_SUB_BITS + 2ull * K + 2;
     const uint64_t max_seq = max_sub / DT + K + 1;
@@ -1182,6 +1239,8 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
         HZ_CUDA(ctx, cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         ctx->attr_decode = true;
     }
+    HZ_LAUNCH(ctx, "dec_ident_copy", dec_ident_copy_kernel, 8 * ctx->sm_count, DT, 0, d_comp, d_comp_off, d_comp_size,
+              d_orig_size, P.orig_off, P.islice, K, d_out, out_cap, ctx->d_status);
     HZ_LAUNCH(ctx, "dec_tables", dec_tables_kernel, K, DT, 0, d_len, P, tables, ctx->d_status);
     HZ_LAUNCH(ctx, "dec_sync", dec_sync_kernel, (unsigned)max_cta, DT, sizeof(SyncSmem),
               d_comp, comp_bytes, d_comp_off, d_comp_size, d_len, K, P, tables, rec, seqcnt, ctx->d_status);

@@ -35,6 +35,7 @@
 // chunks whose longest code exceeds 27 bits take the "wide" instantiation (8 symbols per thread
 // per tile, 64-bit LUT entries, a completed-word check after every symbol, every dense word
 // OR-ed): correct for lengths up to 32, slower; it also serves the ragged last tile of a segment.
+#include <cstdlib>
 #include "hz_common.cuh"
 
 #define ENC_SPT 32                                  // symbols per thread per tile (fast path)
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(ENC_CTA, 2)
 encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t spc, uint32_t cpc, uint32_t mult,
               const uint8_t* __restrict__ len_tab, const uint32_t* __restrict__ code_tab,
               const uint64_t* __restrict__ comp_off, const uint64_t* __restrict__ seg_bitoff,
-              uint32_t K, uint8_t* __restrict__ out, uint64_t out_cap, int* status) {
+              uint32_t K, uint8_t* __restrict__ out, uint64_t out_cap, uint32_t ident_on, int* status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t t = threadIdx.x, lane = t & 31;
     const uint32_t grp = t / HZ_THREADS, tg = t % HZ_THREADS, wid = tg >> 5;
@@ -370,6 +371,12 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
     uint32_t w[8], wn[8];
     if (full_tiles) load_syms32(q, lmode, 32, wn);
     if (total_bytes > out_cap) { if (t == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
+    // Identity chunk: all 256 symbols have 8-bit codes, so the canonical code of a symbol is the symbol itself
+    // (CanonicalHuffman.java:99-132) and the chunk's bitstream is its plaintext - a byte copy (incompressible data).
+    if (__syncthreads_and(ident_on && mylen == 8)) {
+        if (!idle) hz_group_copy(out + chunk_off + sbeg, p, slen, tg, HZ_THREADS);
+        return;
+    }
 
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);
     uint8_t* gsm = smem_raw + ENC_LUT_BYTES + grp * ENC_G_BYTES;
@@ -523,7 +530,9 @@ int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_byte
         HZ_CUDA(ctx, cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
         ctx->attr_encode = true;
     }
+    uint32_t ident_on = 1;                 // developer knob: HZ_IDENT=0 sends identity chunks through the bit packer
+    if (const char* ev = getenv("HZ_IDENT")) ident_on = atoi(ev) != 0;
     HZ_LAUNCH(ctx, "encode", encode_kernel, (unsigned)grid, ENC_CTA, ENC_SMEM_BYTES,
-              d_in, n, chunk_bytes, spc, cpc, mult, d_len, d_code, d_comp_off, d_seg_bitoff, K, d_out, out_cap, ctx->d_status);
+              d_in, n, chunk_bytes, spc, cpc, mult, d_len, d_code, d_comp_off, d_seg_bitoff, K, d_out, out_cap, ident_on, ctx->d_status);
     return HZ_OK;
 }

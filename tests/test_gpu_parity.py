@@ -221,6 +221,42 @@ def test_decode_reads_zero_bits_past_the_end(codec):
     assert rc == 0 and np.array_equal(out, ref)
 
 
+def _perm_blocks(rng, nbytes):
+    """Bytes in which every value occurs equally often per 256-byte block (-> all 256 code lengths are 8)."""
+    nb = (nbytes + 255) // 256
+    return np.concatenate([rng.permutation(256).astype(np.uint8) for _ in range(nb)])[:nbytes]
+
+
+@pytest.mark.parametrize("chunk", [4096, 65536 + 256, 1 * MiB + 512])
+def test_identity_chunks_take_the_copy_path(codec, chunk):
+    """A chunk whose 256 symbols all get 8-bit codes has code[s] == s: encode and decode are byte copies
+    (hz_group_copy).  Mixed with ordinary chunks so that chunk offsets are odd (every source / destination
+    misalignment), with ragged tails, against the oracle bit for bit."""
+    rng = np.random.default_rng(chunk)
+    K = 9
+    parts = []
+    for k in range(K):
+        if k % 3 == 1:
+            parts.append(datasets.zipf_stream(chunk, 1 + k % 7, seed=k))          # ordinary chunk, odd payload size
+        else:
+            parts.append(_perm_blocks(rng, chunk))
+    parts.append(_perm_blocks(rng, 256 * 5))                                      # short identity tail chunk
+    data = np.concatenate(parts)
+    payload, off, lens = check_encode(codec, data, chunk)
+    ident = [k for k in range(K + 1) if (lens[k] == 8).all()]
+    assert len(ident) >= 6
+    for k in ident:
+        assert np.array_equal(payload[int(off[k]):int(off[k + 1])], data[k * chunk:(k + 1) * chunk])
+    # a truncated identity chunk: missing bytes decode as symbol 0 (zero bits past the end), like the oracle
+    k = ident[1]
+    comp = payload[int(off[k]):int(off[k + 1])].copy()
+    n = comp.size
+    out = codec.decode(comp[:n - 100], [0], [n - 100], [n], lens[k:k + 1])
+    ref, rc = orc.decode(comp[:n - 100], lens[k].astype(np.int32), n, literal=True)
+    assert rc == 0 and np.array_equal(out, ref)
+    assert np.array_equal(out[:n - 100], comp[:n - 100]) and not out[n - 100:].any()
+
+
 def test_deterministic(codec):
     data = datasets.zipf_stream(3 * MiB, 4, seed=77)
     a = codec.encode(data, MiB)
