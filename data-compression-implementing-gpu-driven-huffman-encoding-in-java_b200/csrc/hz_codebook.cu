@@ -601,8 +601,10 @@ int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t spc, uint32_t
     // thousands of small chunks: warp per chunk (more serial heaps in flight per SM)
     if (K >= 1024 && spc <= 32) {
         int lens_ready = 0;
-        bool lanes = !d_fixed_len256;              // developer knob HZ_CODEBOOK=warp: serial replay on one lane per warp
-        if (const char* ev = getenv("HZ_CODEBOOK")) lanes = lanes && strcmp(ev, "warp") != 0;
+        // lane-per-chunk replay: a warp of 32 chunks takes ~1.7x as long as one chunk on one lane (0.48 vs 0.29 ms),
+        // so it pays once the warp-per-chunk kernel needs more than one wave of ~40 warps per SM
+        bool lanes = !d_fixed_len256 && K >= 8192;
+        if (const char* ev = getenv("HZ_CODEBOOK")) lanes = !d_fixed_len256 && strcmp(ev, "warp") != 0;   // developer knob: warp | lane
         if (lanes) {
             if (!ctx->attr_codebook) {
                 HZ_CUDA(ctx, cudaFuncSetAttribute(codebook_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CBL_SMEM));

@@ -45,19 +45,25 @@
 #include "hz_common.cuh"
 
 #define DT 256
+#ifndef DEC_SUB_WORDS
 #define DEC_SUB_WORDS 17                      // odd: subsequences start in different smem banks
+#endif
 #define DEC_SUB_BITS (DEC_SUB_WORDS * 32)     // 544
 #define DEC_SUB_BYTES (DEC_SUB_WORDS * 4)     // 68
 #define DEC_SEQ_BYTES (DT * DEC_SUB_BYTES)    // 17408
 #define DEC_SEQ_BITS (DT * DEC_SUB_BITS)
+#ifndef DEC_OVERLAP_BITS
 #define DEC_OVERLAP_BITS 128
-#define DEC_OVERLAP_BYTES 16
+#endif
+#define DEC_OVERLAP_BYTES (DEC_OVERLAP_BITS / 8)
+#ifndef DEC_SEQ_PER_CTA
 #define DEC_SEQ_PER_CTA 12                    // divisible by 1, 2 and 3 write groups
+#endif
 #define DEC_SUBS_PER_CTA (DT * DEC_SEQ_PER_CTA)
 #define LUTB 12
 #define LUTN (1 << LUTB)
 // staged bytes per sequence: 16 alignment slack + 16 overlap + sequence + 32 look-ahead
-#define DEC_STAGE_BYTES (16 + DEC_OVERLAP_BYTES + DEC_SEQ_BYTES + 32)
+#define DEC_STAGE_BYTES ((16 + DEC_OVERLAP_BYTES + DEC_SEQ_BYTES + 32 + 15) & ~15)
 #define DEC_STAGE_WORDS (DEC_STAGE_BYTES / 4)
 #define DEC_WIN_MIN 2304                      // per-warp output window of the write kernel (runtime sized)
 #define DEC_WIN_MAX 9216
@@ -100,8 +106,6 @@ template <bool WANT_W, bool WANT_S>
 __device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __restrict__ slut,
                              uint8_t* __restrict__ scratch, const uint8_t* __restrict__ len_k) {
     uint16_t* base = reinterpret_cast<uint16_t*>(scratch);                // [LUTN] sym | len<<8
-    uint16_t* lj = reinterpret_cast<uint16_t*>(scratch + LUTN * 2);       // [256] left-justified codes (len<=12)
-    uint8_t* ljl = scratch + LUTN * 2 + 512;                              // [256] their lengths
     uint32_t* cntw = reinterpret_cast<uint32_t*>(scratch + LUTN * 2 + 768);   // [8][34]
     uint32_t* first = cntw + 8 * 34;                                      // [34] first canonical code per length
     uint32_t* count = first + 34;                                         // [34] symbols per length
@@ -144,36 +148,31 @@ __device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __re
     if (l >= 1 && l <= 32) {
         uint32_t rank = rank_w;
         for (uint32_t w = 0; w < wid; ++w) rank += cntw[w * 34 + l];
-        const uint32_t pos = offs[l] + rank;
-        A.sorted[pos] = (uint8_t)t;
-        if (l <= LUTB) { lj[pos] = (uint16_t)((first[l] + rank) << (LUTB - l)); ljl[pos] = (uint8_t)l; }
+        A.sorted[offs[l] + rank] = (uint8_t)t;
     }
     bt_sync();
-    // single-symbol table: thread t fills entries [16t, 16t+16)
-    const uint32_t n12 = offs[LUTB + 1];          // symbols with length <= LUTB, sorted by code value
+    // single-symbol table.  The left-justified codes of a canonical code are ordered by length, so the code
+    // that starts a 12-bit prefix x has the first length l with x < lim12[l] (lim12 = A.lim >> 20, exact for
+    // l <= LUTB): LUTB register compares per entry, no search.  Thread t fills entries t, t + 256, ...
+    // (consecutive lanes -> consecutive entries: conflict-free shared accesses, coalesced table stores).
     {
-        const uint32_t x0 = t * 16;
-        uint32_t i = 0;
-        if (n12) {                                 // largest i with lj[i] <= x0 (lj[0] == 0)
-            uint32_t lo = 0, hi = n12;
-            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (lj[mid] <= x0) lo = mid; else hi = mid; }
-            i = lo;
-        }
+        uint32_t lim12[LUTB + 1];
+#pragma unroll
+        for (int L = 1; L <= LUTB; ++L) lim12[L] = (uint32_t)(A.lim[L] >> (32 - LUTB));
 #pragma unroll 4
-        for (uint32_t x = x0; x < x0 + 16; ++x) {
+        for (uint32_t x = t; x < LUTN; x += DT) {
+            uint32_t li = 1;
+#pragma unroll
+            for (int L = 1; L <= LUTB; ++L) li += x >= lim12[L];
             uint16_t e = 0;
-            if (n12) {
-                while (i + 1 < n12 && lj[i + 1] <= x) ++i;
-                const uint32_t li = ljl[i], b = lj[i];
-                if (x >= b && x < b + (1u << (LUTB - li))) e = (uint16_t)(A.sorted[i] | (li << 8));
-            }
+            if (li <= LUTB) e = (uint16_t)(A.sorted[A.symbase[li] + (int32_t)(x >> (LUTB - li))] | (li << 8));
             base[x] = e;
         }
     }
     bt_sync();
     // multi-symbol tables
     const uint32_t maxlen = (uint32_t)A.maxlen;
-    for (uint32_t x = t * 16; x < t * 16 + 16; ++x) {
+    for (uint32_t x = t; x < LUTN; x += DT) {
         const uint32_t e0 = base[x];
         uint2 we = make_uint2(0u, 0xC0000000u);
         uint32_t se = 0;

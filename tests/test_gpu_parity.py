@@ -470,11 +470,11 @@ def test_many_small_chunks_warp_codebook(codec):
 
 
 def test_lane_codebook_ties_and_long_codes(codec, hz):
-    """K >= 1024 histograms take the lane-per-chunk heap replay (codebook_lane_kernel): tie-heavy, sparse,
+    """K >= 8192 histograms take the lane-per-chunk heap replay (codebook_lane_kernel): tie-heavy, sparse,
     one-symbol, empty and long-code histograms, mixed inside the same warps, must give the oracle's lengths."""
     rng = np.random.default_rng(11)
-    hs = np.zeros((1400, 256), dtype=np.uint32)
-    for k in range(1400):
+    hs = np.zeros((8300, 256), dtype=np.uint32)
+    for k in range(8300):
         kind = k % 8
         if kind == 0:
             hs[k] = rng.choice([1, 2, 3], 256)
@@ -497,6 +497,11 @@ def test_lane_codebook_ties_and_long_codes(codec, hz):
     with pytest.raises(hz.HzError) as e:
         codec.build_codebooks(hs)
     assert e.value.status == hz.HZ_ERR_CODE_TOO_LONG
+    # the whole encode stage with K >= 8192 chunks (segment histograms feed the lane kernel), ragged last chunk
+    n, chunk = 8200 * 512 + 99, 512
+    data = datasets.zipf_stream(n, 5, seed=3).copy()
+    data[9 * chunk:10 * chunk] = 0x5A                                              # a one-symbol chunk
+    check_encode(codec, data, chunk)
 
 
 def test_two_contexts_one_process(hz):
