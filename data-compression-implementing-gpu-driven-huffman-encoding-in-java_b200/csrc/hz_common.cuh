@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "../../include/huffb200.h"
@@ -15,6 +16,15 @@
 // ---------------------------------------------------------------------------------------------
 #define HZ_THREADS 256
 #define HZ_SEG_BYTES 57344u
+// An encoder group codes a RANGE of `mult` consecutive segments of a chunk from one starting bit offset
+// (longer ranges amortise the per-range start-up; short chunks keep them short so that both groups of a
+// CTA have work).  The histogram kernel counts a whole range per CTA into the range's FIRST segment slot
+// and zeroes the others: every consumer either sums a chunk's slots or reads the offset of a range start.
+static inline uint32_t hz_range_mult(uint32_t spc) {
+    uint32_t m = spc >= 64 ? 4u : (spc >= 16 ? 2u : 1u);
+    if (const char* ev = getenv("HZ_RANGE_MULT")) { const int v = atoi(ev); if (v >= 1 && v <= 64 && spc >= 64) m = (uint32_t)v; }   // developer knob
+    return m;
+}
 
 struct hz_prof_entry { const char* name; double ms; uint64_t launches; };
 

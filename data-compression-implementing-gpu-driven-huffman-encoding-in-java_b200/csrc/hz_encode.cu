@@ -521,7 +521,7 @@ int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_byte
     const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
     // longer ranges amortise the per-range start-up (LUT build, zeroing, first loads); short
     // chunks keep them short so that both groups of a CTA have work
-    const uint32_t mult = spc >= 64 ? 4 : (spc >= 16 ? 2 : 1);
+    const uint32_t mult = hz_range_mult(spc);
     const uint32_t rpc = (spc + mult - 1) / mult;                      // ranges per chunk
     const uint32_t cpc = (rpc + ENC_GROUPS - 1) / ENC_GROUPS;
     const uint64_t grid = (uint64_t)K * cpc;

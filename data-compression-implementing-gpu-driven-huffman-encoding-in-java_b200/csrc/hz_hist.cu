@@ -160,14 +160,25 @@ hist_seg_atomic(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes
 // IMAD (bin*128 + lane address), RED.  The 32 columns of a bin are summed with a rotated,
 // conflict-free read at the end.
 __global__ void __launch_bounds__(HZ_THREADS)
-hist_seg_lanes(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t spc,
+hist_seg_lanes(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t spc, uint32_t mult,
                uint32_t* __restrict__ seg_hist) {
     __shared__ __align__(16) uint32_t h[256 * 32];
     const uint32_t t = threadIdx.x, lane = t & 31;
-    uint64_t sbeg; uint32_t slen;
-    seg_geometry(n, chunk_bytes, spc, &sbeg, &slen);
-    uint32_t* dst = seg_hist + (size_t)blockIdx.x * 256;
-    if (slen == 0) { dst[t] = 0; return; }
+    // one CTA per RANGE of `mult` segments (the unit an encoder group codes): the 32 KiB of counters are
+    // zeroed and column-summed once per range instead of once per segment (a third of the kernel's
+    // shared-memory wavefronts at one segment per CTA); the range's bins go to its first segment slot
+    const uint32_t rpc = (spc + mult - 1) / mult;
+    const uint32_t k = blockIdx.x / rpc, s0 = (blockIdx.x - k * rpc) * mult;
+    const uint64_t cbeg = (uint64_t)k * chunk_bytes;
+    const uint64_t clen = n - cbeg < chunk_bytes ? n - cbeg : chunk_bytes;
+    const uint64_t rbeg = (uint64_t)s0 * HZ_SEG_BYTES;
+    uint32_t* dst = seg_hist + ((size_t)k * spc + s0) * 256;
+    const uint32_t nslots = spc - s0 < mult ? spc - s0 : mult;
+    for (uint32_t j = 1; j < nslots; ++j) dst[j * 256 + t] = 0;
+    if (rbeg >= clen) { dst[t] = 0; return; }
+    const uint64_t sbeg = cbeg + rbeg;
+    const uint64_t rl = clen - rbeg;
+    const uint32_t slen = rl < (uint64_t)mult * HZ_SEG_BYTES ? (uint32_t)rl : mult * HZ_SEG_BYTES;
     {
         const uint4 z = make_uint4(0, 0, 0, 0);
         uint4* h4 = reinterpret_cast<uint4*>(h);
@@ -227,8 +238,11 @@ int hzk_histogram(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_b
         HZ_LAUNCH(ctx, "hist_seg_private", hist_seg_private, (unsigned)grid, HZ_THREADS, smem,
                   d_in, n, chunk_bytes, spc, d_seg_hist);
     } else if (variant == 2) {
-        HZ_LAUNCH(ctx, "hist_seg_lanes", hist_seg_lanes, (unsigned)grid, HZ_THREADS, 0,
-                  d_in, n, chunk_bytes, spc, d_seg_hist);
+        uint32_t mult = hz_range_mult(spc);
+        if (const char* ev = getenv("HZ_HIST_RANGE")) { if (atoi(ev) == 0) mult = 1; }     // developer knob: one segment per CTA
+        const uint32_t rpc = (spc + mult - 1) / mult;
+        HZ_LAUNCH(ctx, "hist_seg_lanes", hist_seg_lanes, (unsigned)((uint64_t)K * rpc), HZ_THREADS, 0,
+                  d_in, n, chunk_bytes, spc, mult, d_seg_hist);
     } else {
         HZ_LAUNCH(ctx, "hist_seg_atomic", hist_seg_atomic, (unsigned)grid, HZ_THREADS, 0,
                   d_in, n, chunk_bytes, spc, d_seg_hist);
