@@ -392,119 +392,132 @@ codebook_warp_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32
 // Thousands of chunks: ONE LANE per chunk for the serial heap replay.  With one active lane per warp the
 // replay (about 10^5 issue slots per chunk) costs as many issue slots as 32 chunks in lock step do, and it
 // bounded the encode stage of 64 KiB chunks (1.7 ms of 2.7 ms per GiB).  Here every lane of a warp replays
-// the JDK heap of its own chunk; the lanes diverge only in the sift depths.  Heap entries are the same
-// uint64 keys as above, stored [slot][lane] (a lane always stays in its own pair of banks: no conflicts
-// whatever the slots); leaves have node id = symbol, internal nodes 256...; the histogram columns
-// ([sym][lane], stride 33) are consumed by the leaf inserts and their memory then holds the parent
-// links, the heap's memory later holds the node depths (filled top-down: a parent's id is larger than
-// its children's).  Output: the code LENGTHS (leaf depths; a single symbol gets 1) in len_out;
+// the JDK heap of its own chunk; the lanes diverge only in the sift depths.  The kernel is latency bound
+// (a dependent chain of shared-memory loads and compares per heap level), so what counts is how many warps
+// an SM holds, i.e. shared memory per chunk - 1.75 KiB:
+//   keys  u32 [256][32]  (freq << 9) | (symbol + 1), internal nodes carry field 0: comparing keys IS
+//                        HuffmanNode.compareTo (two internal nodes of equal frequency compare equal).  Needs
+//                        freq < 2^23, guaranteed by the caller (chunks of at most 32 segments = 1.75 MiB);
+//   ids   u8  [256][32]  index m of the INTERNAL node in a heap slot (a leaf's identity is in its key);
+//   par   u8  [512][32]  parent (always an internal node, m = 0..254; 0xFF = symbol absent) of leaf s at
+//                        [s], of internal node m at [256 + m];
+// all [slot][lane], so a lane stays in its own bank whatever the slots.  The histogram columns are staged
+// through the par+ids area in two halves (coalesced loads); after the merge loop the keys area holds the
+// internal nodes' depths, filled top-down (a parent's index is larger than its children's).
+// Output: the code LENGTHS (leaf depths; a single symbol gets 1) in len_out;
 // codebook_warp_kernel(lens_ready) derives codes, sizes and segment offsets from them.
 // ---------------------------------------------------------------------------------------------
-#define CBL_HS 33
-#define CBL_HEAP_BYTES (256 * 32 * 8)
-#define CBL_SMEM (CBL_HEAP_BYTES + 256 * CBL_HS * 4)
-static_assert(512 * 32 * 2 <= 256 * CBL_HS * 4, "parent links reuse the histogram columns");
-static_assert(2 * (CBL_SMEM + 1024) <= 227 * 1024, "two warps per SM");
+#define CBL_WARPS 4
+#define CBL_KEYS_BYTES (256 * 32 * 4)
+#define CBL_PAR_BYTES (512 * 32)
+#define CBL_IDS_BYTES (256 * 32)
+#define CBL_WARP_BYTES (CBL_KEYS_BYTES + CBL_PAR_BYTES + CBL_IDS_BYTES)     // 56 KiB
+#define CBL_SMEM (CBL_WARPS * CBL_WARP_BYTES)
+#define CBL_HS 33                                                           // staging stride (words) of one symbol's 32 columns
+static_assert(128 * CBL_HS * 4 <= CBL_PAR_BYTES + CBL_IDS_BYTES, "half a histogram is staged in the par+ids area");
+static_assert(CBL_SMEM <= 227 * 1024, "one CTA of CBL_WARPS warps per SM");
 
-__global__ void __launch_bounds__(32)
-codebook_lane_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t K,
-                     const uint32_t* __restrict__ direct_hist, uint8_t* __restrict__ len_out) {
+__global__ void __launch_bounds__(CBL_WARPS * 32)
+codebook_lane_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t K, uint8_t* __restrict__ len_out) {
     extern __shared__ __align__(16) uint8_t cbl_smem[];
-    uint64_t* heap = reinterpret_cast<uint64_t*>(cbl_smem) + threadIdx.x;              // slot i at heap[i * 32]
-    uint32_t* hs = reinterpret_cast<uint32_t*>(cbl_smem + CBL_HEAP_BYTES);               // [sym * CBL_HS + chunk]
-    uint16_t* par = reinterpret_cast<uint16_t*>(cbl_smem + CBL_HEAP_BYTES) + threadIdx.x;   // node i at par[i * 32]
-    uint8_t* dep = cbl_smem + threadIdx.x;                                               // node i at dep[i * 32]
-    const uint32_t lane = threadIdx.x;
-    const uint32_t k0 = blockIdx.x * 32;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t* wsm = cbl_smem + wid * CBL_WARP_BYTES;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(wsm) + lane;                           // slot i at keys[i * 32]
+    uint8_t* par = wsm + CBL_KEYS_BYTES + lane;                                         // node i at par[i * 32]
+    uint8_t* ids = wsm + CBL_KEYS_BYTES + CBL_PAR_BYTES + lane;                         // slot i at ids[i * 32]
+    uint32_t* hs = reinterpret_cast<uint32_t*>(wsm + CBL_KEYS_BYTES);                   // staging [sym * CBL_HS + chunk]
+    uint8_t* dep = wsm + lane;                                                          // internal node m at dep[m * 32]
+    const uint32_t k0 = (blockIdx.x * CBL_WARPS + wid) * 32;
+    if (k0 >= K) return;
 
-    // 1. chunk histograms of the warp's 32 chunks (coalesced: lane = symbol lane + 32 j)
-    for (uint32_t c = 0; c < 32; ++c) {
-        const uint32_t k = k0 + c;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t sym = lane + 32 * j;
-            uint32_t a = 0;
-            if (k < K) {
-                if (direct_hist) a = direct_hist[(size_t)k * 256 + sym];
-                else for (uint32_t s = 0; s < spc; ++s) a += seg_hist[((size_t)k * spc + s) * 256 + sym];
-            }
-            hs[sym * CBL_HS + c] = a;
-        }
-    }
-    __syncwarp();
-
-    // 2. leaves in ascending symbol order (CanonicalHuffman.java:56-62): offer = siftUp
+    // 1 + 2. leaves in ascending symbol order (CanonicalHuffman.java:56-62), offer = siftUp; the chunk histograms of
+    // the warp's 32 chunks come in two halves of 128 symbols (coalesced: lane = symbol lane + 32 j)
     int size = 0, n = 0, only = 0;
-    for (int s = 0; s < 256; ++s) {
-        const uint32_t fr = hs[s * CBL_HS + lane];
-        if (fr > 0) {
-            const uint64_t x = ((uint64_t)fr << 18) | ((uint64_t)(s + 1) << 9) | (uint64_t)s;
-            const uint64_t xs = x | 511ull;
-            int i = size++;
-            while (i > 0) {
-                const int p = (i - 1) >> 1;
-                const uint64_t e = heap[p * 32];
-                if (!(e > xs)) break;
-                heap[i * 32] = e;
-                i = p;
+    for (int half = 0; half < 2; ++half) {
+        for (uint32_t c = 0; c < 32; ++c) {
+            const uint32_t k = k0 + c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t sl = lane + 32 * j;                // symbol within the half
+                uint32_t a = 0;
+                if (k < K) for (uint32_t s = 0; s < spc; ++s) a += seg_hist[((size_t)k * spc + s) * 256 + half * 128 + sl];
+                hs[sl * CBL_HS + c] = a;
             }
-            heap[i * 32] = x;
-            ++n; only = s;
         }
+        __syncwarp();
+        for (int sl = 0; sl < 128; ++sl) {
+            const uint32_t fr = hs[sl * CBL_HS + lane];
+            if (fr > 0) {
+                const int s = half * 128 + sl;
+                const uint32_t x = (fr << 9) | (uint32_t)(s + 1);
+                int i = size++;
+                while (i > 0) {
+                    const int p = (i - 1) >> 1;
+                    const uint32_t e = keys[p * 32];
+                    if (!(e > x)) break;                          // cmp(x, parent) >= 0
+                    keys[i * 32] = e;
+                    i = p;
+                }
+                keys[i * 32] = x;
+                ++n; only = s;
+            }
+        }
+        __syncwarp();                                             // every lane has consumed its staged column
     }
-    __syncwarp();                                   // every lane has consumed its histogram column
-    for (int s = 0; s < 256; ++s) par[s * 32] = 0xFFFFu;      // absent symbols keep this
-    // 3. merge loop (CanonicalHuffman.java:64-70): two polls, one offer
-    int next = 256;
+    for (int s = 0; s < 256; ++s) par[s * 32] = 0xFFu;           // absent symbols keep this
+    // 3. merge loop (CanonicalHuffman.java:64-70): two polls (move last to root + siftDown), one offer (siftUp)
+    int m = 0;                                                    // next internal node
     while (size > 1) {
-        uint64_t lr[2];
+        uint32_t fsum = 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            lr[h] = heap[0];
-            const int m = --size;
-            if (m > 0) {
-                const uint64_t x = heap[m * 32];
+            const uint32_t top = keys[0];
+            const uint32_t topid = ids[0];
+            const int cnt = --size;
+            if (cnt > 0) {
+                const uint32_t x = keys[cnt * 32];
+                const uint32_t xid = ids[cnt * 32];
                 int i = 0;
-                const int half = m >> 1;
-                while (i < half) {
+                const int halfn = cnt >> 1;
+                while (i < halfn) {
                     int child = 2 * i + 1;
-                    uint64_t c = heap[child * 32];
+                    uint32_t c = keys[child * 32];
                     const int right = child + 1;
-                    if (right < m) {
-                        const uint64_t r = heap[right * 32];
-                        if (key_gt(c, r)) { c = r; child = right; }
+                    if (right < cnt) {
+                        const uint32_t r = keys[right * 32];
+                        if (c > r) { c = r; child = right; }      // cmp(left, right) > 0
                     }
-                    if (!key_gt(x, c)) break;
-                    heap[i * 32] = c;
+                    if (!(x > c)) break;                          // cmp(x, child) <= 0
+                    keys[i * 32] = c;
+                    ids[i * 32] = ids[child * 32];
                     i = child;
                 }
-                heap[i * 32] = x;
+                keys[i * 32] = x;
+                ids[i * 32] = (uint8_t)xid;
             }
+            const uint32_t sf = top & 511u;                       // 0: internal node topid, else leaf symbol sf - 1
+            par[(sf ? sf - 1 : 256 + topid) * 32] = (uint8_t)m;
+            fsum += top >> 9;
         }
-        par[(uint32_t)(lr[0] & 511) * 32] = (uint16_t)next;
-        par[(uint32_t)(lr[1] & 511) * 32] = (uint16_t)next;
-        const uint64_t x = (((lr[0] >> 18) + (lr[1] >> 18)) << 18) | (uint64_t)next;
-        const uint64_t xs = x | 511ull;
+        const uint32_t x = fsum << 9;
         int i = size++;
         while (i > 0) {
             const int p = (i - 1) >> 1;
-            const uint64_t e = heap[p * 32];
-            if (!(e > xs)) break;
-            heap[i * 32] = e;
+            const uint32_t e = keys[p * 32];
+            if (!(e > x)) break;
+            keys[i * 32] = e;
+            ids[i * 32] = ids[p * 32];
             i = p;
         }
-        heap[i * 32] = x;
-        ++next;
+        keys[i * 32] = x;
+        ids[i * 32] = (uint8_t)m;
+        ++m;
     }
     __syncwarp();                                   // the heaps are dead: their memory now holds node depths
-    // 4. depths top-down (extractLengths, :85-92), saturated at 255 (anything > 32 is an error downstream)
-    const int root = next - 1;
+    // 4. depths top-down (extractLengths, :85-92); internal node m - 1 is the root
     if (n >= 2) {
-        dep[root * 32] = 0;
-        for (int id = root - 1; id >= 256; --id) {
-            const uint32_t d = dep[(uint32_t)par[id * 32] * 32] + 1u;
-            dep[id * 32] = (uint8_t)(d > 255u ? 255u : d);
-        }
+        dep[(m - 1) * 32] = 0;
+        for (int j = m - 2; j >= 0; --j) dep[j * 32] = (uint8_t)(dep[(uint32_t)par[(256 + j) * 32] * 32] + 1u);
     }
     const uint32_t k = k0 + lane;
     if (k < K) {
@@ -518,7 +531,7 @@ codebook_lane_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32
                 if (n == 1) l = (s == only) ? 1u : 0u;
                 else if (n >= 2) {
                     const uint32_t p = par[s * 32];
-                    if (p != 0xFFFFu) { l = dep[p * 32] + 1u; if (l > 255u) l = 255u; }
+                    if (p != 0xFFu) { l = dep[p * 32] + 1u; if (l > 255u) l = 255u; }     // > 32 is an error downstream
                 }
                 w |= l << (8 * b);
             }
@@ -601,17 +614,18 @@ int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t spc, uint32_t
     // thousands of small chunks: warp per chunk (more serial heaps in flight per SM)
     if (K >= 1024 && spc <= 32) {
         int lens_ready = 0;
-        // lane-per-chunk replay: a warp of 32 chunks takes ~1.7x as long as one chunk on one lane (0.48 vs 0.29 ms),
-        // so it pays once the warp-per-chunk kernel needs more than one wave of ~40 warps per SM
-        bool lanes = !d_fixed_len256 && K >= 8192;
-        if (const char* ev = getenv("HZ_CODEBOOK")) lanes = !d_fixed_len256 && strcmp(ev, "warp") != 0;   // developer knob: warp | lane
+        // lane-per-chunk replay (segment histograms only: its 32-bit heap keys need freq < 2^23, and spc <= 32
+        // bounds a chunk at 1.75 MiB): a warp of 32 chunks takes ~1.5x as long as one chunk on one lane, so it
+        // pays once the warp-per-chunk kernel needs more than one wave of ~40 warps per SM
+        bool lanes = !d_fixed_len256 && spc >= 1 && K >= 8192;
+        if (const char* ev = getenv("HZ_CODEBOOK")) lanes = !d_fixed_len256 && spc >= 1 && strcmp(ev, "warp") != 0;   // developer knob: warp | lane
         if (lanes) {
             if (!ctx->attr_codebook) {
                 HZ_CUDA(ctx, cudaFuncSetAttribute(codebook_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CBL_SMEM));
                 ctx->attr_codebook = true;
             }
-            HZ_LAUNCH(ctx, "codebook_heap", codebook_lane_kernel, (K + 31) / 32, 32, CBL_SMEM,
-                      spc == 0 ? nullptr : d_seg_hist, spc, K, direct, d_len);
+            HZ_LAUNCH(ctx, "codebook_heap", codebook_lane_kernel, (K + CBL_WARPS * 32 - 1) / (CBL_WARPS * 32), CBL_WARPS * 32, CBL_SMEM,
+                      d_seg_hist, spc, K, d_len);
             lens_ready = 1;
         }
         HZ_LAUNCH(ctx, "codebook", codebook_warp_kernel, (K + CBW_WARPS - 1) / CBW_WARPS, CBW_WARPS * 32, 0,

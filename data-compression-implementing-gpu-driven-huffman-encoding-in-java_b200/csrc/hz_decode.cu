@@ -72,7 +72,7 @@
 #define DEC_TAB_S (LUTN * 8)                    // uint16 slut[LUTN]
 #define DEC_TAB_AUX (LUTN * 8 + LUTN * 2)       // DecAux
 #define DEC_TABLE_BYTES (DEC_TAB_AUX + 1024)
-#define DEC_TAB_PREBUILD_CAP (2ull << 30)        // scratch the prebuilt tables of single-CTA chunks may take
+#define DEC_TAB_PREBUILD_CAP (6ull << 30)        // scratch the prebuilt tables of single-CTA chunks may take (41 KiB per chunk)
 
 struct __align__(16) DecAux {
     uint64_t lim[34];          // exclusive upper bound of the left-justified (32-bit) codes of each length

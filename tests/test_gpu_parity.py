@@ -423,7 +423,8 @@ def test_sharded_two_ranks_one_gpu_equals_reference(hz, codec):
 
 
 # ---- host-buffer pipeline (batches of chunks over three streams) --------------------------------
-@pytest.mark.parametrize("n,chunk,H", [(160 * MiB + 12345, 4 * MiB, 4), (200 * MiB, 16 * MiB, 6), (130 * MiB + 1, 64 * 1024, 2)])
+@pytest.mark.parametrize("n,chunk,H", [(160 * MiB + 12345, 4 * MiB, 4), (200 * MiB, 16 * MiB, 6), (130 * MiB + 1, 64 * 1024, 2),
+                                       (140 * MiB + 3, 1 * MiB, 8)])
 def test_pipelined_host_buffers_match_device_path(codec, n, chunk, H):
     """hz_encode / hz_decode with HOST buffers >= 128 MiB take the pipelined path; the result must be
     byte-identical to the device-resident single-shot path, and chunks must match the oracle."""
@@ -469,39 +470,55 @@ def test_many_small_chunks_warp_codebook(codec):
     _check_codebooks(codec, hist)
 
 
-def test_lane_codebook_ties_and_long_codes(codec, hz):
-    """K >= 8192 histograms take the lane-per-chunk heap replay (codebook_lane_kernel): tie-heavy, sparse,
-    one-symbol, empty and long-code histograms, mixed inside the same warps, must give the oracle's lengths."""
+def _chunk_with_counts(rng, counts, size):
+    """`size` bytes whose histogram is `counts` (256 ints, sum <= size; symbol 0 absorbs the remainder), shuffled."""
+    counts = np.asarray(counts, dtype=np.int64).copy()
+    assert counts.sum() <= size
+    counts[0] += size - counts.sum()
+    b = np.repeat(np.arange(256, dtype=np.uint8), counts)
+    rng.shuffle(b)
+    return b
+
+
+def test_lane_codebook_ties_and_long_codes(codec, monkeypatch):
+    """Streams of thousands of chunks take the lane-per-chunk heap replay (codebook_lane_kernel, 32-bit keys):
+    tie-heavy, sparse, one-symbol and long-code chunk histograms, mixed inside the same warps, must give the
+    oracle's code lengths, offsets and payload (HZ_CODEBOOK=lane forces the kernel from K >= 1024)."""
+    monkeypatch.setenv("HZ_CODEBOOK", "lane")
     rng = np.random.default_rng(11)
-    hs = np.zeros((8300, 256), dtype=np.uint32)
-    for k in range(8300):
-        kind = k % 8
+    chunk, K = 2048, 1300
+    parts = []
+    for k in range(K):
+        kind = k % 7
+        c = np.zeros(256, dtype=np.int64)
         if kind == 0:
-            hs[k] = rng.choice([1, 2, 3], 256)
+            c[:] = rng.choice([1, 2, 3], 256)
         elif kind == 1:
-            m = int(rng.integers(1, 257)); hs[k, rng.choice(256, m, replace=False)] = 1
+            m = int(rng.integers(1, 257)); c[rng.choice(256, m, replace=False)] = 1
         elif kind == 2:
-            hs[k] = 2 ** rng.integers(0, 12, 256)
+            c[rng.choice(256, 40, replace=False)] = 2 ** rng.integers(0, 6, 40)
         elif kind == 3:
-            hs[k, int(rng.integers(0, 256))] = int(rng.integers(1, 70000))       # one symbol
+            c[int(rng.integers(0, 256))] = chunk                                  # one symbol (symbol 0 adds nothing)
         elif kind == 4:
-            pass                                                                   # empty chunk
+            c[:] = 8                                                              # all equal: every length 8
         elif kind == 5:
-            hs[k] = datasets.fib_like_hist(int(rng.integers(2, 34))).astype(np.uint32)   # max length up to 32
-        elif kind == 6:
-            hs[k] = rng.integers(0, 4, 256)
+            c[:14] = datasets.fib_like_hist(14)[:14]                              # long codes (max length ~13)
         else:
-            hs[k] = rng.integers(1, 1 << 16, 256)
-    _check_codebooks(codec, hs)
-    hs[777] = datasets.fib_like_hist(34).astype(np.uint32)                         # depth 33: reference throws
-    with pytest.raises(hz.HzError) as e:
-        codec.build_codebooks(hs)
-    assert e.value.status == hz.HZ_ERR_CODE_TOO_LONG
-    # the whole encode stage with K >= 8192 chunks (segment histograms feed the lane kernel), ragged last chunk
-    n, chunk = 8200 * 512 + 99, 512
-    data = datasets.zipf_stream(n, 5, seed=3).copy()
-    data[9 * chunk:10 * chunk] = 0x5A                                              # a one-symbol chunk
-    check_encode(codec, data, chunk)
+            c[:] = rng.integers(0, 8, 256)
+        parts.append(_chunk_with_counts(rng, c, chunk))
+    parts.append(_chunk_with_counts(rng, np.ones(256), 300))                      # ragged last chunk
+    check_encode(codec, np.concatenate(parts), chunk)
+    # longer codes need bigger chunks: Fibonacci counts up to 24 symbols (max length 23..24), K >= 1024
+    chunk, K = 160 * 1024, 1030
+    parts = []
+    for k in range(K):
+        c = np.zeros(256, dtype=np.int64)
+        nsym = 10 + k % 15
+        c[rng.choice(np.arange(1, 256), nsym, replace=False)] = datasets.fib_like_hist(nsym)[:nsym]
+        parts.append(_chunk_with_counts(rng, c, chunk))
+    data = np.concatenate(parts)
+    payload, off, lens = check_encode(codec, data, chunk)
+    assert lens.max() >= 20
 
 
 def test_two_contexts_one_process(hz):
