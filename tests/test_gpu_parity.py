@@ -521,6 +521,17 @@ def test_lane_codebook_ties_and_long_codes(codec, monkeypatch):
     assert lens.max() >= 20
 
 
+@pytest.mark.parametrize("prebuild", ["0", "1"])
+def test_decode_tables_built_in_place_or_prebuilt(codec, monkeypatch, prebuild):
+    """Single-CTA chunks either get their lookup tables from dec_tables_kernel (default while K tables fit the scratch
+    cap) or build them inside the sync / write CTAs (HZ_DEC_PREBUILD=0, the path streams of > 150 k chunks take): both
+    must decode the same bytes, for small chunks, multi-CTA chunks and a mix of identity and ordinary chunks."""
+    monkeypatch.setenv("HZ_DEC_PREBUILD", prebuild)
+    for n, chunk, H in [(3 * MiB + 17, 64 * 1024, 3), (9 * MiB, 4 * MiB, 5), (2 * MiB + 5, 256 * 1024, 8), (700_001, 4096, 1)]:
+        data = datasets.zipf_stream(n, H, seed=H + 40)
+        check_encode(codec, data, chunk)
+
+
 def test_two_contexts_one_process(hz):
     """Kernel attributes (opt-in shared memory) are set per context, not once per process."""
     data = datasets.zipf_stream(700_000, 4, seed=5)
