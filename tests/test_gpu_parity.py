@@ -212,6 +212,32 @@ def test_decode_oracle_streams_and_errors(codec, hz):
     assert e.value.status == hz.HZ_ERR_BAD_LENGTHS
 
 
+@pytest.mark.parametrize("H,chunk", [(5, 1 * MiB), (2, 300_000), (7, 70_000)])
+def test_decode_damaged_streams_match_the_oracle(codec, H, chunk):
+    """A complete prefix code decodes ANY bit string, so a damaged stream has a well-defined reference result:
+    flipped bits (the self-synchronisation guesses fail and are repaired inside CTAs and across CTA boundaries),
+    a truncated payload (zero bits past the end) and a short orig_size must give the oracle's bytes."""
+    rng = np.random.default_rng(H * 1000 + 7)
+    data = datasets.zipf_stream(3 * chunk, H, seed=H + 60)
+    payload, off, lens = codec.encode(data, chunk)[:3]
+    sizes = np.diff(off).astype(np.uint32)
+    for k in range(3):
+        comp = payload[int(off[k]):int(off[k + 1])].copy()
+        ln = lens[k].astype(np.int32)
+        for trial in range(3):
+            bad = comp.copy()
+            flips = rng.integers(0, bad.size * 8, 25)
+            for f in flips:
+                bad[f >> 3] ^= 0x80 >> (f & 7)
+            cut = int(rng.integers(0, 4))                      # drop up to 3 bytes at the end
+            bad = bad[:bad.size - cut]
+            n_out = chunk - int(rng.integers(0, 3)) * 1000      # sometimes fewer symbols than the stream holds
+            ref, rc = orc.decode(bad, ln, n_out, literal=False)
+            assert rc == 0
+            out = codec.decode(bad, [0], [bad.size], [n_out], lens[k:k + 1])
+            assert np.array_equal(out, ref), "chunk %d trial %d" % (k, trial)
+
+
 def test_decode_reads_zero_bits_past_the_end(codec):
     # TableBasedHuffmanDecoder.java:204-208: bits past the end of the chunk are 0
     ln = np.zeros((1, 256), dtype=np.uint8); ln[0, 7] = 1; ln[0, 9] = 1      # 7 -> '0', 9 -> '1'
