@@ -3,9 +3,10 @@
 // Replaces CanonicalHuffman.buildCanonicalCodes(long[256]) (core/CanonicalHuffman.java:19-132).
 // The code LENGTHS of the reference depend on how java.util.PriorityQueue orders
 // equal-frequency internal nodes (HuffmanNode.compareTo, core/HuffmanNode.java:52-58, returns 0
-// for two internal nodes of equal frequency), so the tree is built by ONE thread that replays the
-// JDK's binary heap literally: offer = siftUp (stop when cmp(x,parent) >= 0), poll = move last
-// to root + siftDown (pick right child only if cmp(left,right) > 0; stop when cmp(x,child) <= 0).
+// for two internal nodes of equal frequency), so the tree is built by replaying the JDK's binary heap
+// operation by operation: offer = siftUp (stop when cmp(x,parent) >= 0), poll = move last to root +
+// siftDown (pick right child only if cmp(left,right) > 0; stop when cmp(x,child) <= 0) - by one warp per
+// chunk (warp_heap_replay) or, for thousands of small chunks, one lane per chunk (codebook_lane_kernel).
 // A heap entry is one uint64: (freq << 18) | ((symbol+1) << 9) | node_id — comparing
 // (entry >> 9) is exactly compareTo (internal nodes carry symbol -1 -> field 0).
 // Everything around the serial heap (summing segment histograms, leaf depths by parent chasing,
@@ -58,6 +59,98 @@ __device__ __forceinline__ uint64_t heap_poll(uint64_t* q, int& size) {
     return result;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same heap replayed by a WARP (HZ_CB_PLAIN keeps the one-thread loops above for A/B runs).
+// A literal siftDown is 7 dependent rounds of load -> compare -> select -> compare -> store.  But the
+// children it visits - the heap's min-child path - do not depend on the element x being sifted:
+//   1. every lane compares the two children of 4 inner slots (one 128-bit load each); four ballots give all
+//      lanes the 127 "right child is the smaller one" bits (cmp(left, right) > 0, as PriorityQueue.siftDown);
+//   2. the path follows from the bits alone (register arithmetic, no memory access);
+//   3. lane L loads the path entry of level L + 1 and compares it with x; a ballot gives the number t of
+//      levels x sinks, lanes < t move their entry up one level, lane t stores x.
+// siftUp is one round as well: lane i loads ancestor i + 1 of the new slot, a ballot counts how far x rises.
+// Slots are 1-based (children 2s, 2s + 1) on q1 = heap - 1, 16-byte aligned so that a child pair is one load.
+// The heap array is identical to the literal loops' after every operation, so the tie-breaks of equal-frequency
+// internal nodes - which decide the reference's code lengths - are preserved.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_heap_offer(uint64_t* q1, int& size, uint64_t x, uint32_t lane) {
+    const uint32_t s = (uint32_t)++size;                        // the new slot
+    const uint32_t anc = lane < 8 ? s >> (lane + 1) : 0u;       // lane i: ancestor i + 1 (s <= 256: at most 8)
+    const uint64_t e = anc ? q1[anc] : 0ull;
+    const bool up = anc && e > (x | 511ull);                    // cmp(x, ancestor) < 0: the ancestor moves down
+    // siftUp stops at the first ancestor that stays; ancestors descend towards the root, so those that move are a prefix
+    const uint32_t t = __popc(__ballot_sync(0xffffffffu, up));
+    if (lane < t) q1[s >> lane] = e;
+    if (lane == t) q1[s >> t] = x;
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint64_t warp_heap_poll(uint64_t* q1, int& size, uint32_t lane) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint64_t result = q1[1];
+    const uint32_t n = (uint32_t)--size;
+    if (n == 0) return result;
+    const uint64_t x = q1[n + 1];
+    uint32_t p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t sl = lane + 32 * i;                      // inner slot (slot 0 does not exist: q1[0], q1[1] are readable, bit unused)
+        const ulonglong2 ch = *reinterpret_cast<const ulonglong2*>(q1 + 2 * sl);
+        p[i] = __ballot_sync(FULL, 2 * sl + 1 <= n && key_gt(ch.x, ch.y));
+    }
+    const uint32_t half = n >> 1;                               // slots 1..half have a left child
+    uint32_t s = 1;
+#pragma unroll
+    for (int L = 0; L < 7; ++L) {
+        const uint32_t w = L < 5 ? p[0] : L == 5 ? p[1] : ((s & 32u) ? p[3] : p[2]);
+        s = 2 * s + (__funnelshift_r(w, 0u, s) & 1u);           // shift amount taken mod 32
+    }
+    // s = 1 b0 b1 .. b6 in binary: the path slot of level L is its top L + 1 bits
+    const uint32_t my_s = s >> (7 - min(lane, 7u));
+    const uint32_t my_sn = s >> (6 - min(lane, 6u));
+    const uint64_t c = q1[my_sn];                               // my_sn <= 255: inside the array
+    const bool sink = lane < 7 && my_s <= half && key_gt(x, c); // cmp(x, child) > 0
+    // siftDown stops at the first level that holds; the entries along the path ascend, so the lanes that sink are
+    // a prefix and their count is that level
+    const uint32_t t = __popc(__ballot_sync(FULL, sink));
+    if (lane < t) q1[my_s] = c;
+    if (lane == t) q1[my_s] = x;
+    __syncwarp();
+    return result;
+}
+
+// buildCodeLengths up to the tree, by all 32 lanes of a warp: leaves offered in ascending symbol order, then
+// poll / poll / offer until one node is left.  Leaf s gets node id leaf_id[s] = its rank among the present symbols,
+// internal nodes continue the numbering; parent[id] is the tree.  heapbuf: 258 words, 16-byte aligned.
+__device__ __forceinline__ int warp_heap_replay(const uint32_t* hist, uint64_t* heapbuf, uint16_t* parent, uint16_t* leaf_id,
+                                                int* root, uint32_t lane) {
+    uint64_t* q1 = heapbuf;                                     // 1-based slots: q1[1..256]
+    if (lane < 2) q1[lane] = 0;
+    int size = 0, n = 0;
+    for (int s = 0; s < 256; ++s) {
+        const uint32_t fr = hist[s];
+        if (fr > 0) {
+            if (lane == 0) leaf_id[s] = (uint16_t)n;
+            warp_heap_offer(q1, size, ((uint64_t)fr << 18) | ((uint64_t)(s + 1) << 9) | (uint64_t)n, lane);
+            ++n;
+        }
+    }
+    const int nsym = n;
+    while (size > 1) {
+        const uint64_t l = warp_heap_poll(q1, size, lane);
+        const uint64_t r = warp_heap_poll(q1, size, lane);
+        if (lane == 0) {
+            parent[l & 511] = (uint16_t)n;
+            parent[r & 511] = (uint16_t)n;
+        }
+        warp_heap_offer(q1, size, (((l >> 18) + (r >> 18)) << 18) | (uint64_t)n, lane);
+        ++n;
+    }
+    *root = n - 1;
+    __syncwarp();
+    return nsym;
+}
+
 // Block-wide exclusive scan helper for 64-bit values over `count` items stored in global memory
 // (in place: in = per-item value, out = exclusive prefix).  Called by all CB_THREADS threads.
 __device__ void block_scan_inplace_u64(uint64_t* data, uint32_t count, uint64_t* s_warp /*[9]*/) {
@@ -93,7 +186,7 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
                 uint64_t* __restrict__ seg_bitoff, const uint8_t* __restrict__ fixed_len,
                 const uint32_t* __restrict__ direct_hist, int* status) {
     __shared__ uint32_t hist[256];
-    __shared__ uint64_t heap[256];
+    __shared__ __align__(16) uint64_t heap[258];
     __shared__ uint16_t parent[512];
     __shared__ uint16_t leaf_id[256];
     __shared__ int s_len[256];
@@ -109,8 +202,17 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
     if (direct_hist) {
         f = direct_hist[(size_t)k * 256 + t];
     } else {
+        // a 16 MiB chunk has 300 segment histograms: 16 independent loads in flight per thread
         const uint32_t* sh = seg_hist + (size_t)k * spc * 256 + t;
-        for (uint32_t s = 0; s < spc; ++s) f += sh[(size_t)s * 256];
+        uint32_t s = 0;
+        for (; s + 16 <= spc; s += 16) {
+            uint32_t v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __ldg(sh + (size_t)(s + j) * 256);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f += v[j];
+        }
+        for (; s < spc; ++s) f += __ldg(sh + (size_t)s * 256);
     }
     hist[t] = f;
     if (chunk_hist_out) chunk_hist_out[(size_t)k * 256 + t] = f;
@@ -124,6 +226,13 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
         if (f > 0 && mylen == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS);
     } else {
         // 2. the serial part: replay java.util.PriorityQueue (CanonicalHuffman.java:55-70)
+#ifndef HZ_CB_PLAIN
+        if (t < 32) {                           // warp 0, all lanes (warp_heap_replay)
+            int root;
+            const int nsym = warp_heap_replay(hist, heap, parent, leaf_id, &root, lane);
+            if (t == 0) { s_nsym = nsym; s_root = root; }
+        }
+#else
         if (t == 0) {
             int size = 0, n = 0;
             for (int s = 0; s < 256; ++s) {
@@ -145,6 +254,7 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
             }
             s_root = n - 1;
         }
+#endif
         __syncthreads();
         // 3. leaf depth = code length (extractLengths, :85-92); single symbol -> 1 (:35-45)
         if (f > 0) {
@@ -208,17 +318,33 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
     // 6. bit offset of every segment inside the chunk's stream
     if (seg_bitoff && seg_hist) {
         uint64_t* so = seg_bitoff + (size_t)k * spc;
-        for (uint32_t s = wid; s < spc; s += CB_THREADS / 32) {
-            const uint32_t* sh = seg_hist + ((size_t)k * spc + s) * 256;
-            uint64_t b = 0;
+        uint32_t l8[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int sym = lane + 32 * j;
-                b += (uint64_t)sh[sym] * (uint32_t)(bad ? 0 : s_len[sym]);
+        for (int j = 0; j < 8; ++j) l8[j] = bad ? 0u : (uint32_t)s_len[lane + 32 * j];
+        // four segments per warp and iteration: 32 independent loads in flight per lane, the four reductions interleaved
+        for (uint32_t s0 = wid * 4; s0 < spc; s0 += CB_THREADS / 32 * 4) {
+            uint32_t v[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t* sh = seg_hist + ((size_t)k * spc + min(s0 + q, spc - 1)) * 256 + lane;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[q][j] = __ldg(sh + 32 * j);
+            }
+            uint64_t b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                b[q] = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[q] += (uint64_t)v[q][j] * l8[j];
             }
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) b += __shfl_xor_sync(0xffffffffu, b, d);
-            if (lane == 0) so[s] = b;
+            for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) b[q] += __shfl_xor_sync(0xffffffffu, b[q], d);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (lane == (uint32_t)q && s0 + q < spc) so[s0 + q] = b[q];
         }
         __syncthreads();
         block_scan_inplace_u64(so, spc, s_warp);
@@ -232,8 +358,8 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
 // Same results as codebook_kernel; used when spc <= 32 (the segment offsets are scanned by one warp).
 // ---------------------------------------------------------------------------------------------
 #define CBW_WARPS 8
-struct CbWarp {
-    uint64_t heap[256];
+struct __align__(16) CbWarp {
+    uint64_t heap[258];                 // 1-based slots for warp_heap_replay; sizeof(CbWarp) is a multiple of 16
     uint32_t hist[256];
     uint16_t parent[512];
     uint16_t leaf_id[256];
@@ -279,13 +405,18 @@ codebook_warp_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32
             mylen[j] = fixed_len[lane + 32 * j];
             if (f[j] > 0 && mylen[j] == 0) hz_set_status(status, HZ_ERR_BAD_LENGTHS);
         }
-    } else if (lens_ready) {
+    } else if (lens_ready == 1) {
         // the heap replay was done by codebook_lane_kernel (32 chunks per warp): leaf depths are in len_out
 #pragma unroll
         for (int j = 0; j < 8; ++j) mylen[j] = len_out[(size_t)k * 256 + lane + 32 * j];
     } else {
         // 2. the serial part: replay java.util.PriorityQueue (CanonicalHuffman.java:55-70)
         int nsym = 0, root = 0;
+#ifndef HZ_CB_PLAIN
+        if (lens_ready == 0) {
+            nsym = warp_heap_replay(W.hist, W.heap, W.parent, W.leaf_id, &root, lane);
+        } else                                  // lens_ready == 2: the one-lane loops (a full GPU of warps is issue bound)
+#endif
         if (lane == 0) {
             int size = 0, n = 0;
             for (int s = 0; s < 256; ++s) {
@@ -627,6 +758,14 @@ int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t spc, uint32_t
             HZ_LAUNCH(ctx, "codebook_heap", codebook_lane_kernel, (K + CBL_WARPS * 32 - 1) / (CBL_WARPS * 32), CBL_WARPS * 32, CBL_SMEM,
                       d_seg_hist, spc, K, d_len);
             lens_ready = 1;
+        }
+        // replay inside the warp kernel: by all 32 lanes (warp_heap_replay: a third less latency per chunk) while the
+        // warps do not fill the GPU (1 MiB chunks, K = 1,024 per GiB: 0.29 -> 0.23 ms), by one lane beyond (mode 2:
+        // with ~40 warps per SM the replay is issue bound and the one-lane loops issue less; K = 4,096: 0.56 vs 0.59 ms)
+        if (!lens_ready) {
+            bool coop = K <= 2048;
+            if (const char* ev = getenv("HZ_CODEBOOK_REPLAY")) coop = strcmp(ev, "lane0") != 0;     // developer knob: warp | lane0
+            if (!coop) lens_ready = 2;
         }
         HZ_LAUNCH(ctx, "codebook", codebook_warp_kernel, (K + CBW_WARPS - 1) / CBW_WARPS, CBW_WARPS * 32, 0,
                   spc == 0 ? nullptr : d_seg_hist, spc, K, d_chunk_hist, d_len, d_code, d_chunk_bits,
