@@ -415,7 +415,7 @@ codebook_warp_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32
 #ifndef HZ_CB_PLAIN
         if (lens_ready == 0) {
             nsym = warp_heap_replay(W.hist, W.heap, W.parent, W.leaf_id, &root, lane);
-        } else                                  // lens_ready == 2: the one-lane loops (a full GPU of warps is issue bound)
+        } else                                  // lens_ready == 2: the one-lane loops (developer knob HZ_CODEBOOK_REPLAY=lane0)
 #endif
         if (lane == 0) {
             int size = 0, n = 0;
@@ -759,11 +759,11 @@ int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t spc, uint32_t
                       d_seg_hist, spc, K, d_len);
             lens_ready = 1;
         }
-        // replay inside the warp kernel: by all 32 lanes (warp_heap_replay: a third less latency per chunk) while the
-        // warps do not fill the GPU (1 MiB chunks, K = 1,024 per GiB: 0.29 -> 0.23 ms), by one lane beyond (mode 2:
-        // with ~40 warps per SM the replay is issue bound and the one-lane loops issue less; K = 4,096: 0.56 vs 0.59 ms)
+        // replay inside the warp kernel: by all 32 lanes (warp_heap_replay) - less latency per chunk while the warps do
+        // not fill the GPU (1 MiB chunks, K = 1,024 per GiB: 0.29 -> 0.195 ms) and fewer issue slots when they do
+        // (256 KiB chunks, K = 4,096: 0.557 -> 0.470 ms); mode 2 keeps the one-lane loops for A/B runs
         if (!lens_ready) {
-            bool coop = K <= 2048;
+            bool coop = true;
             if (const char* ev = getenv("HZ_CODEBOOK_REPLAY")) coop = strcmp(ev, "lane0") != 0;     // developer knob: warp | lane0
             if (!coop) lens_ready = 2;
         }
