@@ -91,14 +91,15 @@ __device__ __forceinline__ uint64_t warp_heap_poll(uint64_t* q1, int& size, uint
     const uint32_t n = (uint32_t)--size;
     if (n == 0) return result;
     const uint64_t x = q1[n + 1];
+    // Slots beyond the heap hold the largest key, so a missing child is never the smaller one and never smaller than
+    // x: no bounds checks.  Slot n + 1 still holds x during this poll - harmless: as a right child it is preferred
+    // only if the left one is larger than x (then x stays above both anyway), and x never sinks below itself.
     uint32_t p[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const uint32_t sl = lane + 32 * i;                      // inner slot (slot 0 does not exist: q1[0], q1[1] are readable, bit unused)
-        const ulonglong2 ch = *reinterpret_cast<const ulonglong2*>(q1 + 2 * sl);
-        p[i] = __ballot_sync(FULL, 2 * sl + 1 <= n && key_gt(ch.x, ch.y));
+        const ulonglong2 ch = *reinterpret_cast<const ulonglong2*>(q1 + 2 * (lane + 32 * i));   // children of slot lane + 32 i
+        p[i] = __ballot_sync(FULL, key_gt(ch.x, ch.y));                                         // (slot 0: unused bit)
     }
-    const uint32_t half = n >> 1;                               // slots 1..half have a left child
     uint32_t s = 1;
 #pragma unroll
     for (int L = 0; L < 7; ++L) {
@@ -107,14 +108,14 @@ __device__ __forceinline__ uint64_t warp_heap_poll(uint64_t* q1, int& size, uint
     }
     // s = 1 b0 b1 .. b6 in binary: the path slot of level L is its top L + 1 bits
     const uint32_t my_s = s >> (7 - min(lane, 7u));
-    const uint32_t my_sn = s >> (6 - min(lane, 6u));
-    const uint64_t c = q1[my_sn];                               // my_sn <= 255: inside the array
-    const bool sink = lane < 7 && my_s <= half && key_gt(x, c); // cmp(x, child) > 0
-    // siftDown stops at the first level that holds; the entries along the path ascend, so the lanes that sink are
-    // a prefix and their count is that level
-    const uint32_t t = __popc(__ballot_sync(FULL, sink));
+    const uint32_t my_sn = lane < 7 ? s >> (6 - lane) : 257u;   // q1[257] is always the largest key
+    const uint64_t c = q1[my_sn];
+    // siftDown stops at the first level with cmp(x, child) <= 0; the entries along the path ascend, so the lanes that
+    // sink are a prefix and their count is that level
+    const uint32_t t = __popc(__ballot_sync(FULL, key_gt(x, c)));
     if (lane < t) q1[my_s] = c;
     if (lane == t) q1[my_s] = x;
+    if (lane == 31) q1[n + 1] = ~0ull;                          // the vacated slot (all lanes have x: it fed the ballot)
     __syncwarp();
     return result;
 }
@@ -124,8 +125,9 @@ __device__ __forceinline__ uint64_t warp_heap_poll(uint64_t* q1, int& size, uint
 // internal nodes continue the numbering; parent[id] is the tree.  heapbuf: 258 words, 16-byte aligned.
 __device__ __forceinline__ int warp_heap_replay(const uint32_t* hist, uint64_t* heapbuf, uint16_t* parent, uint16_t* leaf_id,
                                                 int* root, uint32_t lane) {
-    uint64_t* q1 = heapbuf;                                     // 1-based slots: q1[1..256]
-    if (lane < 2) q1[lane] = 0;
+    uint64_t* q1 = heapbuf;                                     // 1-based slots: q1[1..256]; q1[0], q1[257] never hold entries
+    for (uint32_t i = lane; i < 258; i += 32) q1[i] = ~0ull;    // the largest key beyond the heap (see warp_heap_poll)
+    __syncwarp();
     int size = 0, n = 0;
     for (int s = 0; s < 256; ++s) {
         const uint32_t fr = hist[s];

@@ -496,6 +496,38 @@ def test_many_small_chunks_warp_codebook(codec):
     _check_codebooks(codec, hist)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("replay", ["warp", "lane0"])
+def test_warp_replay_heavy_ties_many_chunks(codec, monkeypatch, replay):
+    """The heap replay of the codebook kernels (warp_heap_replay: child-preference bits by ballot, path in registers)
+    against the oracle's literal PriorityQueue where the tie-breaks decide the lengths: histograms drawn from tiny value
+    ranges, sparse alphabets, powers of two, and counts near 2^31 (64-bit heap keys).  1,300 rows take the
+    warp-per-chunk kernel (K >= 1024), the first 300 alone the CTA-per-chunk kernel; HZ_CODEBOOK_REPLAY=lane0 runs
+    the one-lane literal loops on the same rows."""
+    monkeypatch.setenv("HZ_CODEBOOK_REPLAY", replay)
+    rng = np.random.default_rng(20261019)
+    hs = []
+    for hi in (1, 2, 3, 4, 8, 16, 100):
+        for _ in range(80):
+            hs.append(rng.integers(0, hi + 1, 256))
+            hs.append(rng.integers(1, hi + 1, 256))
+    for _ in range(100):
+        m = int(rng.integers(2, 257))
+        h = np.zeros(256, dtype=np.int64)
+        h[rng.choice(256, m, replace=False)] = 1 << rng.integers(0, 6, m)
+        hs.append(h)
+    for _ in range(60):
+        h = rng.integers(0, 3, 256).astype(np.int64)
+        h[rng.choice(256, 4, replace=False)] = (1 << 31) // 4 - 200 + rng.integers(0, 3, 4)   # sum stays below 2^31
+        hs.append(h)
+    while len(hs) < 1300:
+        hs.append(rng.permutation(hs[int(rng.integers(0, len(hs)))]))
+    hs = np.array(hs, dtype=np.uint32)
+    assert (hs.astype(np.int64).sum(axis=1) < (1 << 31)).all()
+    _check_codebooks(codec, hs)
+    _check_codebooks(codec, hs[:300])
+
+
 def _chunk_with_counts(rng, counts, size):
     """`size` bytes whose histogram is `counts` (256 ints, sum <= size; symbol 0 absorbs the remainder), shuffled."""
     counts = np.asarray(counts, dtype=np.int64).copy()
