@@ -75,13 +75,14 @@ __device__ __forceinline__ uint64_t heap_poll(uint64_t* q, int& size) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_heap_offer(uint64_t* q1, int& size, uint64_t x, uint32_t lane) {
     const uint32_t s = (uint32_t)++size;                        // the new slot
-    const uint32_t anc = lane < 8 ? s >> (lane + 1) : 0u;       // lane i: ancestor i + 1 (s <= 256: at most 8)
-    const uint64_t e = anc ? q1[anc] : 0ull;
-    const bool up = anc && e > (x | 511ull);                    // cmp(x, ancestor) < 0: the ancestor moves down
-    // siftUp stops at the first ancestor that stays; ancestors descend towards the root, so those that move are a prefix
-    const uint32_t t = __popc(__ballot_sync(0xffffffffu, up));
-    if (lane < t) q1[s >> lane] = e;
-    if (lane == t) q1[s >> t] = x;
+    // lane i: ancestor i + 1 (s <= 256: at most 8); the clamping funnel shift gives 0 from lane 8 on and
+    // q1[0] holds the smallest key, which never moves down
+    const uint32_t anc = __funnelshift_rc(s, 0u, lane + 1);
+    const uint64_t e = q1[anc];
+    // cmp(x, ancestor) < 0: the ancestor moves down.  siftUp stops at the first ancestor that stays; ancestors
+    // descend towards the root, so those that move are a prefix
+    const uint32_t t = __popc(__ballot_sync(0xffffffffu, e > (x | 511ull)));
+    if (lane <= t) q1[s >> lane] = lane < t ? e : x;
     __syncwarp();
 }
 
@@ -113,8 +114,7 @@ __device__ __forceinline__ uint64_t warp_heap_poll(uint64_t* q1, int& size, uint
     // siftDown stops at the first level with cmp(x, child) <= 0; the entries along the path ascend, so the lanes that
     // sink are a prefix and their count is that level
     const uint32_t t = __popc(__ballot_sync(FULL, key_gt(x, c)));
-    if (lane < t) q1[my_s] = c;
-    if (lane == t) q1[my_s] = x;
+    if (lane <= t) q1[my_s] = lane < t ? c : x;
     if (lane == 31) q1[n + 1] = ~0ull;                          // the vacated slot (all lanes have x: it fed the ballot)
     __syncwarp();
     return result;
@@ -126,7 +126,7 @@ __device__ __forceinline__ uint64_t warp_heap_poll(uint64_t* q1, int& size, uint
 __device__ __forceinline__ int warp_heap_replay(const uint32_t* hist, uint64_t* heapbuf, uint16_t* parent, uint16_t* leaf_id,
                                                 int* root, uint32_t lane) {
     uint64_t* q1 = heapbuf;                                     // 1-based slots: q1[1..256]; q1[0], q1[257] never hold entries
-    for (uint32_t i = lane; i < 258; i += 32) q1[i] = ~0ull;    // the largest key beyond the heap (see warp_heap_poll)
+    for (uint32_t i = lane; i < 258; i += 32) q1[i] = i ? ~0ull : 0ull;     // the largest key beyond the heap (warp_heap_poll), the smallest in q1[0] (warp_heap_offer)
     __syncwarp();
     int size = 0, n = 0;
     for (int s = 0; s < 256; ++s) {
@@ -141,10 +141,7 @@ __device__ __forceinline__ int warp_heap_replay(const uint32_t* hist, uint64_t* 
     while (size > 1) {
         const uint64_t l = warp_heap_poll(q1, size, lane);
         const uint64_t r = warp_heap_poll(q1, size, lane);
-        if (lane == 0) {
-            parent[l & 511] = (uint16_t)n;
-            parent[r & 511] = (uint16_t)n;
-        }
+        if (lane < 2) parent[(lane ? r : l) & 511] = (uint16_t)n;
         warp_heap_offer(q1, size, (((l >> 18) + (r >> 18)) << 18) | (uint64_t)n, lane);
         ++n;
     }
