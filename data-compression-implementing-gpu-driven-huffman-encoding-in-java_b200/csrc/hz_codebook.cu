@@ -351,9 +351,9 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// Many small chunks: ONE WARP per chunk (8 chunks per CTA).  The serial heap replay still runs on
-// one lane, but an SM now keeps ~40 of them in flight instead of 8, which is what bounds the
-// codebook stage when a stream is cut into thousands of chunks (64 KiB chunks: 16 k per GiB).
+// Many small chunks: ONE WARP per chunk (8 chunks per CTA), each replaying its chunk's heap with
+// warp_heap_replay: an SM keeps ~40 heaps in flight instead of the 8 of one CTA per chunk, which is what
+// bounds the codebook stage when a stream is cut into thousands of chunks (256 KiB chunks: 4 k per GiB).
 // Same results as codebook_kernel; used when spc <= 32 (the segment offsets are scanned by one warp).
 // ---------------------------------------------------------------------------------------------
 #define CBW_WARPS 8
