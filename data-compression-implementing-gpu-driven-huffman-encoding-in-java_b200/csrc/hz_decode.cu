@@ -485,6 +485,19 @@ struct SyncSmem {
     "HZL_END" SFX ":\n"
 static_assert(offsetof(DecAux, lim) == 0, "HZ_PTX_LONGLEN reads lim[] at the start of DecAux");
 
+// Right shifts inside the hand-written loops.  -DHZ_DEC_FMA_SHIFTS (A/B variant for the next GPU session, never the
+// default) takes them as hi32(x * 2^(32 - s)) on the FMA pipe: both loops are bound
+// by the half-rate integer ALU pipe (sync 73 %, write 63 % busy) while the FMA pipe idles.
+#if defined(HZ_DEC_FMA_SHIFTS)
+#define HZ_SHR20(D, S) "mul.hi.u32 " D ", " S ", 4096;\n"
+#define HZ_SHR16(D, S) "mul.hi.u32 " D ", " S ", 65536;\n"
+#define HZ_SHR12(D, S) "mul.hi.u32 " D ", " S ", 1048576;\n"
+#else
+#define HZ_SHR20(D, S) "shr.u32 " D ", " S ", 20;\n"
+#define HZ_SHR16(D, S) "shr.u32 " D ", " S ", 16;\n"
+#define HZ_SHR12(D, S) "shr.u32 " D ", " S ", 12;\n"
+#endif
+
 // Advance from `pos` to the first codeword boundary >= limit; returns the number of codewords
 // that began before `limit`.  Unmatched patterns consume one bit.
 __device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitRd& r, uint32_t& pos, uint32_t limit) {
@@ -502,11 +515,11 @@ __device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitR
         const uint32_t two = 2u * gridDim.y;
 #define HZ_ASTEP(PI, PO, SFX)                                                  \
     "shf.l.wrap.b32 v, %2, %1, " PI ";\n"                                      \
-    "shr.u32 ix, v, 20;\n"                                                     \
+    HZ_SHR20("ix", "v")                                                        \
     "mad.lo.u32 ix, ix, %9, %6;\n"                                             \
     "ld.shared.u16 e, [ix];\n"                                                 \
     "and.b32 l, e, 63;\n"                                                      \
-    "shr.u32 n, e, 12;\n"                                                      \
+    HZ_SHR12("n", "e")                                                         \
     "setp.lt.u32 pz, e, 4096;\n"                                               \
     "@pz bra HZA_RARE" SFX ";\n"                                               \
     "HZA_BACK" SFX ":\n"                                                       \
@@ -1050,7 +1063,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
     "setp.ne.u32 p0, a, 0;\n"                                                 \
     "and.b32 a, t, 0x200000;\n"                                               \
     "setp.ne.u32 p1, a, 0;\n"                                                 \
-    "shr.u32 F, " CI ", 16;\n"                                                \
+    HZ_SHR16("F", CI)                                                         \
     "@p0 mov.u32 %1, %2;\n"                                                   \
     "@p0 prmt.b32 %2, %3, z, 0x0123;\n"                                       \
     "@p0 ld.shared.u32 %3, [%4+8];\n"                                         \
@@ -1063,7 +1076,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
     "selp.b32 %5, t, %5, p1;\n"
 #define HZ_WSTEP(CI, CO, SFX)                                                 \
     "shf.l.wrap.b32 v, %2, %1, " CI ";\n"                                     \
-    "shr.u32 ix, v, 20;\n"                                                    \
+    HZ_SHR20("ix", "v")                                                       \
     "mad.lo.u32 ix, ix, 8, %8;\n"                                             \
     "ld.shared.v2.u32 {ex, ey}, [ix];\n"                                      \
     "shf.l.wrap.b32 t, v, z, ey;\n"                                           \
