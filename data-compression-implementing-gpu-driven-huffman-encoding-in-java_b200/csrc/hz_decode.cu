@@ -488,7 +488,7 @@ static_assert(offsetof(DecAux, lim) == 0, "HZ_PTX_LONGLEN reads lim[] at the sta
 // Right shifts inside the hand-written loops.  -DHZ_DEC_FMA_SHIFTS (A/B variant for the next GPU session, never the
 // default) takes them as hi32(x * 2^(32 - s)) on the FMA pipe: both loops are bound
 // by the half-rate integer ALU pipe (sync 73 %, write 63 % busy) while the FMA pipe idles.
-#if defined(HZ_DEC_FMA_SHIFTS)
+#if defined(HZ_DEC_FMA_SHIFTS) && HZ_DEC_FMA_SHIFTS >= 1
 #define HZ_SHR20(D, S) "mul.hi.u32 " D ", " S ", 4096;\n"
 #define HZ_SHR16(D, S) "mul.hi.u32 " D ", " S ", 65536;\n"
 #define HZ_SHR12(D, S) "mul.hi.u32 " D ", " S ", 1048576;\n"
@@ -496,6 +496,15 @@ static_assert(offsetof(DecAux, lim) == 0, "HZ_PTX_LONGLEN reads lim[] at the sta
 #define HZ_SHR20(D, S) "shr.u32 " D ", " S ", 20;\n"
 #define HZ_SHR16(D, S) "shr.u32 " D ", " S ", 16;\n"
 #define HZ_SHR12(D, S) "shr.u32 " D ", " S ", 12;\n"
+#endif
+// Level 2 (-DHZ_DEC_FMA_SHIFTS=2) also advances the reader / writer pointers with a multiply-add by a 2 that ptxas
+// cannot fold (TWO = the operand holding 2 * gridDim.y; grids are one-dimensional).
+#if defined(HZ_DEC_FMA_SHIFTS) && HZ_DEC_FMA_SHIFTS >= 2
+#define HZ_ADD4(PRED, R, TWO) PRED " mad.lo.u32 " R ", " TWO ", 2, " R ";\n"
+#define HZ_W_TWO_OPERAND , "r"(2u * gridDim.y)
+#else
+#define HZ_ADD4(PRED, R, TWO) PRED " add.u32 " R ", " R ", 4;\n"
+#define HZ_W_TWO_OPERAND
 #endif
 
 // Advance from `pos` to the first codeword boundary >= limit; returns the number of codewords
@@ -531,7 +540,7 @@ __device__ __forceinline__ uint32_t advance(const DecAux& A, uint32_t slut, BitR
     "@p0 mov.u32 %1, %2;\n"                                                    \
     "@p0 prmt.b32 %2, %4, z, 0x0123;\n"                                        \
     "@p0 ld.shared.u32 %4, [%3+8];\n"                                          \
-    "@p0 add.u32 %3, %3, 4;\n"                                                 \
+    HZ_ADD4("@p0", "%3", "%9")                                                 \
     "setp.gt.u32 pc, " PO ", %7;\n"
 #define HZ_ARARE(SFX)                                                          \
     "HZA_RARE" SFX ":\n"                                                       \
@@ -1067,12 +1076,12 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
     "@p0 mov.u32 %1, %2;\n"                                                   \
     "@p0 prmt.b32 %2, %3, z, 0x0123;\n"                                       \
     "@p0 ld.shared.u32 %3, [%4+8];\n"                                         \
-    "@p0 add.u32 %4, %4, 4;\n"                                                \
+    HZ_ADD4("@p0", "%4", "%14")                                               \
     "shf.l.wrap.b32 a, z, ex, F;\n"                                           \
     "shf.l.wrap.b32 t, ex, z, F;\n"                                           \
     "add.u32 %5, %5, a;\n"                                                    \
     "@p1 st.shared.u32 [%6], %5;\n"                                           \
-    "@p1 add.u32 %6, %6, 4;\n"                                                \
+    HZ_ADD4("@p1", "%6", "%14")                                               \
     "selp.b32 %5, t, %5, p1;\n"
 #define HZ_WSTEP(CI, CO, SFX)                                                 \
     "shf.l.wrap.b32 v, %2, %1, " CI ";\n"                                     \
@@ -1140,6 +1149,7 @@ dec_write_kernel(const uint8_t* __restrict__ comp, uint64_t comp_bytes, const ui
                         : "+r"(C), "+r"(r.hi), "+r"(r.lo), "+r"(nx), "+r"(r.wa), "+r"(acc), "+r"(sp)
                         : "r"(Cmain), "r"(smem_u32(W.wlut)), "l"(status),
                           "n"(LUTN * 8), "n"(offsetof(DecAux, symbase)), "n"(offsetof(DecAux, sorted)), "n"(HZ_ERR_DECODE)
+                          HZ_W_TWO_OPERAND
                         : "memory");
 #undef HZ_WSTEP
 #undef HZ_WCHECK

@@ -57,6 +57,7 @@ def _spills(ptxas_log):
     ("hz_encode.cu", "-DHZ_ENC_IMAD_EXTRACT=2", ("encode_kernel",), "IMAD.HI"),                 # ... all four bytes
     ("hz_encode.cu", "-DHZ_ENC_IMAD_EXTRACT=3", ("encode_kernel",), "IMAD.HI"),                 # ... and the row pointer advanced by an IMAD
     ("hz_decode.cu", "-DHZ_DEC_FMA_SHIFTS", ("dec_sync_kernel", "dec_write_kernel"), "IMAD.HI"),  # loop shifts as hi32(x * 2^k)
+    ("hz_decode.cu", "-DHZ_DEC_FMA_SHIFTS=2", ("dec_sync_kernel", "dec_write_kernel"), "IMAD.HI"),  # ... and the stream pointers by IMAD
 ])
 def test_ab_switches_compile(tmp_path, src, flag, hot, expect):
     obj = str(tmp_path / (src + ".o"))

@@ -10,8 +10,9 @@ declare -A VAR=(
   [enc1]="-DHZ_ENC_IMAD_EXTRACT=1"
   [enc2]="-DHZ_ENC_IMAD_EXTRACT=2"
   [enc3]="-DHZ_ENC_IMAD_EXTRACT=3"
-  [decfma]="-DHZ_DEC_FMA_SHIFTS"
-  [all]="-DHZ_ENC_IMAD_EXTRACT=2 -DHZ_DEC_FMA_SHIFTS"
+  [decfma]="-DHZ_DEC_FMA_SHIFTS=1"
+  [decfma2]="-DHZ_DEC_FMA_SHIFTS=2"
+  [all]="-DHZ_ENC_IMAD_EXTRACT=2 -DHZ_DEC_FMA_SHIFTS=2"
 )
 case "${1:-}" in
   build)
