@@ -40,7 +40,7 @@ struct hz_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     // kernel attributes (opt-in shared memory) are per device: set once per context, not once per process
-    bool attr_encode = false, attr_decode = false, attr_hist = false, attr_codebook = false;
+    bool attr_encode = false, attr_decode = false, attr_decode_fused = false, attr_hist = false, attr_codebook = false;
     // device-side status word (first error latched by kernels) + pinned host mirror
     int* d_status = nullptr;
     int* h_status = nullptr;
@@ -110,6 +110,10 @@ int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_byte
 int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const uint64_t* d_comp_off,
                const uint32_t* d_comp_size, const uint32_t* d_orig_size, const uint64_t* d_orig_off,
                const uint8_t* d_len, uint32_t K, uint8_t* d_out, uint64_t out_cap);
+int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const uint64_t* d_comp_off,
+                     const uint32_t* d_comp_size, const uint32_t* d_orig_size, const uint64_t* d_orig_off,
+                     const uint8_t* d_len, uint32_t K, uint8_t* d_out, uint64_t out_cap, const uint8_t* d_ident,
+                     const uint64_t** plan_orig_off, const uint32_t** plan_islice);
 int hzk_sha256(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
                uint8_t* d_digests);
 

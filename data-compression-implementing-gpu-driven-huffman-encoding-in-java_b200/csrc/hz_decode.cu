@@ -41,10 +41,9 @@
 //             .y bits 31+30: several candidate lengths or no code, .x = shortest | longest<<6.
 // Codes whose used lengths are all equal never self-synchronise but need no synchronisation
 // either: entries are computed arithmetically.
-#include <cstdlib>
-#include "hz_common.cuh"
+#include <cstring>
+#include "hz_decode_tables.cuh"
 
-#define DT 256
 #ifndef DEC_SUB_WORDS
 #define DEC_SUB_WORDS 17                      // odd: subsequences start in different smem banks
 #endif
@@ -60,162 +59,14 @@
 #define DEC_SEQ_PER_CTA 12                    // divisible by 1, 2 and 3 write groups
 #endif
 #define DEC_SUBS_PER_CTA (DT * DEC_SEQ_PER_CTA)
-#define LUTB 12
-#define LUTN (1 << LUTB)
 // staged bytes per sequence: 16 alignment slack + 16 overlap + sequence + 32 look-ahead
 #define DEC_STAGE_BYTES ((16 + DEC_OVERLAP_BYTES + DEC_SEQ_BYTES + 32 + 15) & ~15)
 #define DEC_STAGE_WORDS (DEC_STAGE_BYTES / 4)
 #define DEC_WIN_MIN 2304                      // per-warp output window of the write kernel (runtime sized)
 #define DEC_WIN_MAX 9216
-#define DEC_NO_TABLE 0xFFFFFFFFu
-#define DEC_TAB_W 0                              // uint2 wlut[LUTN]
-#define DEC_TAB_S (LUTN * 8)                    // uint16 slut[LUTN]
-#define DEC_TAB_AUX (LUTN * 8 + LUTN * 2)       // DecAux
-#define DEC_TABLE_BYTES (DEC_TAB_AUX + 1024)
 #define DEC_TAB_PREBUILD_CAP (6ull << 30)        // scratch the prebuilt tables of single-CTA chunks may take (41 KiB per chunk)
 
-struct __align__(16) DecAux {
-    uint64_t lim[34];          // exclusive upper bound of the left-justified (32-bit) codes of each length
-    int32_t symbase[34];       // sorted[symbase[l] + code] = symbol of a length-l code
-    uint8_t sorted[256];       // symbols ordered by (length, symbol)
-    uint8_t len[256];          // code length of every symbol
-    int maxlen, minlen, uniform, bad;
-};
-static_assert(sizeof(DecAux) <= 1024, "DecAux must fit its 1 KiB slot");
-// shared-memory offset of DecAux::sorted relative to the write kernel's wlut (WriteShared: wlut, then aux)
-#define DEC_W_SORTED_REL (LUTN * 8 + (uint32_t)offsetof(DecAux, sorted))
 
-// ---------------------------------------------------------------------------------------------
-// table construction (all DT threads).  scratch: >= 8 KiB + 2 KiB of shared memory.
-// ---------------------------------------------------------------------------------------------
-#define DEC_BUILD_SCRATCH (LUTN * 2 + 512 + 256 + 8 * 34 * 4 + 3 * 34 * 4)
-
-// length of the (long) code that starts the left-justified 32 stream bits v, searched in
-// [lmin, lmax]; 0 = no code matches
-__device__ __forceinline__ uint32_t long_len(const DecAux& A, uint32_t v, uint32_t lmin, uint32_t lmax) {
-    if (lmin == 0) return 0;
-    uint32_t l = lmin;
-    while (l < lmax && (uint64_t)v >= A.lim[l]) ++l;
-    return (uint64_t)v < A.lim[l] ? l : 0;
-}
-
-// barrier of the DT threads that build a table (threads 0..DT-1 of the CTA; the write kernel's CTA is larger)
-__device__ __forceinline__ void bt_sync() { asm volatile("bar.sync 1, %0;" ::"n"(DT) : "memory"); }
-
-template <bool WANT_W, bool WANT_S>
-__device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __restrict__ slut,
-                             uint8_t* __restrict__ scratch, const uint8_t* __restrict__ len_k) {
-    uint16_t* base = reinterpret_cast<uint16_t*>(scratch);                // [LUTN] sym | len<<8
-    uint32_t* cntw = reinterpret_cast<uint32_t*>(scratch + LUTN * 2 + 768);   // [8][34]
-    uint32_t* first = cntw + 8 * 34;                                      // [34] first canonical code per length
-    uint32_t* count = first + 34;                                         // [34] symbols per length
-    uint32_t* offs = count + 34;                                          // [34] offset of each length in sorted[]
-    const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    uint32_t l = len_k[t];
-    if (l > 32) l = 33;
-    A.len[t] = (uint8_t)l;
-    for (uint32_t i = t; i < 8 * 34; i += DT) cntw[i] = 0;
-    bt_sync();
-    const uint32_t same = __match_any_sync(0xffffffffu, l);
-    const uint32_t rank_w = __popc(same & ((1u << lane) - 1));
-    if (rank_w == 0) cntw[wid * 34 + l] = __popc(same);
-    bt_sync();
-    if (t < 34) {
-        uint32_t c = 0;
-        for (int w = 0; w < 8; ++w) c += cntw[w * 34 + t];
-        count[t] = t == 0 ? 0 : c;
-    }
-    bt_sync();
-    if (t == 0) {
-        uint32_t c = 0, o = 0;
-        int mx = 0, mn = 0;
-        uint64_t kraft = 0;                       // in units of 2^-32
-        first[0] = 0; offs[0] = 0; A.lim[0] = 0; A.symbase[0] = 0;
-        for (int L = 1; L <= 32; ++L) {
-            c = (c + (L > 1 ? count[L - 1] : 0u)) << 1;
-            first[L] = c; offs[L] = o; o += count[L];
-            A.symbase[L] = (int32_t)offs[L] - (int32_t)c;
-            A.lim[L] = ((uint64_t)c + count[L]) << (32 - L);
-            if (count[L]) { mx = L; if (!mn) mn = L; kraft += (uint64_t)count[L] << (32 - L); }
-        }
-        offs[33] = o; first[33] = 0; A.lim[33] = 0; A.symbase[33] = 0;
-        A.maxlen = mx; A.minlen = mn;
-        A.uniform = (mx > 0 && mx == mn) ? mx : 0;
-        A.bad = (count[33] != 0) || (kraft > (1ull << 32));
-    }
-    bt_sync();
-    if (A.bad) return;
-    if (l >= 1 && l <= 32) {
-        uint32_t rank = rank_w;
-        for (uint32_t w = 0; w < wid; ++w) rank += cntw[w * 34 + l];
-        A.sorted[offs[l] + rank] = (uint8_t)t;
-    }
-    bt_sync();
-    // single-symbol table.  The left-justified codes of a canonical code are ordered by length, so the code
-    // that starts a 12-bit prefix x has the first length l with x < lim12[l] (lim12 = A.lim >> 20, exact for
-    // l <= LUTB): LUTB register compares per entry, no search.  Thread t fills entries t, t + 256, ...
-    // (consecutive lanes -> consecutive entries: conflict-free shared accesses, coalesced table stores).
-    {
-        uint32_t lim12[LUTB + 1];
-#pragma unroll
-        for (int L = 1; L <= LUTB; ++L) lim12[L] = (uint32_t)(A.lim[L] >> (32 - LUTB));
-#pragma unroll 4
-        for (uint32_t x = t; x < LUTN; x += DT) {
-            uint32_t li = 1;
-#pragma unroll
-            for (int L = 1; L <= LUTB; ++L) li += x >= lim12[L];
-            uint16_t e = 0;
-            if (li <= LUTB) e = (uint16_t)(A.sorted[A.symbase[li] + (int32_t)(x >> (LUTB - li))] | (li << 8));
-            base[x] = e;
-        }
-    }
-    bt_sync();
-    // multi-symbol tables
-    const uint32_t maxlen = (uint32_t)A.maxlen;
-    for (uint32_t x = t; x < LUTN; x += DT) {
-        const uint32_t e0 = base[x];
-        uint2 we = make_uint2(0u, 0xC0000000u);
-        uint32_t se = 0;
-        if (e0) {
-            const uint32_t l0 = e0 >> 8;
-            uint32_t syms = e0 & 0xFF, used = l0, n = 1, wtot = l0, wn = 1, cur = x, lprev = l0;
-            for (;;) {
-                cur = (cur << lprev) & (LUTN - 1);
-                const uint32_t e = base[cur];
-                if (!e) break;
-                const uint32_t le = e >> 8;
-                if (used + le > LUTB) break;
-                if (n < 4) { syms |= (e & 0xFF) << (8 * n); wtot = used + le; wn = n + 1; }
-                used += le; ++n; lprev = le;
-            }
-            we = make_uint2(syms, wtot | (wn << 19));
-            se = used | (l0 << 6) | (n << 12);
-        } else if (maxlen > LUTB) {
-            // the prefix starts a code longer than LUTB bits (or no code): candidate lengths at both ends
-            const uint32_t vlo = x << (32 - LUTB), vhi = vlo | ((1u << (32 - LUTB)) - 1);
-            const uint32_t lmin = long_len(A, vlo, LUTB + 1, maxlen);
-            if (lmin) {
-                uint32_t lmax = long_len(A, vhi, lmin, maxlen);
-                if (!lmax) lmax = maxlen;
-                we.x = lmin | (lmax << 6);
-                // every code under this prefix has the same length: `sorted` is the second-level table
-                if (lmin == lmax && lmin < 32)
-                    we = make_uint2(DEC_W_SORTED_REL + (uint32_t)A.symbase[lmin], 0x80000000u | lmin | (8u << 16));
-                se = lmin == lmax ? (lmin | (lmin << 6) | (1u << 12)) : (lmin | (lmax << 6));
-            }
-        }
-        if (WANT_W) wlut[x] = we;
-        if (WANT_S) slut[x] = (uint16_t)se;
-    }
-    bt_sync();
-}
-
-// copy `bytes` (multiple of 16) from global to shared with all threads of the CTA
-__device__ __forceinline__ void copy_g2s16(void* dst, const void* src, uint32_t bytes) {
-    const uint4* s = reinterpret_cast<const uint4*>(src);
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = s[i];
-}
 
 // ---------------------------------------------------------------------------------------------
 // plan
@@ -347,22 +198,6 @@ dec_tables_kernel(const uint8_t* __restrict__ len_tab, DecPlan P, uint8_t* __res
 // ---------------------------------------------------------------------------------------------
 // staging of one sequence's compressed bytes: 1-D TMA bulk copy + mbarrier
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 
 struct StageGeom {
     uint64_t a0;         // 16-byte aligned global address of stage byte 0
@@ -426,17 +261,6 @@ __device__ __forceinline__ void stage_fixup(uint8_t* stage, const StageGeom& g, 
 // ---------------------------------------------------------------------------------------------
 // bit reader over the staged bytes: (hi, lo) = 64 upcoming stream bits, sh = consumed bits of hi
 // ---------------------------------------------------------------------------------------------
-// shared-state-space accesses with 32-bit addresses (keeps the hot loops free of generic->shared
-// window arithmetic)
-__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-
-// keep a value in a register: stops the compiler from re-deriving shared-window bases in hot loops
-__device__ __forceinline__ uint32_t pin_reg(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 
 struct BitRd {
     uint32_t wa;           // shared address of the word held in `lo`
@@ -464,26 +288,6 @@ struct SyncSmem {
     uint32_t s_k;
 };
 
-// PTX twin of long_len() for the hand-written loops.  Registers of the enclosing asm block: v (32 stream
-// bits), l (in: shortest, out: length found or 0), m (longest candidate), auxb (shared address of DecAux);
-// temporaries a, t, u and predicate pq.  SFX makes the labels unique.
-#define HZ_PTX_LONGLEN(SFX)                         \
-    "setp.eq.u32 pq, l, 0;\n"                       \
-    "@pq bra HZL_END" SFX ";\n"                     \
-    "HZL_TOP" SFX ":\n"                             \
-    "mad.lo.u32 a, l, 8, auxb;\n"                   \
-    "ld.shared.v2.u32 {t, u}, [a];\n"               \
-    "setp.ne.u32 pq, u, 0;\n"                       \
-    "@pq bra HZL_END" SFX ";\n"                     \
-    "setp.lt.u32 pq, v, t;\n"                       \
-    "@pq bra HZL_END" SFX ";\n"                     \
-    "setp.ge.u32 pq, l, m;\n"                       \
-    "@pq mov.u32 l, 0;\n"                           \
-    "@pq bra HZL_END" SFX ";\n"                     \
-    "add.u32 l, l, 1;\n"                            \
-    "bra HZL_TOP" SFX ";\n"                         \
-    "HZL_END" SFX ":\n"
-static_assert(offsetof(DecAux, lim) == 0, "HZ_PTX_LONGLEN reads lim[] at the start of DecAux");
 
 // Right shifts inside the hand-written loops.  -DHZ_DEC_FMA_SHIFTS (A/B variant for the next GPU session, never the
 // default) takes them as hi32(x * 2^(32 - s)) on the FMA pipe: both loops are bound
@@ -1242,6 +1046,15 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     uint32_t ident_on = 1;                 // developer knob: HZ_IDENT=0 sends identity chunks through the table walk
     if (const char* ev = getenv("HZ_IDENT")) ident_on = atoi(ev) != 0;
     HZ_LAUNCH(ctx, "dec_ident", dec_ident_flags_kernel, (K + DT / 32 - 1) / (DT / 32), DT, 0, d_len, d_orig_size, K, ident, ident_on);
+    static const bool legacy = [] { const char* ev = getenv("HZ_DEC"); return ev && strcmp(ev, "legacy") == 0; }();   // developer knob
+    if (!legacy) {
+        const uint64_t* p_orig_off = nullptr; const uint32_t* p_islice = nullptr;
+        HZ_TRY(hzk_decode_fused(ctx, d_comp, comp_bytes, d_comp_off, d_comp_size, d_orig_size, d_orig_off, d_len, K, d_out, out_cap,
+                                ident, &p_orig_off, &p_islice));
+        HZ_LAUNCH(ctx, "dec_ident_copy", dec_ident_copy_kernel, 8 * ctx->sm_count, DT, 0, d_comp, d_comp_off, d_comp_size,
+                  d_orig_size, p_orig_off, p_islice, K, d_out, out_cap, ctx->d_status);
+        return HZ_OK;
+    }
     HZ_LAUNCH(ctx, "dec_plan", dec_plan_kernel, 1, 1024, 0, d_comp_size, d_orig_size, d_orig_off, K, P, tab_min_seq, ident);
     // upper bounds (no host sync): every chunk has at most ceil(comp_size*8/SUB_BITS)+1 subsequences
     const uint64_t max_sub = comp_bytes * 8 / DEC_SUB_BITS + 2ull * K + 2;

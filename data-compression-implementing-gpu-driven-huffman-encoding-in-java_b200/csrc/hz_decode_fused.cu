@@ -1,0 +1,858 @@
+// hz_decode_fused.cu — single-residency chunked Huffman decode: ONE walk over the compressed stream.
+//
+// Replaces CanonicalHuffman.generateCanonicalCodesFromLengths + TableBasedHuffmanDecoder.decode
+// (core/CanonicalHuffman.java:141-146, core/TableBasedHuffmanDecoder.java:36-152, driven by
+// CpuCompressionService.decodeChunkParallel, service/cpu/CpuCompressionService.java:511-532).
+//
+// A chunk of the .dcz payload is one sequential bitstream without restart markers.  It is cut into
+// subsequences of S 32-bit words (S per chunk, so that a subsequence holds ~128 symbols); 32 consecutive
+// subsequences form a UNIT, the work item of one warp.  A warp
+//   1. receives its unit's bytes by a 1-D TMA bulk copy into its private stage (cp.async.bulk + mbarrier),
+//      byte-swaps them in place (the bit reader then needs no PRMT) and zero-fills what lies outside the chunk;
+//   2. lane i starts a few words before subsequence i (a guess), walks to the first codeword boundary inside it
+//      (self-synchronisation), then decodes the subsequence ONCE, up to four symbols per table lookup, into its
+//      private row of shared memory (word-interleaved rows: lane == bank, no conflicts), counting symbols;
+//      exit[i-1] == entry[i] is checked with shuffles and mismatching lanes re-walk from the neighbour's exit;
+//   3. publishes {entry of lane 0, exit of lane 31, symbol count} and obtains the unit's output offset by a
+//      decoupled look-back over the records of the chunk's earlier units.  A record is FINAL once its chain of
+//      entry == previous exit links reaches the chunk's first unit; a unit whose own link is broken re-walks
+//      from the true entry before it finalises, so the result never depends on the guesses;
+//   4. compacts the 32 rows in place (all rows to registers, then shifted word stores) into one contiguous
+//      window aligned like the destination and sends it to global memory with one asynchronous bulk copy.
+// Units are handed out in stream order by a per-chunk atomic counter, so a unit only ever waits for units that
+// running warps hold.  A CTA (24 warps) keeps one chunk's lookup table (32 KiB, shared by its warps); CTAs take
+// chunks from a global ticket and, when none are left, join chunks that still have units.
+#include <cstdio>
+#include "hz_decode_tables.cuh"
+
+#define FU_WARPS 24
+#define FU_THREADS (FU_WARPS * 32)
+#define FU_SUB_MIN 4
+#define FU_SUB_MAX 17
+#define FU_ROW_WORDS 46                            // 44 words of symbols + 2 guard words (overflow is tested once per two lookups)
+#define FU_CAP_SYMS 176
+#define FU_CAP_BITS (FU_CAP_SYMS * 8)              // multiple of 32: the packed counter's low five bits stay the byte lane
+#define FU_OUT_BIAS (0x8000u - FU_CAP_BITS)        // bit 15 of the output field <=> the row is full
+#define FU_STAGE_BYTES 2240                        // 15 alignment + 16 lead-in + 17 * 128 + 32 look-ahead, rounded to 16
+#define FU_ROWS_BYTES (32 * FU_ROW_WORDS * 4)
+#define FU_WARP_BYTES (FU_STAGE_BYTES + FU_ROWS_BYTES)
+#define FU_TABLE_BYTES (LUTN * 8 + 1024)           // wlut + DecAux
+#define FU_NONE 0xFFFFFFFFu
+
+struct FuShared {
+    __align__(16) uint2 wlut[LUTN];
+    __align__(16) uint8_t aux[1024];
+    __align__(8) uint64_t bar[FU_WARPS];
+    uint32_t s_k, s_pick;
+};
+static_assert(offsetof(FuShared, aux) + offsetof(DecAux, sorted) == DEC_W_SORTED_REL, "long-code entries address sorted[] relative to wlut");
+#define FU_SHARED_BYTES ((sizeof(FuShared) + 15) & ~(size_t)15)
+#define FU_SMEM_BYTES (FU_SHARED_BYTES + (size_t)FU_WARPS * FU_WARP_BYTES)
+
+struct FuPlan {
+    uint64_t* orig_off;     // [K+1]
+    uint32_t* nsub;         // [K]   subsequences (0: empty, identity or rejected chunk)
+    uint32_t* nunit;        // [K]
+    uint32_t* unit_base;    // [K+1] first look-back record of chunk k
+    uint32_t* geom;         // [K]   S | lead-in words << 8
+    uint32_t* unit_ctr;     // [K]   next unit of chunk k (device tickets)
+    uint32_t* islice;       // [K+1] identity-copy slices before chunk k
+    uint32_t* ctl;          // [0] chunk ticket
+};
+#define FU_IDENT_SLICE 65536u
+
+// ---------------------------------------------------------------------------------------------
+// plan: per-chunk geometry and prefix sums (1 CTA)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fu_chunk_geom(uint32_t csize, uint32_t osize, bool ident, bool ok,
+                                              uint32_t& S, uint32_t& lead, uint32_t& ns) {
+    S = FU_SUB_MAX; lead = 4; ns = 0;
+    if (!ok || ident || osize == 0) return;
+    // ~128 symbols per subsequence: S = 128 * (8 csize / osize) / 32 words
+    uint64_t s = ((uint64_t)csize * 32) / osize;
+    S = (uint32_t)(s < FU_SUB_MIN ? FU_SUB_MIN : (s > FU_SUB_MAX ? FU_SUB_MAX : s));
+    // lead-in of ~28 codewords before a subsequence for the self-synchronisation guess
+    uint64_t l = ((uint64_t)csize * 7 + osize - 1) / osize;
+    lead = (uint32_t)(l < 2 ? 2 : (l > 4 ? 4 : l));
+    const uint64_t bits = (uint64_t)csize * 8, sb = (uint64_t)S * 32;
+    ns = (uint32_t)((bits + sb - 1) / sb);
+    if (ns == 0) ns = 1;
+}
+
+__global__ void __launch_bounds__(1024)
+fu_plan_kernel(const uint64_t* __restrict__ comp_off, const uint32_t* __restrict__ comp_size,
+               const uint32_t* __restrict__ orig_size, const uint64_t* __restrict__ orig_off_in, uint64_t comp_bytes,
+               uint32_t K, FuPlan P, const uint8_t* __restrict__ ident, int* status) {
+    __shared__ uint64_t part[3][1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (K + 1023) / 1024;
+    const uint32_t lo = min(K, t * per), hi = min(K, lo + per);
+    uint64_t s0 = 0, s1 = 0, s2 = 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+        // the chunk must lie inside the addressable stream (untrusted footer fields reach this ABI)
+        const bool ok = comp_off[i] <= comp_bytes && comp_size[i] <= comp_bytes - comp_off[i];
+        if (!ok) hz_set_status(status, HZ_ERR_ARG);
+        uint32_t S, lead, ns;
+        fu_chunk_geom(comp_size[i], orig_size[i], ident[i] != 0, ok, S, lead, ns);
+        s0 += (ns + 31) / 32; s1 += orig_size[i];
+        s2 += (ok && ident[i]) ? (orig_size[i] + FU_IDENT_SLICE - 1) / FU_IDENT_SLICE : 0u;
+    }
+    part[0][t] = s0; part[1][t] = s1; part[2][t] = s2;
+    __syncthreads();
+    if (t < 3) {
+        uint64_t a = 0;
+        for (int j = 0; j < 1024; ++j) { uint64_t x = part[t][j]; part[t][j] = a; a += x; }
+        if (t == 0) P.unit_base[K] = (uint32_t)a;
+        if (t == 1) P.orig_off[K] = a;
+        if (t == 2) P.islice[K] = (uint32_t)a;
+    }
+    __syncthreads();
+    s0 = part[0][t]; s1 = part[1][t]; s2 = part[2][t];
+    for (uint32_t i = lo; i < hi; ++i) {
+        const bool ok = comp_off[i] <= comp_bytes && comp_size[i] <= comp_bytes - comp_off[i];
+        uint32_t S, lead, ns;
+        fu_chunk_geom(comp_size[i], orig_size[i], ident[i] != 0, ok, S, lead, ns);
+        P.nsub[i] = ns; P.nunit[i] = (ns + 31) / 32; P.unit_base[i] = (uint32_t)s0; P.geom[i] = S | (lead << 8);
+        P.unit_ctr[i] = 0;
+        P.orig_off[i] = orig_off_in ? orig_off_in[i] : s1;
+        P.islice[i] = (uint32_t)s2;
+        s0 += (ns + 31) / 32; s1 += orig_size[i];
+        s2 += (ok && ident[i]) ? (orig_size[i] + FU_IDENT_SLICE - 1) / FU_IDENT_SLICE : 0u;
+    }
+    if (t == 0) P.ctl[0] = 0;
+}
+
+// look-back records of the units that exist (their number is only known on the device)
+__global__ void __launch_bounds__(256)
+fu_zero_kernel(uint64_t* __restrict__ rec, const uint32_t* __restrict__ unit_base, uint32_t K) {
+    const uint32_t n = unit_base[K];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) rec[i] = 0;
+}
+
+// tables: one CTA per chunk, written to global memory once, copied by every CTA that works on the chunk
+__global__ void __launch_bounds__(DT)
+fu_tables_kernel(const uint8_t* __restrict__ len_tab, FuPlan P, uint8_t* __restrict__ tables) {
+    __shared__ __align__(16) uint8_t scratch[DEC_BUILD_SCRATCH];
+    __shared__ __align__(16) uint8_t aux_raw[1024];
+    const uint32_t k = blockIdx.x;
+    if (P.nsub[k] == 0) return;
+    DecAux& A = *reinterpret_cast<DecAux*>(aux_raw);
+    uint8_t* dst = tables + (size_t)k * FU_TABLE_BYTES;
+    build_tables<true, false, 1>(A, reinterpret_cast<uint2*>(dst), nullptr, scratch, len_tab + (size_t)k * 256);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 1024 / 16; i += DT) reinterpret_cast<uint4*>(dst + LUTN * 8)[i] = reinterpret_cast<uint4*>(aux_raw)[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// look-back records: state (2) | entry of lane 0 (6) | exit of lane 31 (6) | symbols (18) | inclusive prefix (32)
+// ---------------------------------------------------------------------------------------------
+#define FU_EMPTY 0u
+#define FU_SPEC 1u
+#define FU_FINAL 2u
+__device__ __forceinline__ uint64_t fu_pack(uint32_t st, uint32_t entry, uint32_t exitv, uint32_t cnt, uint32_t pre) {
+    return (uint64_t)(st | (entry << 2) | (exitv << 8) | (cnt << 14)) | ((uint64_t)pre << 32);
+}
+__device__ __forceinline__ uint64_t ld_rec(const uint64_t* p) {
+    uint64_t v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_rec(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Decoupled look-back of unit u (u >= 1) over the chunk's records R[0..u).  Returns true with the number of
+// symbols before the unit in `prefix`, or false with the true entry of the unit's first subsequence in
+// `true_entry` when the unit has to re-walk (its guess differs from the FINAL exit of unit u - 1).
+__device__ bool fu_lookback(const uint64_t* __restrict__ R, uint32_t u, uint32_t my_entry0, uint32_t lane,
+                            uint32_t& prefix, uint32_t& true_entry) {
+    uint32_t acc = 0, expect = my_entry0;
+    int base = (int)u - 1;
+    uint32_t spins = 0;
+    for (;;) {
+        const int j = base - (int)lane;
+        const uint64_t rec = j >= 0 ? ld_rec(R + j) : 0ull;
+        const uint32_t w = (uint32_t)rec;
+        const uint32_t st = w & 3, en = (w >> 2) & 63, ex = (w >> 8) & 63, cnt = (w >> 14) & 0x3FFFF;
+        const uint32_t en_up = __shfl_up_sync(0xffffffffu, en, 1);
+        const uint32_t E = lane == 0 ? expect : en_up;            // entry used by the unit after unit j
+        const uint32_t me = __ballot_sync(0xffffffffu, st == FU_EMPTY);
+        const uint32_t mf = __ballot_sync(0xffffffffu, st == FU_FINAL);
+        const uint32_t mb = __ballot_sync(0xffffffffu, st != FU_EMPTY && ex != E);
+        const uint32_t any = me | mf | mb;
+        if (!any) {                                               // 32 consistent speculative records: keep going back
+            uint32_t c = cnt;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+            acc += c; expect = __shfl_sync(0xffffffffu, en, 31); base -= 32;
+            continue;
+        }
+        const uint32_t d = __ffs(any) - 1;                        // first decisive record
+        if ((mb >> d) & 1) {
+            if (d == 0 && base == (int)u - 1 && (mf & 1)) {       // my own link, against a FINAL record
+                true_entry = __shfl_sync(0xffffffffu, ex, 0);
+                return false;
+            }
+        } else if ((mf >> d) & 1) {
+            uint32_t c = lane < d ? cnt : 0;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+            prefix = __shfl_sync(0xffffffffu, (uint32_t)(rec >> 32), d) + acc + c;
+            return true;
+        }
+        // an unpublished record, or a broken link whose owner has not finalised yet: start over
+        if (++spins > 8) __nanosleep(spins > 64 ? 400 : 100);
+        acc = 0; expect = my_entry0; base = (int)u - 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage geometry of one unit
+// ---------------------------------------------------------------------------------------------
+struct UnitGeom {
+    uint64_t a0;            // 16-byte aligned global address of stage byte 0
+    int32_t need;           // stage bytes the unit uses (multiple of 16)
+    int32_t vlo, vhi;       // stage-relative byte range that belongs to the chunk
+    int32_t tlo, thi;       // stage-relative byte range delivered by the bulk copy
+    uint32_t bit0;          // stage-relative bit index of the unit's first bit (multiple of 8, >= 128)
+};
+__device__ __forceinline__ UnitGeom fu_geom(const uint8_t* comp, uint64_t comp_bytes, uint64_t chunk_off,
+                                            uint32_t chunk_size, uint32_t u, uint32_t S) {
+    UnitGeom g;
+    const uint64_t cb = reinterpret_cast<uint64_t>(comp) + chunk_off;
+    const uint64_t us = cb + (uint64_t)u * (128u * S);
+    g.a0 = (us - 16) & ~(uint64_t)15;
+    g.bit0 = (uint32_t)(us - g.a0) * 8;
+    g.need = (int32_t)(((us - g.a0) + 128u * S + 32 + 15) & ~(uint64_t)15);
+    int64_t vlo = (int64_t)cb - (int64_t)g.a0, vhi = vlo + chunk_size;
+    if (vlo < 0) vlo = 0;
+    if (vhi > g.need) vhi = g.need;
+    if (vhi < vlo) vhi = vlo;
+    g.vlo = (int32_t)vlo; g.vhi = (int32_t)vhi;
+    const uint64_t blo = (reinterpret_cast<uint64_t>(comp) + 15) & ~(uint64_t)15;
+    const uint64_t bhi = (reinterpret_cast<uint64_t>(comp) + comp_bytes) & ~(uint64_t)15;
+    uint64_t tl = g.a0 > blo ? g.a0 : blo;
+    uint64_t th = g.a0 + g.need < bhi ? g.a0 + g.need : bhi;
+    // nothing outside the chunk is needed: do not fetch it
+    const uint64_t cl = (g.a0 + (uint64_t)g.vlo) & ~(uint64_t)15, ch = (g.a0 + (uint64_t)g.vhi + 15) & ~(uint64_t)15;
+    if (tl < cl) tl = cl;
+    if (th > ch) th = ch;
+    if (th < tl) th = tl;
+    g.tlo = (int32_t)(tl - g.a0); g.thi = (int32_t)(th - g.a0);
+    return g;
+}
+
+// issued by ONE lane
+__device__ __forceinline__ void fu_stage_issue(uint32_t stage_a, uint32_t bar_a, const UnitGeom& g) {
+    const uint32_t bytes = (uint32_t)(g.thi - g.tlo);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (bytes) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(stage_a + (uint32_t)g.tlo), "l"(g.a0 + (uint64_t)g.tlo), "r"(bytes), "r"(bar_a) : "memory");
+    } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
+    }
+}
+__device__ __forceinline__ void fu_mbar_wait(uint32_t bar_a, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FW_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FW_DONE;\n"
+        "bra FW_LOOP;\n"
+        "FW_DONE:\n"
+        "}\n" ::"r"(bar_a), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// After the bulk copy landed: words become big-endian values (stream bit 0 = bit 31 of word 0), bytes outside
+// the chunk read as zero (TableBasedHuffmanDecoder.java:204-208), chunk bytes the 16-byte aligned copy could
+// not deliver are fetched one by one.  All lanes of the warp.
+__device__ __forceinline__ void fu_stage_prepare(uint32_t stage_a, const UnitGeom& g, uint32_t lane) {
+    const int32_t glo = g.vlo > g.tlo ? g.vlo : g.tlo, ghi = g.vhi < g.thi ? g.vhi : g.thi;   // good bytes
+    for (int32_t b0 = (int32_t)lane * 16; b0 < g.need; b0 += 32 * 16) {
+        uint4 w;
+        if (b0 >= glo && b0 + 16 <= ghi) {
+            w = lds128(stage_a + b0);
+        } else {
+            uint32_t x[4] = {0, 0, 0, 0};
+            for (int32_t j = 0; j < 16; ++j) {
+                const int32_t b = b0 + j;
+                uint32_t v = 0;
+                if (b >= g.vlo && b < g.vhi)
+                    v = (b >= g.tlo && b < g.thi) ? lds8(stage_a + b) : *reinterpret_cast<const uint8_t*>(g.a0 + (uint64_t)b);
+                x[j >> 2] |= v << (8 * (j & 3));
+            }
+            w = make_uint4(x[0], x[1], x[2], x[3]);
+        }
+        w.x = bswap32(w.x); w.y = bswap32(w.y); w.z = bswap32(w.z); w.w = bswap32(w.w);
+        sts128(stage_a + b0, w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bit reader + walks.  Packed counter C: bits 16-27 stream position relative to a multiple of 32 at or
+// before the walk's start (so (C >> 16) & 31 is the reader's funnel-shift amount), bits 0-15 output bits
+// (8 per symbol) + FU_OUT_BIAS, whose low five bits are the shift that puts a lookup's symbols behind the
+// bytes already in the accumulator.  One add of the table entry's .y advances both; bit 31 / 30 of an
+// entry (long code / several candidate lengths) make the sum fail the loop's single compare.
+// ---------------------------------------------------------------------------------------------
+struct Reader { uint32_t hi, lo, nx, wa; };      // stream words j, j+1, j+2 and the shared address of word j+2
+__device__ __forceinline__ void fu_seek(Reader& r, uint32_t stage_a, uint32_t pos) {
+    const uint32_t a = stage_a + ((pos >> 5) << 2);
+    r.hi = lds32(a); r.lo = lds32(a + 4); r.nx = lds32(a + 8); r.wa = a + 8;
+}
+
+#define FU_REFILL(CI, CO)                                                     \
+    "xor.b32 t, " CI ", " CO ";\n"                                            \
+    "and.b32 a, t, 0x200000;\n"                                               \
+    "setp.ne.u32 p0, a, 0;\n"                                                 \
+    "@p0 mov.u32 %1, %2;\n"                                                   \
+    "@p0 mov.u32 %2, %3;\n"                                                   \
+    "@p0 ld.shared.u32 %3, [%4+4];\n"                                         \
+    "@p0 add.u32 %4, %4, 4;\n"
+
+// resolves an entry with several candidate lengths / no code: l = its length, 0 when nothing matches
+#define FU_RARE_LEN(SFX, TAB, AUXOFF)                                         \
+    "ld.shared.v2.u32 {ex, ey}, [ix];\n"                                      \
+    "shr.u32 l, ex, 5;\n"                                                     \
+    "and.b32 l, l, 63;\n"                                                     \
+    "shr.u32 m, ex, 11;\n"                                                    \
+    "and.b32 m, m, 63;\n"                                                     \
+    "add.u32 auxb, " TAB ", " AUXOFF ";\n"                                    \
+    HZ_PTX_LONGLEN(SFX)
+
+// Walk WITHOUT output from C until the position field reaches Cend's: used for the lead-in before a
+// subsequence and to finish a subsequence whose row is full.  Cb / exl = counter before and symbols of the
+// last lookup (fu_settle() needs them).
+__device__ __forceinline__ void fu_skim(uint32_t& C, Reader& r, uint32_t Cend, uint32_t wlut_a, uint32_t& Cb, uint32_t& exl) {
+#define FU_SSTEP(CI, CO, SFX)                                                 \
+    "shr.u32 s, " CI ", 16;\n"                                                \
+    "shf.l.wrap.b32 v, %2, %1, s;\n"                                          \
+    "shr.u32 ix, v, 20;\n"                                                    \
+    "mad.lo.u32 ix, ix, 8, %7;\n"                                             \
+    "ld.shared.v2.u32 {ex, ey}, [ix];\n"                                      \
+    "add.u32 " CO ", " CI ", ey;\n"                                           \
+    "setp.lt.s32 pl, ey, 0;\n"                                                \
+    "@pl add.u32 " CO ", " CO ", 0x80000000;\n"                               \
+    "setp.ge.u32 px, " CO ", %8;\n"                                           \
+    "@px bra FS_CHECK" SFX ";\n"                                              \
+    "FS_BACK" SFX ":\n"                                                       \
+    FU_REFILL(CI, CO)
+#define FU_SCHECK(CI, CO, SFX, FIN)                                           \
+    "FS_CHECK" SFX ":\n"                                                      \
+    "and.b32 t, " CO ", 0x40000000;\n"                                        \
+    "setp.eq.u32 pq, t, 0;\n"                                                 \
+    "@pq bra FS_LAST" SFX ";\n"                                               \
+    FU_RARE_LEN("S" SFX, "%7", "%9")                                          \
+    "max.u32 l, l, 1;\n"                                                      \
+    "shl.b32 t, l, 16;\n"                                                     \
+    "add.u32 " CO ", " CI ", t;\n"                                            \
+    "add.u32 " CO ", " CO ", 8;\n"                                            \
+    "mov.u32 ex, 0;\n"                                                        \
+    "setp.lt.u32 pq, " CO ", %8;\n"                                           \
+    "@pq bra FS_BACK" SFX ";\n"                                               \
+    "FS_LAST" SFX ":\n"                                                       \
+    FU_REFILL(CI, CO)                                                         \
+    "mov.u32 %5, " CI ";\n"                                                   \
+    "mov.u32 %6, ex;\n"                                                       \
+    FIN                                                                       \
+    "bra FS_DONE;\n"
+    asm volatile(
+        "{\n"
+        ".reg .pred pl, px, p0, pq;\n"
+        ".reg .u32 D, s, v, ix, ex, ey, t, u, a, l, m, auxb;\n"
+        "FS_TOP:\n"
+        FU_SSTEP("%0", "D", "1")
+        FU_SSTEP("D", "%0", "2")
+        "bra FS_TOP;\n"
+        FU_SCHECK("%0", "D", "1", "mov.u32 %0, D;\n")
+        FU_SCHECK("D", "%0", "2", "")
+        "FS_DONE:\n"
+        "}\n"
+        : "+r"(C), "+r"(r.hi), "+r"(r.lo), "+r"(r.nx), "+r"(r.wa), "=&r"(Cb), "=&r"(exl)
+        : "r"(wlut_a), "r"(Cend), "n"(LUTN * 8)
+        : "memory");
+#undef FU_SSTEP
+#undef FU_SCHECK
+}
+
+// Walk WITH output: symbols go to the lane's word-interleaved row (sp = shared address of the next word,
+// acc = bytes not stored yet).  Stops when the position field reaches Cend's (ovf = 0) or, tested once per
+// two lookups, when the row is full (ovf = 1; the caller finishes with fu_skim).  badc = smallest output
+// field at which a bit pattern matched no codeword.
+__device__ __forceinline__ void fu_walk(uint32_t& C, Reader& r, uint32_t Cend, uint32_t wlut_a, uint32_t& acc, uint32_t& sp,
+                                        uint32_t& Cb, uint32_t& exl, uint32_t& badc, uint32_t& ovf) {
+#define FU_COMMIT(CI, CO)                                                     \
+    "xor.b32 t, " CI ", " CO ";\n"                                            \
+    "and.b32 a, t, 0x200000;\n"                                               \
+    "setp.ne.u32 p0, a, 0;\n"                                                 \
+    "and.b32 a, t, 32;\n"                                                     \
+    "setp.ne.u32 p1, a, 0;\n"                                                 \
+    "@p0 mov.u32 %1, %2;\n"                                                   \
+    "@p0 mov.u32 %2, %3;\n"                                                   \
+    "@p0 ld.shared.u32 %3, [%4+4];\n"                                         \
+    "@p0 add.u32 %4, %4, 4;\n"                                                \
+    "shf.l.wrap.b32 a, z, ex, " CI ";\n"                                      \
+    "shf.l.wrap.b32 t, ex, z, " CI ";\n"                                      \
+    "add.u32 %5, %5, a;\n"                                                    \
+    "@p1 st.shared.u32 [%6], %5;\n"                                           \
+    "@p1 add.u32 %6, %6, 128;\n"                                              \
+    "selp.b32 %5, t, %5, p1;\n"
+#define FU_WSTEP(CI, CO, SFX)                                                 \
+    "shr.u32 s, " CI ", 16;\n"                                                \
+    "shf.l.wrap.b32 v, %2, %1, s;\n"                                          \
+    "shr.u32 ix, v, 20;\n"                                                    \
+    "mad.lo.u32 ix, ix, 8, %11;\n"                                            \
+    "ld.shared.v2.u32 {ex, ey}, [ix];\n"                                      \
+    "shf.r.wrap.b32 t, v, z, ex;\n"                                           \
+    "shr.s32 a, ex, 5;\n"                                                     \
+    "add.u32 a, a, t;\n"                                                      \
+    "add.u32 a, a, %11;\n"                                                    \
+    "add.u32 " CO ", " CI ", ey;\n"                                           \
+    "setp.lt.s32 pl, ey, 0;\n"                                                \
+    "@pl ld.shared.u8 ex, [a];\n"                                             \
+    "@pl add.u32 " CO ", " CO ", 0x80000000;\n"                               \
+    "setp.ge.u32 px, " CO ", %12;\n"                                          \
+    "@px bra FW_CHECK" SFX ";\n"                                              \
+    "FW_BACK" SFX ":\n"                                                       \
+    FU_COMMIT(CI, CO)
+#define FU_WCHECK(CI, CO, SFX, FIN)                                           \
+    "FW_CHECK" SFX ":\n"                                                      \
+    "and.b32 t, " CO ", 0x40000000;\n"                                        \
+    "setp.eq.u32 pq, t, 0;\n"                                                 \
+    "@pq bra FW_LAST" SFX ";\n"                                               \
+    FU_RARE_LEN("W" SFX, "%11", "%13")                                        \
+    "setp.eq.u32 pq, l, 0;\n"                                                 \
+    "@pq bra FW_BAD" SFX ";\n"                                                \
+    "mad.lo.u32 a, l, 4, auxb;\n"                                             \
+    "ld.shared.u32 t, [a+%14];\n"                                             \
+    "sub.u32 u, 32, l;\n"                                                     \
+    "shr.u32 u, v, u;\n"                                                      \
+    "add.u32 a, t, u;\n"                                                      \
+    "add.u32 a, a, auxb;\n"                                                   \
+    "ld.shared.u8 ex, [a+%15];\n"                                             \
+    "bra FW_GOT" SFX ";\n"                                                    \
+    "FW_BAD" SFX ":\n"                                                        \
+    "mov.u32 l, 1;\n"                                                         \
+    "mov.u32 ex, 0;\n"                                                        \
+    "and.b32 t, " CI ", 0xFFFF;\n"                                            \
+    "min.u32 %7, %7, t;\n"                                                    \
+    "FW_GOT" SFX ":\n"                                                        \
+    "shl.b32 t, l, 16;\n"                                                     \
+    "add.u32 " CO ", " CI ", t;\n"                                            \
+    "add.u32 " CO ", " CO ", 8;\n"                                            \
+    "setp.lt.u32 pq, " CO ", %12;\n"                                          \
+    "@pq bra FW_BACK" SFX ";\n"                                               \
+    "FW_LAST" SFX ":\n"                                                       \
+    FU_COMMIT(CI, CO)                                                         \
+    "mov.u32 %8, " CI ";\n"                                                   \
+    "mov.u32 %9, ex;\n"                                                       \
+    FIN                                                                       \
+    "mov.u32 %10, 0;\n"                                                       \
+    "bra FW_DONE;\n"
+    asm volatile(
+        "{\n"
+        ".reg .pred pl, px, p0, p1, pq, po;\n"
+        ".reg .u32 D, s, v, ix, ex, ey, t, u, a, z, l, m, auxb;\n"
+        "mov.u32 z, 0;\n"
+        "FW_TOP:\n"
+        FU_WSTEP("%0", "D", "1")
+        FU_WSTEP("D", "%0", "2")
+        "and.b32 t, %0, 0x8000;\n"
+        "setp.eq.u32 po, t, 0;\n"
+        "@po bra FW_TOP;\n"
+        "mov.u32 %10, 1;\n"
+        "mov.u32 %8, %0;\n"
+        "mov.u32 %9, 0;\n"
+        "bra FW_DONE;\n"
+        FU_WCHECK("%0", "D", "1", "mov.u32 %0, D;\n")
+        FU_WCHECK("D", "%0", "2", "")
+        "FW_DONE:\n"
+        "}\n"
+        : "+r"(C), "+r"(r.hi), "+r"(r.lo), "+r"(r.nx), "+r"(r.wa), "+r"(acc), "+r"(sp), "+r"(badc),
+          "=&r"(Cb), "=&r"(exl), "=&r"(ovf)
+        : "r"(wlut_a), "r"(Cend), "n"(LUTN * 8), "n"(offsetof(DecAux, symbase)), "n"(offsetof(DecAux, sorted))
+        : "memory");
+#undef FU_WSTEP
+#undef FU_WCHECK
+#undef FU_COMMIT
+}
+
+// The walks stop at the first lookup that ENDS at or beyond the limit; that lookup may hold several symbols,
+// some of which begin at or after the limit (they belong to the next subsequence).  Takes them back:
+// returns the walk's counter with the position of the first codeword boundary >= limit and only the symbols
+// that begin before it.  Cb / exl = counter before and symbols of the last lookup, lim = position field of the limit.
+__device__ __forceinline__ uint32_t fu_settle(uint32_t C, uint32_t Cb, uint32_t exl, uint32_t lim, uint32_t aux_a) {
+    const uint32_t n = ((C - Cb) & 0xFFFFu) >> 3;
+    if (n > 1 && (C >> 16) > lim) {
+        uint32_t q = Cb >> 16, j = 0;
+        do {
+            q += lds8(aux_a + (uint32_t)offsetof(DecAux, len) + ((exl >> (8 * j)) & 0xFFu));
+            ++j;
+        } while (q < lim && j < n);
+        C = (q << 16) | ((Cb & 0xFFFFu) + 8 * j);
+    }
+    return C;
+}
+
+// exactly one codeword at the 32 stream bits v (slow paths): returns its length, the symbol in sym
+__device__ __forceinline__ uint32_t fu_one(const DecAux& A, uint32_t wlut_a, uint32_t v, uint32_t& sym, bool& bad) {
+    const uint2 e = lds64(wlut_a + ((v >> 20) << 3));
+    if ((int32_t)e.y >= 0) { sym = e.x & 0xFFu; return A.len[sym]; }
+    const uint32_t l = long_len(A, v, LUTB + 1, (uint32_t)A.maxlen);
+    if (!l) { bad = true; sym = 0; return 1; }
+    sym = A.sorted[A.symbase[l] + (int32_t)(v >> (32 - l))];
+    return l;
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += x;
+    }
+    return inc - v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+struct FuArgs {
+    const uint8_t* comp; uint64_t comp_bytes;
+    const uint64_t* comp_off; const uint32_t* comp_size; const uint32_t* orig_size;
+    uint32_t K; FuPlan P; const uint8_t* tables; uint64_t* rec;
+    uint8_t* out; uint64_t out_cap; int* status;
+    uint32_t* dbg;          // developer dump (HZ_FU_DUMP): entry | exit << 8 | count << 16 per subsequence
+};
+
+// chunk for this CTA: a fresh one from the ticket, else (few large chunks) one that still has units left
+__device__ uint32_t fu_pick_chunk(const FuArgs& a, FuShared& S) {
+    const uint32_t K = a.K;
+    if (threadIdx.x == 0) {
+        uint32_t k = FU_NONE;
+        for (;;) {
+            const uint32_t t = atomicAdd(&a.P.ctl[0], 1u);
+            if (t >= K) break;
+            if (a.P.nunit[t]) { k = t; break; }
+        }
+        S.s_k = k; S.s_pick = FU_NONE;
+    }
+    __syncthreads();
+    if (S.s_k != FU_NONE) return S.s_k;
+    if (K > 2048) return FU_NONE;                         // thousands of chunks balance by themselves
+    // helping: the first chunk (from a start that spreads the CTAs) whose unit counter has not run out
+    const uint32_t start = (uint32_t)(((uint64_t)blockIdx.x * K) / gridDim.x);
+    for (uint32_t i0 = 0; i0 < K; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        if (i < K) {
+            const uint32_t k = (start + i) % K;
+            const uint32_t nu = a.P.nunit[k];
+            if (nu && *reinterpret_cast<volatile uint32_t*>(a.P.unit_ctr + k) < nu) atomicMin(&S.s_pick, i);
+        }
+        __syncthreads();
+        if (S.s_pick != FU_NONE) break;
+    }
+    __syncthreads();
+    const uint32_t p = S.s_pick;
+    return p == FU_NONE ? FU_NONE : (start + p) % K;
+}
+
+__global__ void __launch_bounds__(FU_THREADS, 1)
+dec_fused_kernel(const FuArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FuShared& S = *reinterpret_cast<FuShared*>(smem_raw);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t stage_a = pin_reg(smem_u32(smem_raw + FU_SHARED_BYTES + (size_t)wid * FU_WARP_BYTES));
+    const uint32_t rows_a = stage_a + FU_STAGE_BYTES;
+    const uint32_t bar_a = smem_u32(&S.bar[wid]);
+    const uint32_t wlut_a = pin_reg(smem_u32(S.wlut)), aux_a = pin_reg(smem_u32(S.aux));
+    const DecAux& A = *reinterpret_cast<const DecAux*>(S.aux);
+    if (lane == 0) {
+        mbar_init(&S.bar[wid], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t phase = 0;                                   // parity of this warp's mbarrier
+    bool out_pending = false;                             // a bulk copy out of this warp's rows may still be reading them
+    __syncthreads();
+
+    for (;;) {
+        const uint32_t k = fu_pick_chunk(a, S);
+        if (k == FU_NONE) break;
+        {
+            const uint8_t* tb = a.tables + (size_t)k * FU_TABLE_BYTES;
+            copy_g2s16(S.wlut, tb, LUTN * 8);
+            copy_g2s16(S.aux, tb + LUTN * 8, 1024);
+        }
+        __syncthreads();
+        const uint32_t osize = a.orig_size[k];
+        const uint64_t ooff = a.P.orig_off[k];
+        const uint32_t nunit = a.P.nunit[k];
+        int reject = 0;
+        if (A.bad) reject = HZ_ERR_BAD_LENGTHS;
+        else if (ooff + osize > a.out_cap) reject = HZ_ERR_OUT_TOO_SMALL;
+        if (reject) {
+            if (threadIdx.x == 0) { hz_set_status(a.status, reject); atomicMax(a.P.unit_ctr + k, nunit); }
+            __syncthreads();
+            continue;
+        }
+        const uint64_t coff = a.comp_off[k];
+        const uint32_t csize = a.comp_size[k];
+        const uint32_t nsub = a.P.nsub[k];
+        const uint32_t Sw = a.P.geom[k] & 0xFF, lead = a.P.geom[k] >> 8;
+        const uint32_t sub_bits = Sw * 32;
+        const uint32_t U = (uint32_t)A.uniform;
+        uint64_t* R = a.rec + a.P.unit_base[k];
+        const uint64_t gout = reinterpret_cast<uint64_t>(a.out) + ooff;
+
+        // ---- warp loop over the chunk's units -------------------------------------------------
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(a.P.unit_ctr + k, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
+        while (u < nunit) {
+            const UnitGeom g = fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw);
+            fu_mbar_wait(bar_a, phase); phase ^= 1;
+            fu_stage_prepare(stage_a, g, lane);
+            if (out_pending) {                            // the previous unit's window must have left the rows
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                out_pending = false;
+            }
+            __syncwarp();
+
+            const uint32_t i = u * 32 + lane;             // subsequence index within the chunk
+            const bool active = i < nsub;
+            const uint32_t nominal = g.bit0 + lane * sub_bits, end = nominal + sub_bits;     // stage-relative bits
+            uint32_t entry = 0;
+            if (active && i != 0) {
+                if (U) {                                  // equal-length code: boundaries are the multiples of U
+                    const uint64_t nomc = (uint64_t)i * sub_bits;
+                    entry = (uint32_t)((U - nomc % U) % U);
+                } else {                                  // guess: walk the lead-in, take the first boundary inside
+                    const uint32_t p0 = nominal - lead * 32, org = p0 & ~31u;
+                    Reader r; fu_seek(r, stage_a, p0);
+                    uint32_t C = ((p0 - org) << 16) | FU_OUT_BIAS, Cb, exl;
+                    fu_skim(C, r, (nominal - org) << 16, wlut_a, Cb, exl);
+                    C = fu_settle(C, Cb, exl, nominal - org, aux_a);
+                    entry = (C >> 16) - (nominal - org);
+                }
+            }
+            // decode (and re-decode where a guess was wrong) until the chain of the unit is consistent and
+            // anchored in the chunk's earlier units
+            bool need = active;
+            uint32_t count = 0, exitv = 0, badc = 0xFFFFFFFFu, prefix = 0;
+            bool published = false;
+            for (;;) {
+                if (need) {
+                    const uint32_t p0 = nominal + entry, org = p0 & ~31u;
+                    Reader r; fu_seek(r, stage_a, p0);
+                    uint32_t C = ((p0 - org) << 16) | FU_OUT_BIAS, Cb, exl, ovf, acc = 0, sp = rows_a + lane * 4;
+                    const uint32_t Cend = (end - org) << 16;
+                    badc = 0xFFFFFFFFu;
+                    fu_walk(C, r, Cend, wlut_a, acc, sp, Cb, exl, badc, ovf);
+                    if (ovf) fu_skim(C, r, Cend, wlut_a, Cb, exl);
+                    else sts32(sp, acc);                  // bytes still in the accumulator (the row has two guard words)
+                    C = fu_settle(C, Cb, exl, end - org, aux_a);
+                    count = ((C & 0xFFFFu) - FU_OUT_BIAS) >> 3;
+                    exitv = (C >> 16) - (end - org);
+                }
+                const uint32_t want = __shfl_up_sync(0xffffffffu, exitv, 1);
+                need = active && lane > 0 && want != entry;
+                if (need) entry = want;
+                if (__any_sync(0xffffffffu, need)) { published = false; continue; }
+                // the last ACTIVE lane's exit is the unit's exit
+                const uint32_t nact = min(32u, nsub - u * 32);
+                const uint32_t uexit = __shfl_sync(0xffffffffu, exitv, nact - 1);
+                const uint32_t uentry = __shfl_sync(0xffffffffu, entry, 0);
+                const uint32_t ucount = warp_sum(active ? count : 0);
+                if (u == 0) {
+                    if (lane == 0) st_rec(R, fu_pack(FU_FINAL, 0, uexit, ucount, ucount));
+                    prefix = 0;
+                    break;
+                }
+                if (!published) {
+                    if (lane == 0) st_rec(R + u, fu_pack(FU_SPEC, uentry, uexit, ucount, 0));
+                    published = true;
+                }
+                uint32_t true_entry = 0;
+                if (fu_lookback(R, u, uentry, lane, prefix, true_entry)) {
+                    if (lane == 0) st_rec(R + u, fu_pack(FU_FINAL, uentry, uexit, ucount, prefix + ucount));
+                    break;
+                }
+                need = lane == 0;                         // the guess of the first subsequence was wrong: re-walk from the truth
+                if (need) entry = true_entry;
+                published = false;
+            }
+            __syncwarp();
+            if (a.dbg) a.dbg[(size_t)(a.P.unit_base[k] + u) * 32 + lane] = entry | (exitv << 8) | (count << 16);
+            // the stage is free: fetch the next unit while this one is written out
+            const uint32_t u_cur = u;
+            if (lane == 0) u = atomicAdd(a.P.unit_ctr + k, 1u);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            // ---- output ------------------------------------------------------------------------
+            if (!active) count = 0;
+            const uint32_t rel = warp_excl_scan(count, lane);
+            const uint32_t obase = prefix + rel;                           // chunk-relative index of the lane's first symbol
+            const uint32_t cw = obase >= osize ? 0u : min(count, osize - obase);   // symbols of this lane that exist
+            const bool over = __any_sync(0xffffffffu, count > FU_CAP_SYMS);
+            if (badc != 0xFFFFFFFFu && obase + ((badc - FU_OUT_BIAS) >> 3) < osize) hz_set_status(a.status, HZ_ERR_DECODE);
+            if (over) {
+                // a row overflowed (far more symbols than the chunk's average in one subsequence): every lane
+                // decodes its subsequence again, one codeword at a time, straight to global memory
+                if (cw) {
+                    uint32_t p = nominal + entry, idx = obase;
+                    const uint32_t stop = obase + cw;
+                    bool bad = false;
+                    while (idx < stop) {
+                        const uint32_t wa = stage_a + ((p >> 5) << 2);
+                        const uint32_t v = __funnelshift_l(lds32(wa + 4), lds32(wa), p);
+                        uint32_t sym;
+                        p += fu_one(A, wlut_a, v, sym, bad);
+                        *reinterpret_cast<uint8_t*>(gout + idx) = (uint8_t)sym;
+                        ++idx;
+                    }
+                    if (bad) hz_set_status(a.status, HZ_ERR_DECODE);
+                }
+                __syncwarp();
+                if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
+            } else {
+                if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
+                const uint32_t T = warp_sum(cw);
+                if (T) {
+                    const uint32_t first = __shfl_sync(0xffffffffu, obase, 0);
+                    const uint64_t g0 = gout + first;                     // global address of the window's first symbol
+                    const uint32_t shift = (uint32_t)(g0 & 15);
+                    const uint32_t d = shift + (obase - first);           // window byte of the lane's first symbol
+                    // all rows to registers (the window overlays the rows)
+                    uint32_t rw[FU_ROW_WORDS - 1];
+#pragma unroll
+                    for (int j = 0; j < FU_ROW_WORDS - 1; ++j) rw[j] = lds32(rows_a + (j * 32 + lane) * 4);
+                    const uint32_t hn = min(cw, (4u - (d & 3)) & 3);      // bytes before the lane's first whole window word
+                    const uint32_t nfull = (cw - hn) >> 2, tn = (cw - hn) & 3;
+                    uint32_t tail = 0;                                    // the last tn bytes (row bytes hn + 4 nfull ...)
+                    {
+                        const uint32_t tb = hn + 4 * nfull;
+                        for (uint32_t j = 0; j < tn; ++j) {
+                            const uint32_t b = tb + j;
+                            tail |= lds8(rows_a + ((b >> 2) * 32 + lane) * 4 + (b & 3)) << (8 * j);
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t bs = (d & 3) * 8;
+                    const uint32_t w0 = rows_a + (d & ~3u);               // window word that holds the first symbol
+                    for (uint32_t j = 0; j < hn; ++j) sts8(w0 + (d & 3) + j, rw[0] >> (8 * j));
+                    const uint32_t jmin = bs ? 1u : 0u;
+                    {
+                        // window word w0 + 4 j = row bytes [4 j - (d & 3), +4)
+                        uint32_t prev = 0;
+#pragma unroll
+                        for (int j = 0; j < FU_ROW_WORDS - 1; ++j) {
+                            const uint32_t val = __funnelshift_l(prev, rw[j], bs);
+                            if ((uint32_t)j >= jmin && (uint32_t)j < jmin + nfull) sts32(w0 + 4 * j, val);
+                            prev = rw[j];
+                        }
+                    }
+                    {
+                        const uint32_t ta = w0 + 4 * (jmin + nfull);
+                        for (uint32_t j = 0; j < tn; ++j) sts8(ta + j, tail >> (8 * j));
+                    }
+                    __syncwarp();
+                    // window bytes [shift, shift + T) -> global [g0, g0 + T): whole 16-byte units by one bulk copy
+                    const uint64_t gw = g0 - shift;                       // global address of window byte 0 (16-byte aligned)
+                    const uint32_t b0 = shift, b1 = shift + T;
+                    const uint32_t f0 = (b0 + 15) >> 4, f1 = b1 >> 4;
+                    if (f1 > f0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                         ::"l"(gw + (uint64_t)f0 * 16), "r"(rows_a + f0 * 16), "r"((f1 - f0) * 16) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        out_pending = true;
+                        // ragged ends, one byte per lane (lanes 0-15: first unit, lanes 16-31: last unit)
+                        const uint32_t bb = lane < 16 ? (b0 & ~15u) + lane : (b1 & ~15u) + (lane - 16);
+                        const bool edge = lane < 16 ? (b0 & 15) != 0 : (b1 & 15) != 0;
+                        if (edge && bb >= b0 && bb < b1) *reinterpret_cast<uint8_t*>(gw + bb) = (uint8_t)lds8(rows_a + bb);
+                    } else {
+                        for (uint32_t bb = b0 + lane; bb < b1; bb += 32) *reinterpret_cast<uint8_t*>(gw + bb) = (uint8_t)lds8(rows_a + bb);
+                    }
+                }
+            }
+            // the chunk's last unit: when the stream holds fewer symbols than orig_size the decoder goes on reading
+            // zero bits (TableBasedHuffmanDecoder.java:204-208), i.e. the all-zero codeword's symbol repeats
+            if (u_cur == nunit - 1) {
+                const uint32_t have = prefix + __shfl_sync(0xffffffffu, rel + count, 31);
+                if (have < osize) {
+                    const uint8_t s0 = A.sorted[0];
+                    for (uint64_t b = (uint64_t)have + lane; b < osize; b += 32) *reinterpret_cast<uint8_t*>(gout + b) = s0;
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();                                  // every warp is done with this chunk's table
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the copies
+}
+
+// ---------------------------------------------------------------------------------------------
+// launcher.  `ident` = per-chunk identity flags (hz_decode.cu); identity chunks are copied by the caller with the
+// slice prefix sums this plan provides.
+// ---------------------------------------------------------------------------------------------
+int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const uint64_t* d_comp_off,
+                     const uint32_t* d_comp_size, const uint32_t* d_orig_size, const uint64_t* d_orig_off,
+                     const uint8_t* d_len, uint32_t K, uint8_t* d_out, uint64_t out_cap, const uint8_t* d_ident,
+                     const uint64_t** plan_orig_off, const uint32_t** plan_islice) {
+    HZ_TRY(hz_reserve(ctx, &ctx->dec_meta, ((size_t)K + 1) * (6 * sizeof(uint32_t) + sizeof(uint64_t)) + 256));
+    FuPlan P;
+    uint8_t* m = (uint8_t*)ctx->dec_meta.p;
+    P.orig_off = (uint64_t*)m; m += ((size_t)K + 1) * sizeof(uint64_t);
+    P.nsub = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
+    P.nunit = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
+    P.unit_base = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
+    P.geom = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
+    P.unit_ctr = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
+    P.islice = (uint32_t*)m; m += ((size_t)K + 1) * sizeof(uint32_t);
+    P.ctl = (uint32_t*)m;
+    // every chunk has at most ceil(comp_size / (4 * FU_SUB_MIN * 32)) + 1 units
+    const uint64_t max_units = comp_bytes / (128ull * FU_SUB_MIN) + 2ull * K + 2;
+    if (max_units > 0xFFFFFFFFull) return hz_fail(ctx, HZ_ERR_ARG, "decode: stream too large for one call");
+    HZ_TRY(hz_reserve(ctx, &ctx->dec_rec, max_units * sizeof(uint64_t)));
+    HZ_TRY(hz_reserve(ctx, &ctx->dec_tables, (size_t)K * FU_TABLE_BYTES));
+    if (!ctx->attr_decode_fused) {
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
+        ctx->attr_decode_fused = true;
+    }
+    HZ_LAUNCH(ctx, "dec_plan", fu_plan_kernel, 1, 1024, 0, d_comp_off, d_comp_size, d_orig_size, d_orig_off, comp_bytes, K, P,
+              d_ident, ctx->d_status);
+    HZ_LAUNCH(ctx, "dec_zero", fu_zero_kernel, 2 * ctx->sm_count, 256, 0, (uint64_t*)ctx->dec_rec.p, P.unit_base, K);
+    HZ_LAUNCH(ctx, "dec_tables", fu_tables_kernel, K, DT, 0, d_len, P, (uint8_t*)ctx->dec_tables.p);
+    FuArgs a;
+    a.comp = d_comp; a.comp_bytes = comp_bytes; a.comp_off = d_comp_off; a.comp_size = d_comp_size; a.orig_size = d_orig_size;
+    a.K = K; a.P = P; a.tables = (const uint8_t*)ctx->dec_tables.p; a.rec = (uint64_t*)ctx->dec_rec.p;
+    a.out = d_out; a.out_cap = out_cap; a.status = ctx->d_status; a.dbg = nullptr;
+    const char* dump = getenv("HZ_FU_DUMP");               // developer knob: per-subsequence records to a file
+    if (dump) { cudaMallocManaged(&a.dbg, max_units * 32 * sizeof(uint32_t)); cudaMemset(a.dbg, 0xFF, max_units * 32 * sizeof(uint32_t)); }
+    static const int grid_knob = [] { const char* ev = getenv("HZ_FU_GRID"); return ev ? atoi(ev) : 0; }();   // developer knob
+    const unsigned grid = grid_knob > 0 ? (unsigned)grid_knob : (unsigned)ctx->sm_count;
+    HZ_LAUNCH(ctx, "dec_fused", dec_fused_kernel, grid, FU_THREADS, FU_SMEM_BYTES, a);
+    if (dump) {
+        cudaStreamSynchronize(ctx->stream);
+        if (FILE* f = fopen(dump, "wb")) { fwrite(a.dbg, sizeof(uint32_t), max_units * 32, f); fclose(f); }
+        cudaFree(a.dbg);
+    }
+    *plan_orig_off = P.orig_off; *plan_islice = P.islice;
+    return HZ_OK;
+}
