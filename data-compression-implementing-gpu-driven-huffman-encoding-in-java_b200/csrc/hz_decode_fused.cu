@@ -27,21 +27,24 @@
 
 #define FU_WARPS 24
 #define FU_THREADS (FU_WARPS * 32)
-#define FU_SUB_MIN 4
+#define FU_SUB_MIN 3
 #define FU_SUB_MAX 17
 #define FU_ROW_WORDS 46                            // 44 words of symbols + 2 guard words (overflow is tested once per two lookups)
 #define FU_CAP_SYMS 176
 #define FU_CAP_BITS (FU_CAP_SYMS * 8)              // multiple of 32: the packed counter's low five bits stay the byte lane
 #define FU_OUT_BIAS (0x8000u - FU_CAP_BITS)        // bit 15 of the output field <=> the row is full
-#define FU_STAGE_BYTES 2240                        // 15 alignment + 16 lead-in + 17 * 128 + 32 look-ahead, rounded to 16
+#define FU_LEAD_MAX 8
+#define FU_STAGE_BYTES 2256                        // 15 alignment + 32 lead-in + 17 * 128 + 32 look-ahead, rounded to 16
 #define FU_ROWS_BYTES (32 * FU_ROW_WORDS * 4)
 #define FU_WARP_BYTES (FU_STAGE_BYTES + FU_ROWS_BYTES)
 #define FU_TABLE_BYTES (LUTN * 8 + 1024)           // wlut + DecAux
 #define FU_NONE 0xFFFFFFFFu
+#define FU_RING 64                                 // > look-back window (32) + units in flight in one CTA (24)
 
 struct FuShared {
     __align__(16) uint2 wlut[LUTN];
     __align__(16) uint8_t aux[1024];
+    __align__(16) uint4 ring[FU_RING];       // look-back records of the units THIS CTA decoded: {record, unit + 1}
     __align__(8) uint64_t bar[FU_WARPS];
     uint32_t s_k, s_pick;
 };
@@ -66,14 +69,19 @@ struct FuPlan {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fu_chunk_geom(uint32_t csize, uint32_t osize, bool ident, bool ok,
                                               uint32_t& S, uint32_t& lead, uint32_t& ns) {
-    S = FU_SUB_MAX; lead = 4; ns = 0;
+    S = FU_SUB_MAX; lead = 3; ns = 0;
     if (!ok || ident || osize == 0) return;
-    // ~128 symbols per subsequence: S = 128 * (8 csize / osize) / 32 words
-    uint64_t s = ((uint64_t)csize * 32) / osize;
-    S = (uint32_t)(s < FU_SUB_MIN ? FU_SUB_MIN : (s > FU_SUB_MAX ? FU_SUB_MAX : s));
-    // lead-in of ~28 codewords before a subsequence for the self-synchronisation guess
-    uint64_t l = ((uint64_t)csize * 7 + osize - 1) / osize;
-    lead = (uint32_t)(l < 2 ? 2 : (l > 4 ? 4 : l));
+    // ~136 symbols per subsequence at most (a row holds 176): S <= 136 * (8 csize / osize) / 32 words, and ODD, so that
+    // the 32 lanes' stream words (stride S) fall into 32 different shared-memory banks
+    uint64_t s = ((uint64_t)csize * 34) / osize;
+    s = s < FU_SUB_MIN ? FU_SUB_MIN : (s > FU_SUB_MAX ? FU_SUB_MAX : s);
+    S = (uint32_t)((s - 1) | 1);
+    // lead-in before a subsequence for the self-synchronisation guess: the nearer a code is to equal lengths, the
+    // more codewords it takes to fall into step (measured with tests/fused_model.py on Zipf streams: a wrong guess
+    // per 10^3..10^4 subsequences with 1 word at <= 2 bits/symbol, 3 words at 4, 6 at 6, 8 at 7)
+    int64_t l = (int64_t)(((uint64_t)csize * 12 + osize / 2) / osize) - 3;
+    lead = (uint32_t)(l < 1 ? 1 : (l > FU_LEAD_MAX ? FU_LEAD_MAX : l));
+    if (lead > S) lead = S;
     const uint64_t bits = (uint64_t)csize * 8, sb = (uint64_t)S * 32;
     ns = (uint32_t)((bits + sb - 1) / sb);
     if (ns == 0) ns = 1;
@@ -159,17 +167,57 @@ __device__ __forceinline__ void st_rec(uint64_t* p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += x;
+    }
+    return inc - v;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// A record lives in global memory (every CTA that works on the chunk sees it) and, for the units this CTA decoded
+// itself, in a shared-memory ring that spares the look-back the global round trips (a CTA that has a chunk to
+// itself never leaves shared memory).  Ring entries are written and read as ONE 128-bit access.
+__device__ __forceinline__ void fu_put(uint64_t* R, uint32_t ring_a, uint32_t u, uint64_t rec) {
+    sts128(ring_a + (u & (FU_RING - 1)) * 16, make_uint4((uint32_t)rec, (uint32_t)(rec >> 32), u + 1, 0u));
+    st_rec(R + u, rec);
+}
+__device__ __forceinline__ uint64_t fu_get(const uint64_t* R, uint32_t ring_a, int q) {
+    const uint4 e = lds128(ring_a + ((uint32_t)q & (FU_RING - 1)) * 16);
+    if (e.z == (uint32_t)q + 1) return (uint64_t)e.x | ((uint64_t)e.y << 32);
+    return ld_rec(R + q);
+}
+__device__ __forceinline__ void fu_wait_rec(const uint64_t* R, uint32_t ring_a, int q, uint32_t min_state) {
+    uint32_t ns = 32;
+    while (((uint32_t)fu_get(R, ring_a, q) & 3u) < min_state) { __nanosleep(ns); if (ns < 256) ns += ns; }
+}
+
 // Decoupled look-back of unit u (u >= 1) over the chunk's records R[0..u).  Returns true with the number of
 // symbols before the unit in `prefix`, or false with the true entry of the unit's first subsequence in
 // `true_entry` when the unit has to re-walk (its guess differs from the FINAL exit of unit u - 1).
-__device__ bool fu_lookback(const uint64_t* __restrict__ R, uint32_t u, uint32_t my_entry0, uint32_t lane,
+// Waiting (for a record to be published, or for the owner of a broken link to finalise) polls ONE record.
+__device__ bool fu_lookback(const uint64_t* __restrict__ R, uint32_t ring_a, uint32_t u, uint32_t my_entry0, uint32_t lane,
                             uint32_t& prefix, uint32_t& true_entry) {
     uint32_t acc = 0, expect = my_entry0;
     int base = (int)u - 1;
-    uint32_t spins = 0;
+    fu_wait_rec(R, ring_a, base, FU_SPEC);
     for (;;) {
         const int j = base - (int)lane;
-        const uint64_t rec = j >= 0 ? ld_rec(R + j) : 0ull;
+        const uint64_t rec = j >= 0 ? fu_get(R, ring_a, j) : 0ull;
         const uint32_t w = (uint32_t)rec;
         const uint32_t st = w & 3, en = (w >> 2) & 63, ex = (w >> 8) & 63, cnt = (w >> 14) & 0x3FFFF;
         const uint32_t en_up = __shfl_up_sync(0xffffffffu, en, 1);
@@ -179,28 +227,26 @@ __device__ bool fu_lookback(const uint64_t* __restrict__ R, uint32_t u, uint32_t
         const uint32_t mb = __ballot_sync(0xffffffffu, st != FU_EMPTY && ex != E);
         const uint32_t any = me | mf | mb;
         if (!any) {                                               // 32 consistent speculative records: keep going back
-            uint32_t c = cnt;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-            acc += c; expect = __shfl_sync(0xffffffffu, en, 31); base -= 32;
+            acc += warp_sum(cnt); expect = __shfl_sync(0xffffffffu, en, 31); base -= 32;
             continue;
         }
         const uint32_t d = __ffs(any) - 1;                        // first decisive record
         if ((mb >> d) & 1) {
-            if (d == 0 && base == (int)u - 1 && (mf & 1)) {       // my own link, against a FINAL record
-                true_entry = __shfl_sync(0xffffffffu, ex, 0);
-                return false;
+            // the link between unit base - d and its successor is broken: the successor re-walks once its
+            // predecessor is FINAL.  Mine: do that; somebody else's: wait until that unit has finalised.
+            if (d == 0 && base == (int)u - 1) {
+                if (mf & 1) { true_entry = __shfl_sync(0xffffffffu, ex, 0); return false; }
+                fu_wait_rec(R, ring_a, base, FU_FINAL);
+            } else {
+                fu_wait_rec(R, ring_a, base - (int)d + 1, FU_FINAL);
             }
         } else if ((mf >> d) & 1) {
-            uint32_t c = lane < d ? cnt : 0;
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
-            prefix = __shfl_sync(0xffffffffu, (uint32_t)(rec >> 32), d) + acc + c;
+            prefix = __shfl_sync(0xffffffffu, (uint32_t)(rec >> 32), d) + acc + warp_sum(lane < d ? cnt : 0u);
             return true;
+        } else {
+            fu_wait_rec(R, ring_a, base - (int)d, FU_SPEC);        // not published yet
         }
-        // an unpublished record, or a broken link whose owner has not finalised yet: start over
-        if (++spins > 8) __nanosleep(spins > 64 ? 400 : 100);
-        acc = 0; expect = my_entry0; base = (int)u - 1;
+        acc = 0; expect = my_entry0; base = (int)u - 1;           // start over
     }
 }
 
@@ -212,14 +258,14 @@ struct UnitGeom {
     int32_t need;           // stage bytes the unit uses (multiple of 16)
     int32_t vlo, vhi;       // stage-relative byte range that belongs to the chunk
     int32_t tlo, thi;       // stage-relative byte range delivered by the bulk copy
-    uint32_t bit0;          // stage-relative bit index of the unit's first bit (multiple of 8, >= 128)
+    uint32_t bit0;          // stage-relative bit index of the unit's first bit (multiple of 8, >= 256)
 };
 __device__ __forceinline__ UnitGeom fu_geom(const uint8_t* comp, uint64_t comp_bytes, uint64_t chunk_off,
                                             uint32_t chunk_size, uint32_t u, uint32_t S) {
     UnitGeom g;
     const uint64_t cb = reinterpret_cast<uint64_t>(comp) + chunk_off;
     const uint64_t us = cb + (uint64_t)u * (128u * S);
-    g.a0 = (us - 16) & ~(uint64_t)15;
+    g.a0 = (us - 4 * FU_LEAD_MAX) & ~(uint64_t)15;
     g.bit0 = (uint32_t)(us - g.a0) * 8;
     g.need = (int32_t)(((us - g.a0) + 128u * S + 32 + 15) & ~(uint64_t)15);
     int64_t vlo = (int64_t)cb - (int64_t)g.a0, vhi = vlo + chunk_size;
@@ -262,13 +308,6 @@ __device__ __forceinline__ void fu_mbar_wait(uint32_t bar_a, uint32_t parity) {
         "bra FW_LOOP;\n"
         "FW_DONE:\n"
         "}\n" ::"r"(bar_a), "r"(parity) : "memory");
-}
-
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-    uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // After the bulk copy landed: words become big-endian values (stream bit 0 = bit 31 of word 0), bytes outside
@@ -512,29 +551,21 @@ __device__ __forceinline__ uint32_t fu_one(const DecAux& A, uint32_t wlut_a, uin
     return l;
 }
 
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-}
-__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane) {
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += x;
-    }
-    return inc - v;
-}
-
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+// -DFU_TIMING (developer build): per-phase clock64 totals over all warps, printed by the launcher
+#ifdef FU_TIMING
+#define FU_T(i) do { const long long now__ = clock64(); tim__[i] += now__ - last__; last__ = now__; } while (0)
+#else
+#define FU_T(i) do { } while (0)
+#endif
 struct FuArgs {
     const uint8_t* comp; uint64_t comp_bytes;
     const uint64_t* comp_off; const uint32_t* comp_size; const uint32_t* orig_size;
     uint32_t K; FuPlan P; const uint8_t* tables; uint64_t* rec;
     uint8_t* out; uint64_t out_cap; int* status;
+    unsigned long long* tim;   // -DFU_TIMING
     uint32_t* dbg;          // developer dump (HZ_FU_DUMP): entry | exit << 8 | count << 16 per subsequence
 };
 
@@ -579,11 +610,15 @@ dec_fused_kernel(const FuArgs a) {
     const uint32_t rows_a = stage_a + FU_STAGE_BYTES;
     const uint32_t bar_a = smem_u32(&S.bar[wid]);
     const uint32_t wlut_a = pin_reg(smem_u32(S.wlut)), aux_a = pin_reg(smem_u32(S.aux));
+    const uint32_t ring_a = smem_u32(S.ring);
     const DecAux& A = *reinterpret_cast<const DecAux*>(S.aux);
     if (lane == 0) {
         mbar_init(&S.bar[wid], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+#ifdef FU_TIMING
+    long long tim__[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last__ = clock64();
+#endif
     uint32_t phase = 0;                                   // parity of this warp's mbarrier
     bool out_pending = false;                             // a bulk copy out of this warp's rows may still be reading them
     __syncthreads();
@@ -595,6 +630,7 @@ dec_fused_kernel(const FuArgs a) {
             const uint8_t* tb = a.tables + (size_t)k * FU_TABLE_BYTES;
             copy_g2s16(S.wlut, tb, LUTN * 8);
             copy_g2s16(S.aux, tb + LUTN * 8, 1024);
+            if (threadIdx.x < FU_RING) S.ring[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();
         const uint32_t osize = a.orig_size[k];
@@ -624,7 +660,9 @@ dec_fused_kernel(const FuArgs a) {
         if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
         while (u < nunit) {
             const UnitGeom g = fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw);
+            FU_T(0);
             fu_mbar_wait(bar_a, phase); phase ^= 1;
+            FU_T(1);
             fu_stage_prepare(stage_a, g, lane);
             if (out_pending) {                            // the previous unit's window must have left the rows
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -649,6 +687,7 @@ dec_fused_kernel(const FuArgs a) {
                     entry = (C >> 16) - (nominal - org);
                 }
             }
+            FU_T(2);
             // decode (and re-decode where a guess was wrong) until the chain of the unit is consistent and
             // anchored in the chunk's earlier units
             bool need = active;
@@ -661,7 +700,9 @@ dec_fused_kernel(const FuArgs a) {
                     uint32_t C = ((p0 - org) << 16) | FU_OUT_BIAS, Cb, exl, ovf, acc = 0, sp = rows_a + lane * 4;
                     const uint32_t Cend = (end - org) << 16;
                     badc = 0xFFFFFFFFu;
+                    FU_T(7);
                     fu_walk(C, r, Cend, wlut_a, acc, sp, Cb, exl, badc, ovf);
+                    FU_T(3);
                     if (ovf) fu_skim(C, r, Cend, wlut_a, Cb, exl);
                     else sts32(sp, acc);                  // bytes still in the accumulator (the row has two guard words)
                     C = fu_settle(C, Cb, exl, end - org, aux_a);
@@ -678,17 +719,20 @@ dec_fused_kernel(const FuArgs a) {
                 const uint32_t uentry = __shfl_sync(0xffffffffu, entry, 0);
                 const uint32_t ucount = warp_sum(active ? count : 0);
                 if (u == 0) {
-                    if (lane == 0) st_rec(R, fu_pack(FU_FINAL, 0, uexit, ucount, ucount));
+                    if (lane == 0) fu_put(R, ring_a, 0, fu_pack(FU_FINAL, 0, uexit, ucount, ucount));
                     prefix = 0;
                     break;
                 }
                 if (!published) {
-                    if (lane == 0) st_rec(R + u, fu_pack(FU_SPEC, uentry, uexit, ucount, 0));
+                    if (lane == 0) fu_put(R, ring_a, u, fu_pack(FU_SPEC, uentry, uexit, ucount, 0));
                     published = true;
                 }
                 uint32_t true_entry = 0;
-                if (fu_lookback(R, u, uentry, lane, prefix, true_entry)) {
-                    if (lane == 0) st_rec(R + u, fu_pack(FU_FINAL, uentry, uexit, ucount, prefix + ucount));
+                FU_T(7);
+                const bool lb_ok = fu_lookback(R, ring_a, u, uentry, lane, prefix, true_entry);
+                FU_T(4);
+                if (lb_ok) {
+                    if (lane == 0) fu_put(R, ring_a, u, fu_pack(FU_FINAL, uentry, uexit, ucount, prefix + ucount));
                     break;
                 }
                 need = lane == 0;                         // the guess of the first subsequence was wrong: re-walk from the truth
@@ -698,9 +742,11 @@ dec_fused_kernel(const FuArgs a) {
             __syncwarp();
             if (a.dbg) a.dbg[(size_t)(a.P.unit_base[k] + u) * 32 + lane] = entry | (exitv << 8) | (count << 16);
             // the stage is free: fetch the next unit while this one is written out
+            FU_T(7);
             const uint32_t u_cur = u;
             if (lane == 0) u = atomicAdd(a.P.unit_ctr + k, 1u);
             u = __shfl_sync(0xffffffffu, u, 0);
+            FU_T(5);
             // ---- output ------------------------------------------------------------------------
             if (!active) count = 0;
             const uint32_t rel = warp_excl_scan(count, lane);
@@ -791,6 +837,7 @@ dec_fused_kernel(const FuArgs a) {
                     }
                 }
             }
+            FU_T(6);
             // the chunk's last unit: when the stream holds fewer symbols than orig_size the decoder goes on reading
             // zero bits (TableBasedHuffmanDecoder.java:204-208), i.e. the all-zero codeword's symbol repeats
             if (u_cur == nunit - 1) {
@@ -805,6 +852,10 @@ dec_fused_kernel(const FuArgs a) {
         __syncthreads();                                  // every warp is done with this chunk's table
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the copies
+#ifdef FU_TIMING
+    FU_T(0);
+    if (lane == 0 && a.tim) for (int i = 0; i < 8; ++i) atomicAdd(a.tim + i, (unsigned long long)tim__[i]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -842,12 +893,26 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
     FuArgs a;
     a.comp = d_comp; a.comp_bytes = comp_bytes; a.comp_off = d_comp_off; a.comp_size = d_comp_size; a.orig_size = d_orig_size;
     a.K = K; a.P = P; a.tables = (const uint8_t*)ctx->dec_tables.p; a.rec = (uint64_t*)ctx->dec_rec.p;
-    a.out = d_out; a.out_cap = out_cap; a.status = ctx->d_status; a.dbg = nullptr;
+    a.out = d_out; a.out_cap = out_cap; a.status = ctx->d_status; a.dbg = nullptr; a.tim = nullptr;
+#ifdef FU_TIMING
+    cudaMallocManaged(&a.tim, 8 * sizeof(unsigned long long)); cudaMemset(a.tim, 0, 8 * sizeof(unsigned long long));
+#endif
     const char* dump = getenv("HZ_FU_DUMP");               // developer knob: per-subsequence records to a file
     if (dump) { cudaMallocManaged(&a.dbg, max_units * 32 * sizeof(uint32_t)); cudaMemset(a.dbg, 0xFF, max_units * 32 * sizeof(uint32_t)); }
     static const int grid_knob = [] { const char* ev = getenv("HZ_FU_GRID"); return ev ? atoi(ev) : 0; }();   // developer knob
     const unsigned grid = grid_knob > 0 ? (unsigned)grid_knob : (unsigned)ctx->sm_count;
     HZ_LAUNCH(ctx, "dec_fused", dec_fused_kernel, grid, FU_THREADS, FU_SMEM_BYTES, a);
+#ifdef FU_TIMING
+    cudaStreamSynchronize(ctx->stream);
+    {
+        static const char* nm[8] = {"idle/other", "tma wait", "prepare", "walk", "lookback", "ticket", "output", "skim+glue"};
+        double tot = 0; for (int i = 0; i < 8; ++i) tot += (double)a.tim[i];
+        fprintf(stderr, "FU_TIMING");
+        for (int i = 0; i < 8; ++i) fprintf(stderr, "  %s %.1f%%", nm[i], 100.0 * (double)a.tim[i] / tot);
+        fprintf(stderr, "\n");
+        cudaFree(a.tim);
+    }
+#endif
     if (dump) {
         cudaStreamSynchronize(ctx->stream);
         if (FILE* f = fopen(dump, "wb")) { fwrite(a.dbg, sizeof(uint32_t), max_units * 32, f); fclose(f); }
