@@ -25,7 +25,9 @@
 #include <cstdio>
 #include "hz_decode_tables.cuh"
 
+#ifndef FU_WARPS
 #define FU_WARPS 24
+#endif
 #define FU_THREADS (FU_WARPS * 32)
 #define FU_SUB_MIN 3
 #define FU_SUB_MAX 17
@@ -67,7 +69,7 @@ struct FuPlan {
 // ---------------------------------------------------------------------------------------------
 // plan: per-chunk geometry and prefix sums (1 CTA)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fu_chunk_geom(uint32_t csize, uint32_t osize, bool ident, bool ok,
+__device__ __forceinline__ void fu_chunk_geom(uint32_t csize, uint32_t osize, bool ident, bool ok, uint32_t lead_knob,
                                               uint32_t& S, uint32_t& lead, uint32_t& ns) {
     S = FU_SUB_MAX; lead = 3; ns = 0;
     if (!ok || ident || osize == 0) return;
@@ -78,8 +80,10 @@ __device__ __forceinline__ void fu_chunk_geom(uint32_t csize, uint32_t osize, bo
     S = (uint32_t)((s - 1) | 1);
     // lead-in before a subsequence for the self-synchronisation guess: the nearer a code is to equal lengths, the
     // more codewords it takes to fall into step (measured with tests/fused_model.py on Zipf streams: a wrong guess
-    // per 10^3..10^4 subsequences with 1 word at <= 2 bits/symbol, 3 words at 4, 6 at 6, 8 at 7)
-    int64_t l = (int64_t)(((uint64_t)csize * 12 + osize / 2) / osize) - 3;
+    // per 10^3..10^4 subsequences with 1 word at <= 2 bits/symbol, 2 words at 3..4, 6 at 6, 8 at 7)
+    // x = 1.5 * bits per symbol (x4 fixed point): one word below 2.5 bits/symbol, two below 4.5, then 1.5 b - 3
+    const uint64_t x4 = ((uint64_t)csize * 48) / osize;
+    const int64_t l = lead_knob ? (int64_t)lead_knob : (x4 < 15 ? 1 : (x4 < 21 ? 2 : (int64_t)((x4 + 2) / 4) - 3));
     lead = (uint32_t)(l < 1 ? 1 : (l > FU_LEAD_MAX ? FU_LEAD_MAX : l));
     if (lead > S) lead = S;
     const uint64_t bits = (uint64_t)csize * 8, sb = (uint64_t)S * 32;
@@ -90,7 +94,7 @@ __device__ __forceinline__ void fu_chunk_geom(uint32_t csize, uint32_t osize, bo
 __global__ void __launch_bounds__(1024)
 fu_plan_kernel(const uint64_t* __restrict__ comp_off, const uint32_t* __restrict__ comp_size,
                const uint32_t* __restrict__ orig_size, const uint64_t* __restrict__ orig_off_in, uint64_t comp_bytes,
-               uint32_t K, FuPlan P, const uint8_t* __restrict__ ident, int* status) {
+               uint32_t K, FuPlan P, const uint8_t* __restrict__ ident, uint32_t lead_knob, int* status) {
     __shared__ uint64_t part[3][1024];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (K + 1023) / 1024;
@@ -101,7 +105,7 @@ fu_plan_kernel(const uint64_t* __restrict__ comp_off, const uint32_t* __restrict
         const bool ok = comp_off[i] <= comp_bytes && comp_size[i] <= comp_bytes - comp_off[i];
         if (!ok) hz_set_status(status, HZ_ERR_ARG);
         uint32_t S, lead, ns;
-        fu_chunk_geom(comp_size[i], orig_size[i], ident[i] != 0, ok, S, lead, ns);
+        fu_chunk_geom(comp_size[i], orig_size[i], ident[i] != 0, ok, lead_knob, S, lead, ns);
         s0 += (ns + 31) / 32; s1 += orig_size[i];
         s2 += (ok && ident[i]) ? (orig_size[i] + FU_IDENT_SLICE - 1) / FU_IDENT_SLICE : 0u;
     }
@@ -119,7 +123,7 @@ fu_plan_kernel(const uint64_t* __restrict__ comp_off, const uint32_t* __restrict
     for (uint32_t i = lo; i < hi; ++i) {
         const bool ok = comp_off[i] <= comp_bytes && comp_size[i] <= comp_bytes - comp_off[i];
         uint32_t S, lead, ns;
-        fu_chunk_geom(comp_size[i], orig_size[i], ident[i] != 0, ok, S, lead, ns);
+        fu_chunk_geom(comp_size[i], orig_size[i], ident[i] != 0, ok, lead_knob, S, lead, ns);
         P.nsub[i] = ns; P.nunit[i] = (ns + 31) / 32; P.unit_base[i] = (uint32_t)s0; P.geom[i] = S | (lead << 8);
         P.unit_ctr[i] = 0;
         P.orig_off[i] = orig_off_in ? orig_off_in[i] : s1;
@@ -886,8 +890,9 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
         HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
         ctx->attr_decode_fused = true;
     }
+    static const uint32_t lead_knob = [] { const char* ev = getenv("HZ_FU_LEAD"); return ev ? (uint32_t)atoi(ev) : 0u; }();   // developer knob
     HZ_LAUNCH(ctx, "dec_plan", fu_plan_kernel, 1, 1024, 0, d_comp_off, d_comp_size, d_orig_size, d_orig_off, comp_bytes, K, P,
-              d_ident, ctx->d_status);
+              d_ident, lead_knob, ctx->d_status);
     HZ_LAUNCH(ctx, "dec_zero", fu_zero_kernel, 2 * ctx->sm_count, 256, 0, (uint64_t*)ctx->dec_rec.p, P.unit_base, K);
     HZ_LAUNCH(ctx, "dec_tables", fu_tables_kernel, K, DT, 0, d_len, P, (uint8_t*)ctx->dec_tables.p);
     FuArgs a;
