@@ -95,6 +95,7 @@ def lib():
         L.hz_launch_count.argtypes = [vp]
         L.hz_launch_count.restype = u64
         L.hz_synth_fill.argtypes = [vp, vp, u64, u64, u64, vp]
+        L.hz_dev_reload_knobs.argtypes = [vp]
         L.hz_host_sha256.argtypes = [vp, u64, vp]
         L.hz_host_sha256.restype = None
         _lib = L
@@ -190,6 +191,10 @@ class Codec:
     def decode_raw(self, comp, comp_bytes, comp_off, comp_size, orig_size, orig_off, lens, K, out, out_cap):
         self._check(self._L.hz_decode(self._h, _ptr(comp), comp_bytes, _ptr(comp_off), _ptr(comp_size),
                                       _ptr(orig_size), _ptr(orig_off), _ptr(lens), K, _ptr(out), out_cap))
+
+    def reload_knobs(self):
+        """Developer knobs (HZ_* environment variables) are read when the context is created; re-read them."""
+        self._check(self._L.hz_dev_reload_knobs(self._h))
 
     def synth_fill(self, d_out, n, stream_offset, seed, qtable):
         self._check(self._L.hz_synth_fill(self._h, _ptr(d_out), n, stream_offset, seed, _ptr(qtable)))

@@ -76,6 +76,24 @@ void hz_prof_resolve(hz_ctx* ctx) {
     ctx->prof_pending.clear();
 }
 
+void hz_read_knobs(hz_knobs* k) {
+    auto num = [](const char* name, int dflt) { const char* ev = getenv(name); return ev ? atoi(ev) : dflt; };
+    k->range_mult = num("HZ_RANGE_MULT", 0);
+    if (const char* ev = getenv("HZ_HIST")) k->hist = strcmp(ev, "private") == 0 ? 0 : (strcmp(ev, "atomic") == 0 ? 1 : 2);
+    k->hist_range = num("HZ_HIST_RANGE", 1);
+    if (const char* ev = getenv("HZ_CODEBOOK")) k->codebook = strcmp(ev, "warp") == 0 ? 1 : 2;
+    if (const char* ev = getenv("HZ_CODEBOOK_REPLAY")) k->codebook_lane0 = strcmp(ev, "lane0") == 0;
+    k->ident = num("HZ_IDENT", 1) != 0;
+    if (const char* ev = getenv("HZ_DEC")) k->dec_mode = strcmp(ev, "legacy") == 0 ? 1 : (strcmp(ev, "fused") == 0 ? 2 : 0);
+    k->dec_prebuild = num("HZ_DEC_PREBUILD", -1);
+    k->dec_win = num("HZ_DEC_WIN", 0);
+    k->dec_groups = num("HZ_DEC_GROUPS", 0);
+    k->dec_bulk = num("HZ_DEC_BULK", 1) != 0;
+    k->fu_lead = num("HZ_FU_LEAD", 0);
+    k->fu_grid = num("HZ_FU_GRID", 0);
+    if (const char* ev = getenv("HZ_FU_DUMP")) k->fu_dump = ev;
+}
+
 static int check_status(hz_ctx* ctx) {
     // copy + reset the device status word; caller has synchronised or will right here
     cudaError_t e = cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
@@ -128,6 +146,7 @@ int hz_create(int device, hz_ctx** out_ctx) {
     if (ndev <= 0 || device < 0 || device >= ndev) return HZ_ERR_CUDA;   // no CPU fallback
     hz_ctx* c = new hz_ctx();
     c->device = device;
+    hz_read_knobs(&c->knobs);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_status, sizeof(int));

@@ -748,7 +748,7 @@ int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t spc, uint32_t
         // bounds a chunk at 1.75 MiB): a warp of 32 chunks takes ~1.5x as long as one chunk on one lane, so it
         // pays once the warp-per-chunk kernel needs more than one wave of ~40 warps per SM
         bool lanes = !d_fixed_len256 && spc >= 1 && K >= 8192;
-        if (const char* ev = getenv("HZ_CODEBOOK")) lanes = !d_fixed_len256 && spc >= 1 && strcmp(ev, "warp") != 0;   // developer knob: warp | lane
+        if (ctx->knobs.codebook) lanes = !d_fixed_len256 && spc >= 1 && ctx->knobs.codebook == 2;   // developer knob: warp | lane
         if (lanes) {
             if (!ctx->attr_codebook) {
                 HZ_CUDA(ctx, cudaFuncSetAttribute(codebook_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CBL_SMEM));
@@ -763,7 +763,7 @@ int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t spc, uint32_t
         // (256 KiB chunks, K = 4,096: 0.557 -> 0.470 ms); mode 2 keeps the one-lane loops for A/B runs
         if (!lens_ready) {
             bool coop = true;
-            if (const char* ev = getenv("HZ_CODEBOOK_REPLAY")) coop = strcmp(ev, "lane0") != 0;     // developer knob: warp | lane0
+            if (ctx->knobs.codebook_lane0) coop = false;     // developer knob: warp | lane0
             if (!coop) lens_ready = 2;
         }
         HZ_LAUNCH(ctx, "codebook", codebook_warp_kernel, (K + CBW_WARPS - 1) / CBW_WARPS, CBW_WARPS * 32, 0,

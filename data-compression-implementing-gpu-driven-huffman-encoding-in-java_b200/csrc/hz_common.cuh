@@ -20,11 +20,31 @@
 // (longer ranges amortise the per-range start-up; short chunks keep them short so that both groups of a
 // CTA have work).  The histogram kernel counts a whole range per CTA into the range's FIRST segment slot
 // and zeroes the others: every consumer either sums a chunk's slots or reads the offset of a range start.
-static inline uint32_t hz_range_mult(uint32_t spc) {
+static inline uint32_t hz_range_mult(uint32_t spc, int knob) {
     uint32_t m = spc >= 64 ? 4u : (spc >= 16 ? 2u : 1u);
-    if (const char* ev = getenv("HZ_RANGE_MULT")) { const int v = atoi(ev); if (v >= 1 && v <= 64 && spc >= 64) m = (uint32_t)v; }   // developer knob
+    if (knob >= 1 && knob <= 64 && spc >= 64) m = (uint32_t)knob;
     return m;
 }
+
+// Developer knobs (A/B switches of kernel variants, never needed in production): read from the environment ONCE,
+// when the context is created (hz_create), not on every launch.
+struct hz_knobs {
+    int range_mult = 0;        // HZ_RANGE_MULT   segments per encoder range (0 = default rule)
+    int hist = 2;              // HZ_HIST         private | atomic | lanes (default)
+    int hist_range = 1;        // HZ_HIST_RANGE   0 = one segment per histogram CTA
+    int codebook = 0;          // HZ_CODEBOOK     0 = default rule, 1 = warp, 2 = lane
+    int codebook_lane0 = 0;    // HZ_CODEBOOK_REPLAY=lane0
+    int ident = 1;             // HZ_IDENT        0 = identity chunks go through the coder
+    int dec_mode = 0;          // HZ_DEC          0 = by chunk size, 1 = legacy multi-pass kernels, 2 = fused kernel
+    int dec_prebuild = -1;     // HZ_DEC_PREBUILD (legacy kernels)
+    int dec_win = 0;           // HZ_DEC_WIN
+    int dec_groups = 0;        // HZ_DEC_GROUPS
+    int dec_bulk = 1;          // HZ_DEC_BULK
+    int fu_lead = 0;           // HZ_FU_LEAD      lead-in words of the fused decoder
+    int fu_grid = 0;           // HZ_FU_GRID      CTAs of the fused decoder
+    std::string fu_dump;       // HZ_FU_DUMP      file for per-subsequence records
+};
+void hz_read_knobs(hz_knobs* k);
 
 struct hz_prof_entry { const char* name; double ms; uint64_t launches; };
 
@@ -39,6 +59,7 @@ struct hz_ctx {
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
+    hz_knobs knobs;
     // kernel attributes (opt-in shared memory) are per device: set once per context, not once per process
     bool attr_encode = false, attr_decode = false, attr_decode_fused = false, attr_hist = false, attr_codebook = false;
     // device-side status word (first error latched by kernels) + pinned host mirror

@@ -1040,14 +1040,23 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     // every chunk's tables are built once by dec_tables_kernel (a small CTA, many per SM) and copied in.
     uint32_t tab_min_seq = DEC_SEQ_PER_CTA;
     if ((uint64_t)K * DEC_TABLE_BYTES <= DEC_TAB_PREBUILD_CAP) tab_min_seq = 0;
-    if (const char* ev = getenv("HZ_DEC_PREBUILD")) tab_min_seq = atoi(ev) ? 0 : DEC_SEQ_PER_CTA;   // developer knob
+    if (ctx->knobs.dec_prebuild >= 0) tab_min_seq = ctx->knobs.dec_prebuild ? 0 : DEC_SEQ_PER_CTA;   // developer knob
     HZ_TRY(hz_reserve(ctx, &ctx->dec_misc, (size_t)K + 64));
     uint8_t* ident = (uint8_t*)ctx->dec_misc.p;
-    uint32_t ident_on = 1;                 // developer knob: HZ_IDENT=0 sends identity chunks through the table walk
-    if (const char* ev = getenv("HZ_IDENT")) ident_on = atoi(ev) != 0;
+    const uint32_t ident_on = ctx->knobs.ident;   // developer knob: HZ_IDENT=0 sends identity chunks through the table walk
     HZ_LAUNCH(ctx, "dec_ident", dec_ident_flags_kernel, (K + DT / 32 - 1) / (DT / 32), DT, 0, d_len, d_orig_size, K, ident, ident_on);
-    static const bool legacy = [] { const char* ev = getenv("HZ_DEC"); return ev && strcmp(ev, "legacy") == 0; }();   // developer knob
-    if (!legacy) {
+    // Chunks of >= ~64 units (a unit = 32 subsequences, 0.4 - 2 KiB of stream) go to the fused single-walk kernel; streams
+    // of smaller chunks keep the multi-pass kernels below, whose CTAs are not tied to one chunk's table for long
+    // (measured on B200 at 4 bits/symbol: 64 KiB chunks 387 vs 246 GB/s, 256 KiB 574 vs 499, 1 MiB 646 vs 763).
+    const int mode = ctx->knobs.dec_mode;   // developer knob HZ_DEC=legacy|fused
+    bool fused = mode != 1;
+    if (mode == 0) {
+        uint64_t s = out_cap ? comp_bytes * 34 / out_cap : 17;
+        s = s < 3 ? 3 : (s > 17 ? 17 : s);
+        const uint64_t unit_bytes = ((s - 1) | 1) * 128;
+        fused = comp_bytes / K >= 64 * unit_bytes;
+    }
+    if (fused) {
         const uint64_t* p_orig_off = nullptr; const uint32_t* p_islice = nullptr;
         HZ_TRY(hzk_decode_fused(ctx, d_comp, comp_bytes, d_comp_off, d_comp_size, d_orig_size, d_orig_off, d_len, K, d_out, out_cap,
                                 ident, &p_orig_off, &p_islice));
@@ -1086,7 +1095,7 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     uint64_t est = comp_bytes ? (uint64_t)(32.0 * DEC_SUB_BYTES * 1.1 * (double)out_cap / (double)comp_bytes) + 64 : DEC_WIN_MIN;
     est = (est + 255) & ~(uint64_t)255;
     uint32_t win_bytes = (uint32_t)(est < DEC_WIN_MIN ? DEC_WIN_MIN : (est > DEC_WIN_MAX ? DEC_WIN_MAX : est));
-    if (const char* ev = getenv("HZ_DEC_WIN")) { int v = atoi(ev); if (v >= 256 && v <= DEC_WIN_MAX) win_bytes = (uint32_t)v & ~255u; }   // developer knob
+    if (ctx->knobs.dec_win >= 256 && ctx->knobs.dec_win <= DEC_WIN_MAX) win_bytes = (uint32_t)ctx->knobs.dec_win & ~255u;   // developer knob
     // groups per CTA: as many as fit the SM's shared memory next to the shared table (developer knob HZ_DEC_GROUPS)
     const size_t gbytes = DEC_WRITE_GROUP + (DT / 32) * (size_t)win_bytes;
     uint32_t groups = (uint32_t)((227 * 1024 - 1024 - DEC_WRITE_SHARED) / gbytes);
@@ -1096,9 +1105,8 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     // (two table builds in flight) beat one CTA whose extra groups wait for the build
     const uint32_t fit = groups;
     if (comp_bytes / K < 4ull * DEC_SEQ_BYTES) groups = 1;
-    if (const char* ev = getenv("HZ_DEC_GROUPS")) { int v = atoi(ev); if (v >= 1 && v <= (int)fit) groups = (uint32_t)v; }
-    uint32_t bulk_out = 1;                 // developer knob: HZ_DEC_BULK=0 copies the windows out with 128-bit stores
-    if (const char* ev = getenv("HZ_DEC_BULK")) bulk_out = atoi(ev) != 0;
+    if (ctx->knobs.dec_groups >= 1 && ctx->knobs.dec_groups <= (int)fit) groups = (uint32_t)ctx->knobs.dec_groups;
+    const uint32_t bulk_out = ctx->knobs.dec_bulk;   // developer knob: HZ_DEC_BULK=0 copies the windows out with 128-bit stores
     HZ_LAUNCH(ctx, "dec_write", dec_write_kernel, (unsigned)max_cta, DT * groups, DEC_WRITE_SHARED + groups * gbytes,
               d_comp, comp_bytes, d_comp_off, d_comp_size, d_orig_size, d_len, K, P, tables, rec, seqcnt, d_out, out_cap,
               win_bytes, bulk_out, ctx->d_status);

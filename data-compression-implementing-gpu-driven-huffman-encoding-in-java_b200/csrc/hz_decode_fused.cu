@@ -890,7 +890,7 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
         HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
         ctx->attr_decode_fused = true;
     }
-    static const uint32_t lead_knob = [] { const char* ev = getenv("HZ_FU_LEAD"); return ev ? (uint32_t)atoi(ev) : 0u; }();   // developer knob
+    const uint32_t lead_knob = (uint32_t)ctx->knobs.fu_lead;   // developer knob
     HZ_LAUNCH(ctx, "dec_plan", fu_plan_kernel, 1, 1024, 0, d_comp_off, d_comp_size, d_orig_size, d_orig_off, comp_bytes, K, P,
               d_ident, lead_knob, ctx->d_status);
     HZ_LAUNCH(ctx, "dec_zero", fu_zero_kernel, 2 * ctx->sm_count, 256, 0, (uint64_t*)ctx->dec_rec.p, P.unit_base, K);
@@ -902,9 +902,9 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
 #ifdef FU_TIMING
     cudaMallocManaged(&a.tim, 8 * sizeof(unsigned long long)); cudaMemset(a.tim, 0, 8 * sizeof(unsigned long long));
 #endif
-    const char* dump = getenv("HZ_FU_DUMP");               // developer knob: per-subsequence records to a file
+    const char* dump = ctx->knobs.fu_dump.empty() ? nullptr : ctx->knobs.fu_dump.c_str();   // developer knob: per-subsequence records to a file
     if (dump) { cudaMallocManaged(&a.dbg, max_units * 32 * sizeof(uint32_t)); cudaMemset(a.dbg, 0xFF, max_units * 32 * sizeof(uint32_t)); }
-    static const int grid_knob = [] { const char* ev = getenv("HZ_FU_GRID"); return ev ? atoi(ev) : 0; }();   // developer knob
+    const int grid_knob = ctx->knobs.fu_grid;   // developer knob
     const unsigned grid = grid_knob > 0 ? (unsigned)grid_knob : (unsigned)ctx->sm_count;
     HZ_LAUNCH(ctx, "dec_fused", dec_fused_kernel, grid, FU_THREADS, FU_SMEM_BYTES, a);
 #ifdef FU_TIMING

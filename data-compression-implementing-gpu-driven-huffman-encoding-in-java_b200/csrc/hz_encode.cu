@@ -548,7 +548,7 @@ int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_byte
     const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
     // longer ranges amortise the per-range start-up (LUT build, zeroing, first loads); short
     // chunks keep them short so that both groups of a CTA have work
-    const uint32_t mult = hz_range_mult(spc);
+    const uint32_t mult = hz_range_mult(spc, ctx->knobs.range_mult);
     const uint32_t rpc = (spc + mult - 1) / mult;                      // ranges per chunk
     const uint32_t cpc = (rpc + ENC_GROUPS - 1) / ENC_GROUPS;
     const uint64_t grid = (uint64_t)K * cpc;
@@ -557,8 +557,7 @@ int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_byte
         HZ_CUDA(ctx, cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES));
         ctx->attr_encode = true;
     }
-    uint32_t ident_on = 1;                 // developer knob: HZ_IDENT=0 sends identity chunks through the bit packer
-    if (const char* ev = getenv("HZ_IDENT")) ident_on = atoi(ev) != 0;
+    const uint32_t ident_on = ctx->knobs.ident;   // developer knob: HZ_IDENT=0 sends identity chunks through the bit packer
     HZ_LAUNCH(ctx, "encode", encode_kernel, (unsigned)grid, ENC_CTA, ENC_SMEM_BYTES,
               d_in, n, chunk_bytes, spc, cpc, mult, d_len, d_code, d_comp_off, d_seg_bitoff, K, d_out, out_cap, ident_on, ctx->d_status);
     return HZ_OK;

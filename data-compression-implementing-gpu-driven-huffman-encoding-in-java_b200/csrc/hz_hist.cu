@@ -224,11 +224,7 @@ int hzk_histogram(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_b
     uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
     uint64_t grid = (uint64_t)K * spc;
     if (grid > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "too many segments (%llu)", (unsigned long long)grid);
-    static int variant = -1;
-    if (variant < 0) {
-        const char* e = getenv("HZ_HIST");
-        variant = (e && strcmp(e, "private") == 0) ? 0 : (e && strcmp(e, "atomic") == 0) ? 1 : 2;
-    }
+    const int variant = ctx->knobs.hist;
     if (variant == 0) {
         const size_t smem = (64 * 256 + 256) * sizeof(uint32_t);
         if (!ctx->attr_hist) {
@@ -238,8 +234,8 @@ int hzk_histogram(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_b
         HZ_LAUNCH(ctx, "hist_seg_private", hist_seg_private, (unsigned)grid, HZ_THREADS, smem,
                   d_in, n, chunk_bytes, spc, d_seg_hist);
     } else if (variant == 2) {
-        uint32_t mult = hz_range_mult(spc);
-        if (const char* ev = getenv("HZ_HIST_RANGE")) { if (atoi(ev) == 0) mult = 1; }     // developer knob: one segment per CTA
+        uint32_t mult = hz_range_mult(spc, ctx->knobs.range_mult);
+        if (ctx->knobs.hist_range == 0) mult = 1;     // developer knob: one segment per CTA
         const uint32_t rpc = (spc + mult - 1) / mult;
         HZ_LAUNCH(ctx, "hist_seg_lanes", hist_seg_lanes, (unsigned)((uint64_t)K * rpc), HZ_THREADS, 0,
                   d_in, n, chunk_bytes, spc, mult, d_seg_hist);

@@ -51,3 +51,10 @@ extern "C" int hz_synth_fill(hz_ctx* ctx, uint8_t* d_out, uint64_t n, uint64_t s
     HZ_LAUNCH(ctx, "synth_fill", synth_kernel, (unsigned)blocks, 256, 0, d_out, n, stream_offset, seed, (const uint8_t*)d_q);
     return HZ_OK;
 }
+
+extern "C" int hz_dev_reload_knobs(hz_ctx* ctx) {
+    if (!ctx) return HZ_ERR_ARG;
+    ctx->knobs = hz_knobs();
+    hz_read_knobs(&ctx->knobs);
+    return HZ_OK;
+}

@@ -13,6 +13,9 @@ extern "C" {
  * d_out must be device memory; qtable65536 may be host or device memory. */
 int hz_synth_fill(hz_ctx* ctx, uint8_t* d_out, uint64_t n, uint64_t stream_offset, uint64_t seed,
                   const uint8_t* qtable65536);
+/* Re-read the developer knobs (HZ_* environment variables that select kernel variants for A/B runs and for the
+ * parity tests of the alternative paths).  They are otherwise read once, in hz_create. */
+int hz_dev_reload_knobs(hz_ctx* ctx);
 #ifdef __cplusplus
 }
 #endif

@@ -24,3 +24,23 @@ def codec(hz):
     c = hz.Codec(0)
     yield c
     c.close()
+
+
+@pytest.fixture
+def knob(codec, monkeypatch):
+    """Set a developer knob (HZ_* environment variable) for one test: the library reads them at context creation,
+    so the session's context is told to re-read them, and again when the test is over."""
+    def set_knob(name, value):
+        monkeypatch.setenv(name, value)
+        codec.reload_knobs()
+    yield set_knob
+    monkeypatch.undo()
+    codec.reload_knobs()
+
+
+@pytest.fixture(params=["fused", "legacy"])
+def decmode(request, knob):
+    """Both decoders on the same cases: the fused single-walk kernel and the multi-pass kernels (the library picks
+    by chunk size; HZ_DEC forces one)."""
+    knob("HZ_DEC", request.param)
+    return request.param

@@ -142,13 +142,13 @@ def test_codebook_long_codes(codec, hz):
 
 # ---- encode + decode ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("idx", range(11))
-def test_reference_inputs(codec, idx):
+def test_reference_inputs(codec, decmode, idx):
     data, name, chunk, _ = datasets.reference_cases()[idx]
     check_encode(codec, data, chunk)
     check_encode(codec, data, 1 * MiB)
 
 
-def test_fixtures(codec):
+def test_fixtures(codec, decmode):
     for chunk in (1 * MiB, 2 * MiB, 16 * MiB, 32 * MiB):
         payload, off, lens = check_encode(codec, datasets.fixture_bytes("test_2mb.bin"), chunk)
         assert not payload.any() and payload.size == 262144
@@ -160,19 +160,19 @@ def test_fixtures(codec):
 
 @pytest.mark.parametrize("entropy", [1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("chunk", [64 * 1024, 1 * MiB])
-def test_zipf_streams(codec, entropy, chunk):
+def test_zipf_streams(codec, decmode, entropy, chunk):
     data = datasets.zipf_stream(2 * MiB + 4321, entropy, seed=entropy)
     check_encode(codec, data, chunk)
 
 
 @pytest.mark.parametrize("n,chunk", [(0, 1024), (1, 1024), (7, 3), (1023, 4096), (61439, 1 << 20), (61440, 1 << 20),
                                       (61441, 1 << 20), (122880, 61440), (57343, 1 << 20), (57344, 1 << 20), (57345, 1 << 20), (114688, 57344), (8191, 8192), (8193, 1 << 20), (1_000_003, 100_003), (300_000, 77)])
-def test_ragged_sizes(codec, n, chunk):
+def test_ragged_sizes(codec, decmode, n, chunk):
     data = datasets.zipf_stream(n, 4, seed=n + 1) if n else np.zeros(0, np.uint8)
     check_encode(codec, data, chunk)
 
 
-def test_wide_codes_encode_decode(codec):
+def test_wide_codes_encode_decode(codec, decmode):
     """Chunks whose longest code is > 16 bits (wide encoder path) and > 12 bits (decoder fallback)."""
     rng = np.random.default_rng(11)
     for nsym in (18, 24, 28, 29, 30):       # longest code 17, 23, 27 (medium path) and 28, 29 (wide path)
@@ -191,7 +191,7 @@ def test_uniform_length_codes(codec):
         assert len(set(lens[0][lens[0] > 0])) == 1
 
 
-def test_decode_oracle_streams_and_errors(codec, hz):
+def test_decode_oracle_streams_and_errors(codec, decmode, hz):
     data = datasets.zipf_stream(500_000, 5, seed=9)
     rp, roff, rlens = oracle_encode(data, 200_000)
     sizes = np.diff(roff).astype(np.uint32)
@@ -213,7 +213,7 @@ def test_decode_oracle_streams_and_errors(codec, hz):
 
 
 @pytest.mark.parametrize("H,chunk", [(5, 1 * MiB), (2, 300_000), (7, 70_000)])
-def test_decode_damaged_streams_match_the_oracle(codec, H, chunk):
+def test_decode_damaged_streams_match_the_oracle(codec, decmode, H, chunk):
     """A complete prefix code decodes ANY bit string, so a damaged stream has a well-defined reference result:
     flipped bits (the self-synchronisation guesses fail and are repaired inside CTAs and across CTA boundaries),
     a truncated payload (zero bits past the end) and a short orig_size must give the oracle's bytes."""
@@ -238,7 +238,7 @@ def test_decode_damaged_streams_match_the_oracle(codec, H, chunk):
             assert np.array_equal(out, ref), "chunk %d trial %d" % (k, trial)
 
 
-def test_decode_reads_zero_bits_past_the_end(codec):
+def test_decode_reads_zero_bits_past_the_end(codec, decmode):
     # TableBasedHuffmanDecoder.java:204-208: bits past the end of the chunk are 0
     ln = np.zeros((1, 256), dtype=np.uint8); ln[0, 7] = 1; ln[0, 9] = 1      # 7 -> '0', 9 -> '1'
     comp = np.array([0b10100000], dtype=np.uint8)
@@ -254,7 +254,7 @@ def _perm_blocks(rng, nbytes):
 
 
 @pytest.mark.parametrize("chunk", [4096, 65536 + 256, 1 * MiB + 512])
-def test_identity_chunks_take_the_copy_path(codec, chunk):
+def test_identity_chunks_take_the_copy_path(codec, decmode, chunk):
     """A chunk whose 256 symbols all get 8-bit codes has code[s] == s: encode and decode are byte copies
     (hz_group_copy).  Mixed with ordinary chunks so that chunk offsets are odd (every source / destination
     misalignment), with ragged tails, against the oracle bit for bit."""
@@ -498,13 +498,13 @@ def test_many_small_chunks_warp_codebook(codec):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("replay", ["warp", "lane0"])
-def test_warp_replay_heavy_ties_many_chunks(codec, monkeypatch, replay):
+def test_warp_replay_heavy_ties_many_chunks(codec, knob, replay):
     """The heap replay of the codebook kernels (warp_heap_replay: child-preference bits by ballot, path in registers)
     against the oracle's literal PriorityQueue where the tie-breaks decide the lengths: histograms drawn from tiny value
     ranges, sparse alphabets, powers of two, and counts near 2^31 (64-bit heap keys).  1,300 rows take the
     warp-per-chunk kernel (K >= 1024), the first 300 alone the CTA-per-chunk kernel; HZ_CODEBOOK_REPLAY=lane0 runs
     the one-lane literal loops on the same rows."""
-    monkeypatch.setenv("HZ_CODEBOOK_REPLAY", replay)
+    knob("HZ_CODEBOOK_REPLAY", replay)
     rng = np.random.default_rng(20261019)
     hs = []
     for hi in (1, 2, 3, 4, 8, 16, 100):
@@ -538,11 +538,11 @@ def _chunk_with_counts(rng, counts, size):
     return b
 
 
-def test_lane_codebook_ties_and_long_codes(codec, monkeypatch):
+def test_lane_codebook_ties_and_long_codes(codec, knob):
     """Streams of thousands of chunks take the lane-per-chunk heap replay (codebook_lane_kernel, 32-bit keys):
     tie-heavy, sparse, one-symbol and long-code chunk histograms, mixed inside the same warps, must give the
     oracle's code lengths, offsets and payload (HZ_CODEBOOK=lane forces the kernel from K >= 1024)."""
-    monkeypatch.setenv("HZ_CODEBOOK", "lane")
+    knob("HZ_CODEBOOK", "lane")
     rng = np.random.default_rng(11)
     chunk, K = 2048, 1300
     parts = []
@@ -580,11 +580,12 @@ def test_lane_codebook_ties_and_long_codes(codec, monkeypatch):
 
 
 @pytest.mark.parametrize("prebuild", ["0", "1"])
-def test_decode_tables_built_in_place_or_prebuilt(codec, monkeypatch, prebuild):
+def test_decode_tables_built_in_place_or_prebuilt(codec, knob, prebuild):
     """Single-CTA chunks either get their lookup tables from dec_tables_kernel (default while K tables fit the scratch
     cap) or build them inside the sync / write CTAs (HZ_DEC_PREBUILD=0, the path streams of > 150 k chunks take): both
     must decode the same bytes, for small chunks, multi-CTA chunks and a mix of identity and ordinary chunks."""
-    monkeypatch.setenv("HZ_DEC_PREBUILD", prebuild)
+    knob("HZ_DEC", "legacy")
+    knob("HZ_DEC_PREBUILD", prebuild)
     for n, chunk, H in [(3 * MiB + 17, 64 * 1024, 3), (9 * MiB, 4 * MiB, 5), (2 * MiB + 5, 256 * 1024, 8), (700_001, 4096, 1)]:
         data = datasets.zipf_stream(n, H, seed=H + 40)
         check_encode(codec, data, chunk)
