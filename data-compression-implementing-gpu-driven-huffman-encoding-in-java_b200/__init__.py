@@ -31,6 +31,7 @@ _EXPORTS = [
     "hz_encode_with_lengths", "hz_decode", "hz_sha256_chunks", "hz_compress_file", "hz_decompress_file",
     "hz_verify_file", "hz_compress_buffer", "hz_decompress_buffer", "hz_free", "hz_prof_enable", "hz_prof_reset",
     "hz_prof_count", "hz_prof_get", "hz_launch_count", "hz_host_alloc", "hz_host_free",
+    "hz_comm_unique_id", "hz_comm_init", "hz_comm_destroy", "hz_encode_global",
 ]
 
 
@@ -80,6 +81,10 @@ def lib():
         L.hz_encode.argtypes = [vp, vp, u64, u32, vp, u64, vp, vp, vp]
         L.hz_encode_with_lengths.argtypes = [vp, vp, u64, u32, vp, vp, u64, vp]
         L.hz_decode.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, u32, vp, u64]
+        L.hz_encode_global.argtypes = [vp, vp, u64, u32, vp, u64, vp, vp]
+        L.hz_comm_unique_id.argtypes = [vp]
+        L.hz_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.hz_comm_destroy.argtypes = [vp]
         L.hz_sha256_chunks.argtypes = [vp, vp, u64, u32, vp]
         L.hz_compress_file.argtypes = [vp, C.c_char_p, C.c_char_p, u32, C.c_char_p, i64, vp, vp]
         L.hz_decompress_file.argtypes = [vp, C.c_char_p, C.c_char_p, vp, vp]
@@ -191,6 +196,36 @@ class Codec:
     def decode_raw(self, comp, comp_bytes, comp_off, comp_size, orig_size, orig_off, lens, K, out, out_cap):
         self._check(self._L.hz_decode(self._h, _ptr(comp), comp_bytes, _ptr(comp_off), _ptr(comp_size),
                                       _ptr(orig_size), _ptr(orig_off), _ptr(lens), K, _ptr(out), out_cap))
+
+    # -- global-codebook extension (one logical file over several GPUs) ----------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (call on ONE rank, give the bytes to every rank's comm_init)."""
+        buf = C.create_string_buffer(128)
+        st = lib().hz_comm_unique_id(buf)
+        if st != HZ_OK:
+            raise HzError(st, "hz_comm_unique_id failed (libnccl.so.2 missing?)")
+        return buf.raw
+
+    def comm_init(self, unique_id, nranks, rank):
+        self._check(self._L.hz_comm_init(self._h, C.c_char_p(bytes(unique_id)), nranks, rank))
+
+    def comm_destroy(self):
+        self._check(self._L.hz_comm_destroy(self._h))
+
+    def encode_global_raw(self, src, n, chunk_bytes, out, out_cap, comp_off, len256_out):
+        self._check(self._L.hz_encode_global(self._h, _ptr(src), n, chunk_bytes, _ptr(out), out_cap, _ptr(comp_off), _ptr(len256_out)))
+
+    def encode_global(self, data, chunk_bytes):
+        """-> (payload, comp_off[K+1], len256): ONE codebook over all chunks (and all ranks after comm_init)."""
+        d = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        K = int(self._L.hz_num_chunks(d.size, chunk_bytes))
+        cap = d.size * 4 + 16
+        out = np.zeros(cap, dtype=np.uint8)
+        off = np.zeros(K + 1, dtype=np.uint64)
+        l256 = np.zeros(256, dtype=np.uint8)
+        self.encode_global_raw(d if d.size else None, d.size, chunk_bytes, out, cap, off, l256)
+        return out[: int(off[K])].copy(), off, l256
 
     def reload_knobs(self):
         """Developer knobs (HZ_* environment variables) are read when the context is created; re-read them."""

@@ -163,7 +163,8 @@ void hz_destroy(hz_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->seg_hist, &c->chunk_hist, &c->len, &c->code, &c->chunk_bits, &c->comp_size, &c->comp_off,
+    hz_comm_destroy(c);
+    DevBuf* bufs[] = {&c->glob, &c->seg_hist, &c->chunk_hist, &c->len, &c->code, &c->chunk_bits, &c->comp_size, &c->comp_off,
                       &c->seg_bitoff, &c->counter, &c->stage_in, &c->stage_out, &c->stage_a, &c->stage_b,
                       &c->stage_c, &c->stage_d, &c->stage_e, &c->dec_meta, &c->dec_rec, &c->dec_seqcnt, &c->dec_misc, &c->dec_tables};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -340,8 +341,11 @@ __global__ void store_total_kernel(const uint64_t* __restrict__ d_total, uint64_
 }
 
 // histogram -> codebook -> encode of K chunks, everything device-resident
+// global != nullptr: ONE codebook from the histogram summed over all chunks (and, after hz_comm_init, over all
+// ranks: hzk_global_histogram); its 256 lengths are also written to global_len256 (device)
 static int encode_device(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K, const uint8_t* d_fixed,
-                         uint8_t* d_out, uint64_t dcap, uint64_t* d_off, uint8_t* d_len, uint32_t* d_hist) {
+                         uint8_t* d_out, uint64_t dcap, uint64_t* d_off, uint8_t* d_len, uint32_t* d_hist,
+                         uint8_t* global_len256 = nullptr) {
     const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
     const size_t nseg = (size_t)K * spc;
     HZ_TRY(hz_reserve(ctx, &ctx->seg_hist, nseg * 1024));
@@ -350,6 +354,14 @@ static int encode_device(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t 
     HZ_TRY(hz_reserve(ctx, &ctx->comp_size, (size_t)K * 4));
     HZ_TRY(hz_reserve(ctx, &ctx->seg_bitoff, nseg * 8));
     HZ_TRY(hzk_histogram(ctx, d_in, n, chunk_bytes, K, (uint32_t*)ctx->seg_hist.p));
+    if (global_len256) {
+        HZ_TRY(hz_reserve(ctx, &ctx->glob, 256 * 8 + 256 * 4));
+        uint64_t* g64 = (uint64_t*)ctx->glob.p;
+        uint32_t* h32 = (uint32_t*)(g64 + 256);
+        HZ_TRY(hzk_global_histogram(ctx, (const uint32_t*)ctx->seg_hist.p, nseg, g64, h32));
+        HZ_TRY(hzk_codebook(ctx, h32, 0, 1, nullptr, global_len256, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        d_fixed = global_len256;
+    }
     HZ_TRY(hzk_codebook(ctx, (const uint32_t*)ctx->seg_hist.p, spc, K, d_hist, d_len,
                         (uint32_t*)ctx->code.p, (uint64_t*)ctx->chunk_bits.p, (uint32_t*)ctx->comp_size.p,
                         d_off, (uint64_t*)ctx->seg_bitoff.p, d_fixed));
@@ -501,6 +513,48 @@ static int encode_impl(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chun
 int hz_encode(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint8_t* out, uint64_t out_cap,
               uint64_t* comp_off, uint8_t* len_out, uint32_t* hist_out) {
     return encode_impl(ctx, in, n, chunk_bytes, nullptr, out, out_cap, comp_off, len_out, hist_out);
+}
+
+int hz_encode_global(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint8_t* out, uint64_t out_cap,
+                     uint64_t* comp_off, uint8_t* len256_out) {
+    if (!ctx || chunk_bytes == 0 || (n && (!in || !out)) || !comp_off || !len256_out)
+        return hz_fail(ctx, HZ_ERR_ARG, "hz_encode_global: bad argument");
+    HZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t K64 = hz_num_chunks(n, chunk_bytes);
+    if (K64 > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "too many chunks");
+    const uint32_t K = (uint32_t)K64;
+    // every rank takes part in the all-reduce, also one whose shard is empty (K == 0: an all-zero histogram)
+    const void* d_in; void *d_out, *d_off, *d_gl; bool s_out, s_off, s_gl;
+    HZ_TRY(in_dev(ctx, &ctx->stage_in, in, n, &d_in));
+    HZ_TRY(out_dev(ctx, &ctx->stage_out, out, out_cap + 16, &d_out, &s_out));
+    HZ_TRY(out_dev(ctx, &ctx->comp_off, comp_off, ((size_t)K + 1) * 8, &d_off, &s_off));
+    HZ_TRY(out_dev(ctx, &ctx->stage_e, len256_out, 256, &d_gl, &s_gl));
+    HZ_TRY(hz_reserve(ctx, &ctx->len, (size_t)(K ? K : 1) * 256));
+    if (K == 0) {
+        HZ_TRY(hz_reserve(ctx, &ctx->glob, 256 * 8 + 256 * 4));
+        HZ_TRY(hz_reserve(ctx, &ctx->seg_hist, 1024));
+        uint64_t* g64 = (uint64_t*)ctx->glob.p;
+        HZ_TRY(hzk_global_histogram(ctx, (const uint32_t*)ctx->seg_hist.p, 0, g64, (uint32_t*)(g64 + 256)));
+        HZ_TRY(hzk_codebook(ctx, (const uint32_t*)(g64 + 256), 0, 1, nullptr, (uint8_t*)d_gl, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        HZ_CUDA(ctx, cudaMemsetAsync(d_off, 0, sizeof(uint64_t), ctx->stream));
+    } else {
+        HZ_TRY(encode_device(ctx, (const uint8_t*)d_in, n, chunk_bytes, K, nullptr, (uint8_t*)d_out, out_cap,
+                             (uint64_t*)d_off, (uint8_t*)ctx->len.p, nullptr, (uint8_t*)d_gl));
+    }
+    if (!(s_out || s_off || s_gl)) return HZ_OK;
+    uint64_t total = 0;
+    if (s_off) HZ_TRY(out_copy(ctx, comp_off, d_off, ((size_t)K + 1) * 8));
+    else HZ_CUDA(ctx, cudaMemcpyAsync(&total, (uint64_t*)d_off + K, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (s_gl) HZ_TRY(out_copy(ctx, len256_out, d_gl, 256));
+    HZ_TRY(check_status(ctx));
+    if (s_off) total = comp_off[K];
+    if (s_out) {
+        if (total > out_cap) return hz_fail(ctx, HZ_ERR_OUT_TOO_SMALL, "payload %llu > capacity %llu",
+                                            (unsigned long long)total, (unsigned long long)out_cap);
+        HZ_TRY(out_copy(ctx, out, d_out, total));
+        HZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return HZ_OK;
 }
 
 int hz_encode_with_lengths(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint8_t* len256,

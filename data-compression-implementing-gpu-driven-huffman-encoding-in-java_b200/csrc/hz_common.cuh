@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include <string>
 #include <vector>
 #include "../../include/huffb200.h"
@@ -60,6 +61,8 @@ struct hz_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     hz_knobs knobs;
+    void* nccl_comm = nullptr; int nccl_ranks = 1, nccl_rank = 0;     // global-codebook mode (hz_comm_init)
+    DevBuf glob;                                                      // u64[256] + u32[256] + u8[256]
     // kernel attributes (opt-in shared memory) are per device: set once per context, not once per process
     bool attr_encode = false, attr_decode = false, attr_decode_fused = false, attr_hist = false, attr_codebook = false;
     // device-side status word (first error latched by kernels) + pinned host mirror
@@ -135,6 +138,7 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
                      const uint32_t* d_comp_size, const uint32_t* d_orig_size, const uint64_t* d_orig_off,
                      const uint8_t* d_len, uint32_t K, uint8_t* d_out, uint64_t out_cap, const uint8_t* d_ident,
                      const uint64_t** plan_orig_off, const uint32_t** plan_islice);
+int hzk_global_histogram(hz_ctx* ctx, const uint32_t* d_seg_hist, uint64_t nseg, uint64_t* d_g64, uint32_t* d_h32);
 int hzk_sha256(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
                uint8_t* d_digests);
 

@@ -3,11 +3,12 @@
 The path shards by file chunk: every chunk has its own histogram, codebook,
 byte-aligned bitstream and footer record (cpu/CpuCompressionService.java:210-261) and chunks are
 concatenated in index order (:160-163).  Rank g of G codes chunks [g*K//G, (g+1)*K//G) on its own
-GPU with NO data-path collective.  What crosses ranks is metadata only:
+GPU with NO data-path collective.  What crosses ranks:
 
-  * per-chunk compressed sizes / code lengths / SHA-256 digests (gathered to rank 0, which
-    assembles the offset table with an exclusive scan on the host and writes the footer,
-    byte-identical to the reference's: core/CompressionHeader.java:51-85);
+  * every rank's compressed payload and its per-chunk compressed sizes / code lengths / SHA-256 digests, sent to
+    rank 0 ONLY (a gather, not an all-gather), which concatenates the payloads in chunk order, assembles the
+    offset table with an exclusive scan on the host and writes the footer, byte-identical to the reference's
+    (core/CompressionHeader.java:51-85);
   * in the optional GLOBAL-CODEBOOK mode, one all-reduce (sum) of a 256 x int64 histogram
     (2 KiB; NCCL over NVLink on GPUs, gloo in the CPU tests) so that every rank builds the same
     codebook.  That mode is an extension: a valid .dcz any reference decoder accepts, but not
@@ -103,13 +104,15 @@ def all_reduce_histogram(hist, group=None):
     return hist
 
 
-def gather_objects(obj, group=None):
-    """All ranks -> list of per-rank python objects on every rank (metadata only)."""
+def gather_objects(obj, group=None, dst=0):
+    """Per-rank python objects -> list on rank `dst` ONLY (None elsewhere): a rank's compressed payload and its
+    per-chunk metadata travel to the rank that writes the file and nowhere else."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return [obj]
-    out = [None] * dist.get_world_size(group)
-    dist.all_gather_object(out, obj, group=group)
+    rank = dist.get_rank(group)
+    out = [None] * dist.get_world_size(group) if rank == dst else None
+    dist.gather_object(obj, out, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
     return out
 
 

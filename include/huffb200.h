@@ -101,6 +101,22 @@ int hz_encode(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 int hz_encode_with_lengths(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
                            const uint8_t* len256, uint8_t* out, uint64_t out_cap, uint64_t* comp_off);
 
+/* Global-codebook extension for one logical file sharded over several GPUs (one context per GPU, one process
+ * per GPU): ONE codebook, built from the byte histogram summed over ALL chunks of ALL ranks, codes every chunk.
+ * hz_comm_unique_id (on one rank; the host distributes the 128 bytes) + hz_comm_init (on every rank) create an
+ * NCCL communicator inside the library (libnccl.so.2 is bound with dlopen at that moment; without these calls
+ * the sum is over this context's chunks only).  hz_encode_global then runs histogram -> device-side reduction to
+ * 256 x u64 -> ncclAllReduce(sum) over NVLink on the context's stream -> the same deterministic codebook build on
+ * every rank -> encode, all enqueued without host synchronisation; len256_out receives the 256 code lengths
+ * (identical on every rank; the footer repeats them in every chunk record).  Counts beyond 32 bits are scaled by a
+ * power of two first.  Collective: every rank must call it, also with n == 0.  Not bit-identical to the reference
+ * compressor (which has no such mode), but a valid .dcz for any reference decoder.                             */
+int hz_comm_unique_id(void* id128);
+int hz_comm_init(hz_ctx* ctx, const void* id128, int nranks, int rank);
+int hz_comm_destroy(hz_ctx* ctx);
+int hz_encode_global(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint8_t* out, uint64_t out_cap,
+                     uint64_t* comp_off, uint8_t* len256_out);
+
 /* Decode K chunks.  Chunk k's bitstream is comp[comp_off[k] .. comp_off[k]+comp_size[k]), its
  * code lengths len[k][256]; exactly orig_size[k] symbols are produced at out[orig_off[k] ..)
  * (orig_off == NULL: chunks are written back to back).  Bits past the end of a chunk read as 0

@@ -306,6 +306,27 @@ def test_global_codebook_extension(codec):
     assert np.array_equal(back, data)
 
 
+def test_encode_global_in_library(codec):
+    """hz_encode_global (one histogram pass, device-side reduction, codebook and encode in one call; the NCCL
+    all-reduce is skipped without a communicator) == histogram + hz_build_codebooks + hz_encode_with_lengths, and
+    the lengths are the oracle's for the summed histogram.  An expanding code (a rare shard coded with a table
+    built elsewhere) and an empty shard work too."""
+    data = datasets.zipf_stream(3_000_001, 3, seed=15)
+    chunk = 400_000
+    payload, off, l256 = codec.encode_global(data, chunk)
+    hist = codec.histogram(data, chunk).astype(np.uint64).sum(axis=0)
+    ref_len = orc.code_lengths(hist)[0].astype(np.uint8)
+    assert np.array_equal(l256, ref_len)
+    p2, o2 = codec.encode_with_lengths(data, chunk, l256)
+    assert np.array_equal(off, o2) and np.array_equal(payload, p2)
+    K = len(off) - 1
+    orig = np.array([min(chunk, data.size - k * chunk) for k in range(K)], dtype=np.uint32)
+    back = codec.decode(payload, off[:-1], np.diff(off).astype(np.uint32), orig, np.tile(l256, (K, 1)))
+    assert np.array_equal(back, data)
+    p0, o0, l0 = codec.encode_global(np.zeros(0, np.uint8), chunk)
+    assert p0.size == 0 and o0.tolist() == [0] and not l0.any()
+
+
 # ---- container (.dcz) ------------------------------------------------------------------------------------
 @pytest.mark.parametrize("idx", range(11))
 def test_dcz_byte_identical(codec, idx):
