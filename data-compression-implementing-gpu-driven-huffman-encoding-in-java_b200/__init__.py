@@ -31,7 +31,7 @@ _EXPORTS = [
     "hz_encode_with_lengths", "hz_decode", "hz_sha256_chunks", "hz_compress_file", "hz_decompress_file",
     "hz_verify_file", "hz_compress_buffer", "hz_decompress_buffer", "hz_free", "hz_prof_enable", "hz_prof_reset",
     "hz_prof_count", "hz_prof_get", "hz_launch_count", "hz_host_alloc", "hz_host_free",
-    "hz_comm_unique_id", "hz_comm_init", "hz_comm_destroy", "hz_encode_global",
+    "hz_comm_unique_id", "hz_comm_init", "hz_comm_destroy", "hz_encode_global", "hz_stage_metrics", "hz_stage_name",
 ]
 
 
@@ -85,6 +85,9 @@ def lib():
         L.hz_comm_unique_id.argtypes = [vp]
         L.hz_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
         L.hz_comm_destroy.argtypes = [vp]
+        L.hz_stage_metrics.argtypes = [vp, vp]
+        L.hz_stage_name.argtypes = [C.c_int]
+        L.hz_stage_name.restype = C.c_char_p
         L.hz_sha256_chunks.argtypes = [vp, vp, u64, u32, vp]
         L.hz_compress_file.argtypes = [vp, C.c_char_p, C.c_char_p, u32, C.c_char_p, i64, vp, vp]
         L.hz_decompress_file.argtypes = [vp, C.c_char_p, C.c_char_p, vp, vp]
@@ -328,6 +331,14 @@ class Codec:
         self._check(self._L.hz_decompress_file(self._h, os.fsencode(in_path), os.fsencode(out_path),
                                                C.cast(cb, C.c_void_p) if cb else None, None))
 
+    def stage_metrics(self):
+        """{stage name: (ms, count, bytes)} of the last file-/buffer-level call, in StageMetrics.Stage order."""
+        class M(C.Structure):
+            _fields_ = [("ms", C.c_double), ("count", C.c_uint64), ("bytes", C.c_uint64)]
+        arr = (M * 8)()
+        self._check(self._L.hz_stage_metrics(self._h, arr))
+        return {self._L.hz_stage_name(i).decode(): (arr[i].ms, int(arr[i].count), int(arr[i].bytes)) for i in range(8)}
+
     def verify_file(self, path):
         ok = C.c_int()
         self._check(self._L.hz_verify_file(self._h, os.fsencode(path), C.byref(ok)))
@@ -378,6 +389,10 @@ class B200CompressionService:
 
     def verify_integrity(self, compressed_path):
         return self._codec.verify_file(compressed_path)
+
+    def get_last_stage_metrics(self):
+        """getLastStageMetrics() of the service classes (cpu/CpuCompressionService.java:52)."""
+        return self._codec.stage_metrics()
 
     def get_service_name(self):
         return "B200 Compression"

@@ -326,6 +326,15 @@ static int pipe_init(hz_ctx* ctx) {
     }
     return HZ_OK;
 }
+struct PipeQuiesce {                           // joins the copy streams when a pipelined call returns, also on errors
+    hz_ctx* ctx;
+    ~PipeQuiesce() {
+        if (ctx->copy_in) cudaStreamSynchronize(ctx->copy_in);
+        if (ctx->copy_out) cudaStreamSynchronize(ctx->copy_out);
+        cudaStreamSynchronize(ctx->stream);
+        cudaGetLastError();
+    }
+};
 static int pipe_totals(hz_ctx* ctx, size_t n) {
     if (ctx->h_totals_cap >= n) return HZ_OK;
     if (ctx->h_totals) { cudaFreeHost(ctx->h_totals); ctx->h_totals = nullptr; ctx->h_totals_cap = 0; }
@@ -380,9 +389,12 @@ static int encode_pipelined(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t
     const uint32_t nb = (K + cpb - 1) / cpb;
     const size_t bbytes = (size_t)cpb * chunk_bytes;
     HZ_TRY(pipe_totals(ctx, nb));
+    // a per-chunk Huffman code never expands a batch (mean length <= 8 bits); a caller-supplied table can, up to 32
+    // bits per symbol: the output slots are then sized for that
+    const size_t slot_cap = fixed_len ? 4 * bbytes : bbytes;
     for (int i = 0; i < S; ++i) {
         HZ_TRY(hz_reserve(ctx, &ctx->pipe_in[i], bbytes));
-        HZ_TRY(hz_reserve(ctx, &ctx->pipe_out[i], bbytes + 16));
+        HZ_TRY(hz_reserve(ctx, &ctx->pipe_out[i], slot_cap + 16));
     }
     HZ_TRY(hz_reserve(ctx, &ctx->pipe_meta_a, ((size_t)K + 1) * 8));   // batch-local offsets of every chunk
     HZ_TRY(hz_reserve(ctx, &ctx->pipe_meta_b, (size_t)K * 256));       // code lengths
@@ -406,10 +418,12 @@ static int encode_pipelined(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t
     std::vector<uint64_t> base(nb + 1, 0);
     uint64_t drained = 0;                      // batches whose payload copy has been issued
     int rc = HZ_OK;
+    PipeQuiesce quiesce{ctx};                  // every exit path waits for the copy streams: no DMA outlives the call
     auto drain = [&](uint32_t b) -> int {      // issue the D2H of batch b (its size is known once its kernels ran)
         const int s = b % S;
         HZ_CUDA(ctx, cudaEventSynchronize(ctx->ev_comp[s]));
         const uint64_t tot = ctx->h_totals[b];
+        if (tot > slot_cap) return hz_fail(ctx, HZ_ERR_OUT_TOO_SMALL, "batch payload %llu > slot %llu", (unsigned long long)tot, (unsigned long long)slot_cap);
         base[b + 1] = base[b] + tot;
         if (base[b + 1] > out_cap) return hz_fail(ctx, HZ_ERR_OUT_TOO_SMALL, "payload > capacity %llu", (unsigned long long)out_cap);
         if (tot) HZ_CUDA(ctx, cudaMemcpyAsync(out + base[b], ctx->pipe_out[s].p, tot, cudaMemcpyDeviceToHost, ctx->copy_out));
@@ -431,7 +445,7 @@ static int encode_pipelined(hz_ctx* ctx, const uint8_t* in, uint64_t n, uint32_t
         HZ_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
         HZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
         rc = encode_device(ctx, (const uint8_t*)ctx->pipe_in[s].p, nbytes, chunk_bytes, kb, (const uint8_t*)d_fixed,
-                           (uint8_t*)ctx->pipe_out[s].p, bbytes, d_off + k0, d_len + (size_t)k0 * 256,
+                           (uint8_t*)ctx->pipe_out[s].p, slot_cap, d_off + k0, d_len + (size_t)k0 * 256,
                            d_hist ? d_hist + (size_t)k0 * 256 : nullptr);
         if (rc != HZ_OK) break;
         HZ_LAUNCH(ctx, "store_total", store_total_kernel, 1, 1, 0, d_off + k0 + kb, h_tot_dev + b);
@@ -567,6 +581,7 @@ static int decode_pipelined(hz_ctx* ctx, const uint8_t* comp, const uint64_t* co
                             const uint32_t* orig_size, const uint8_t* len, uint32_t K, uint8_t* out, uint64_t out_cap) {
     const int S = hz_ctx::PIPE_SLOTS;
     HZ_TRY(pipe_init(ctx));
+    PipeQuiesce quiesce{ctx};                  // every exit path waits for the copy streams: no DMA outlives the call
     uint64_t per = HZ_PIPE_BATCH_BYTES / (orig_size[0] ? orig_size[0] : 1);
     if (per == 0) per = 1;
     const uint32_t cpb = (uint32_t)(per < K ? per : K);

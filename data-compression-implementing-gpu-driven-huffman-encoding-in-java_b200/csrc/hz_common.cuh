@@ -49,6 +49,12 @@ void hz_read_knobs(hz_knobs* k);
 
 struct hz_prof_entry { const char* name; double ms; uint64_t launches; };
 
+// Stage timings of the last file-level call, in the order of the reference's StageMetrics.Stage (hz_stage_metrics)
+struct StageAcc {
+    double ms[HZ_STAGE_COUNT] = {}; uint64_t count[HZ_STAGE_COUNT] = {}, bytes[HZ_STAGE_COUNT] = {};
+    void add(int stage, double milli, uint64_t nbytes) { ms[stage] += milli; count[stage]++; bytes[stage] += nbytes; }
+};
+
 struct DevBuf {                               // grow-only device scratch buffer
     void* p = nullptr; size_t cap = 0;
 };
@@ -61,6 +67,7 @@ struct hz_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     hz_knobs knobs;
+    StageAcc stages;
     void* nccl_comm = nullptr; int nccl_ranks = 1, nccl_rank = 0;     // global-codebook mode (hz_comm_init)
     DevBuf glob;                                                      // u64[256] + u32[256] + u8[256]
     // kernel attributes (opt-in shared memory) are per device: set once per context, not once per process

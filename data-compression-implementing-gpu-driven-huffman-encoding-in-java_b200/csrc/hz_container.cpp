@@ -17,6 +17,7 @@
 #include <thread>
 #include <future>
 #include <atomic>
+#include <chrono>
 #include <algorithm>
 #include <fcntl.h>
 #include <unistd.h>
@@ -248,7 +249,7 @@ struct Source {                     // random-access reader over a file or a mem
         return true;
     }
     bool read(uint64_t off, void* dst, uint64_t n) const {
-        if (off + n > size) return false;
+        if (off > size || n > size - off) return false;            // no wrap-around: off comes from an untrusted footer
         return io_parallel(n, [&](uint64_t lo, uint64_t len) { return read_serial(off + lo, (uint8_t*)dst + lo, len); });
     }
 };
@@ -282,6 +283,56 @@ int pin_reserve(hz_ctx* ctx, size_t bytes) {
     ctx->h_pin_cap = bytes;
     return HZ_OK;
 }
+
+// ---- stage metrics (model/StageMetrics.java) -----------------------------------------------------
+// Host stages are wall-clock times of the pipeline's tasks (reader / writer threads add theirs atomically);
+// kernel stages come from the library's event pairs, collected for the duration of a file-level call.
+struct HostClock {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+struct IoAcc { std::atomic<uint64_t> us{0}, bytes{0}, count{0}; void add(double ms, uint64_t b) { us += (uint64_t)(ms * 1e3); bytes += b; ++count; } };
+
+int stage_of_kernel(const char* name, bool decompressing) {
+    if (!strncmp(name, "hist", 4) || !strcmp(name, "sum_seg_hist") || !strncmp(name, "global_", 7) || !strncmp(name, "nccl", 4)) return HZ_STAGE_FREQUENCY_ANALYSIS;
+    if (!strncmp(name, "codebook", 8) || !strcmp(name, "chunk_offsets") || !strcmp(name, "codes_from_lengths")) return HZ_STAGE_HUFFMAN_TREE_BUILD;
+    if (!strcmp(name, "dec_tables") || !strcmp(name, "dec_plan") || !strcmp(name, "dec_ident") || !strcmp(name, "dec_zero")) return HZ_STAGE_HUFFMAN_TREE_BUILD;   // :518
+    if (!strcmp(name, "encode")) return HZ_STAGE_ENCODING;
+    if (!strncmp(name, "dec_", 4)) return HZ_STAGE_DECODING;
+    if (!strncmp(name, "sha256", 6)) return decompressing ? HZ_STAGE_CHECKSUM_VERIFY : HZ_STAGE_CHECKSUM_COMPUTE;
+    return -1;
+}
+
+struct StageScope {                 // collects the kernels' event pairs of one file-level call into ctx->stages
+    hz_ctx* ctx; bool was; std::vector<hz_prof_entry> saved; uint64_t bytes; bool decompressing;
+    StageScope(hz_ctx* c, uint64_t nbytes, bool dec = false) : ctx(c), was(c->prof), bytes(nbytes), decompressing(dec) {
+        hz_prof_resolve(c);
+        saved.swap(c->prof_entries);
+        c->prof = true;
+        c->stages = StageAcc();
+    }
+    ~StageScope() {
+        hz_prof_resolve(ctx);
+        for (const auto& e : ctx->prof_entries) {
+            const int s = stage_of_kernel(e.name, decompressing);
+            if (s >= 0) { ctx->stages.ms[s] += e.ms; ctx->stages.count[s] += e.launches; ctx->stages.bytes[s] = bytes; }
+        }
+        if (was) for (const auto& e : ctx->prof_entries) {          // a caller that profiles keeps seeing these launches
+            bool found = false;
+            for (auto& o : saved) if (!strcmp(o.name, e.name)) { o.ms += e.ms; o.launches += e.launches; found = true; break; }
+            if (!found) saved.push_back(e);
+        }
+        ctx->prof_entries.swap(saved);
+        ctx->prof = was;
+    }
+};
+
+// SHA-256 of a batch's chunks: on the GPU (hz_sha256.cu, one thread per chunk, ~27 MB/s per chunk) when the batch has
+// enough chunks to beat the host's SHA units (~1.8 GB/s per core, one chunk per thread), else on the host while the
+// GPU codes the batch.  Measured on a B200 box with 16 host cores (profiles/r02_sha256_gpu_vs_host.txt, 1 GiB):
+// 16 KiB chunks 700 vs 29 GB/s, 64 KiB 443 vs 29, 256 KiB 108 vs 29, 1 MiB 27 vs 29, 16 MiB 1.8 vs 29: the kernel wins
+// from about a thousand chunks per call, i.e. chunks <= 64 KiB with 128 MiB batches.
+const size_t kShaGpuMinChunks = 1536;
 
 // bytes of input handled per GPU batch (>= one chunk)
 uint64_t batch_bytes_for(uint32_t chunk_bytes) {
@@ -320,9 +371,11 @@ int compress_core(hz_ctx* ctx, const Source& src, Sink& dst, uint32_t chunk_byte
     HZ_TRY(hz_reserve(ctx, &d_len, kb_max * 256));
 
     uint64_t comp_total = 0, done = 0;
+    IoAcc io;                                         // declared before the futures: the tasks reference it
+    StageScope scope(ctx, n);
     std::future<bool> fut_rd, fut_wr;                 // std::async futures join in their destructor on every exit path
-    if (n) fut_rd = std::async(std::launch::async, [&src, pin_base, off_in, bb, n] {
-        return src.read(0, pin_base + off_in, std::min<uint64_t>(bb, n)); });
+    if (n) fut_rd = std::async(std::launch::async, [&src, &io, pin_base, off_in, bb, n] {
+        HostClock c; const bool ok = src.read(0, pin_base + off_in, std::min<uint64_t>(bb, n)); io.add(c.ms(), std::min<uint64_t>(bb, n)); return ok; });
     uint64_t b = 0;
     for (uint64_t pos = 0, k0 = 0; pos < n; ++b) {
         uint8_t* pin = pin_base + (b & 1) * slot_bytes;
@@ -332,17 +385,25 @@ int compress_core(hz_ctx* ctx, const Source& src, Sink& dst, uint32_t chunk_byte
         if (pos + bn < n) {                           // the other slot's input was consumed (copied, hashed) a batch ago
             uint8_t* nxt = pin_base + ((b + 1) & 1) * slot_bytes + off_in;
             const uint64_t npos = pos + bn, nn = std::min<uint64_t>(bb, n - npos);
-            fut_rd = std::async(std::launch::async, [&src, nxt, npos, nn] { return src.read(npos, nxt, nn); });
+            fut_rd = std::async(std::launch::async, [&src, &io, nxt, npos, nn] {
+                HostClock c; const bool ok = src.read(npos, nxt, nn); io.add(c.ms(), nn); return ok; });
         }
         HZ_CUDA(ctx, cudaMemcpyAsync(d_in.p, pin + off_in, bn, cudaMemcpyHostToDevice, ctx->stream));
         HZ_TRY(hz_encode(ctx, (const uint8_t*)d_in.p, bn, chunk_bytes, (uint8_t*)d_out.p, bn + 16,
                          (uint64_t*)d_off.p, (uint8_t*)d_len.p, nullptr));
         HZ_CUDA(ctx, cudaMemcpyAsync(pin + off_coff, d_off.p, (kb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         HZ_CUDA(ctx, cudaMemcpyAsync(pin + off_len, d_len.p, kb * 256, cudaMemcpyDeviceToHost, ctx->stream));
-        // SHA-256 of the plaintext chunks on the host while the GPU encodes (:226-228)
+        // SHA-256 of the plaintext chunks (:226-228): on the host while the GPU encodes, or — thousands of small
+        // chunks per batch — by the GPU kernel on the batch that is already in device memory
         std::vector<uint64_t> so(kb); std::vector<uint32_t> ss(kb); std::vector<uint8_t> dig(kb * 32);
         for (size_t i = 0; i < kb; ++i) { so[i] = (uint64_t)i * chunk_bytes; ss[i] = (uint32_t)std::min<uint64_t>(chunk_bytes, bn - so[i]); }
-        sha256_chunks_host(pin + off_in, so.data(), ss.data(), kb, dig.data());
+        if (kb >= kShaGpuMinChunks) {
+            HZ_TRY(hz_reserve(ctx, &ctx->stage_a, kb * 32));
+            HZ_TRY(hzk_sha256(ctx, (const uint8_t*)d_in.p, bn, chunk_bytes, (uint32_t)kb, (uint8_t*)ctx->stage_a.p));
+            HZ_CUDA(ctx, cudaMemcpyAsync(dig.data(), ctx->stage_a.p, kb * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            HostClock c; sha256_chunks_host(pin + off_in, so.data(), ss.data(), kb, dig.data()); ctx->stages.add(HZ_STAGE_CHECKSUM_COMPUTE, c.ms(), bn);
+        }
         HZ_TRY(hz_sync(ctx));
         const uint64_t* coff = (const uint64_t*)(pin + off_coff);
         const uint64_t btotal = coff[kb];
@@ -350,7 +411,8 @@ int compress_core(hz_ctx* ctx, const Source& src, Sink& dst, uint32_t chunk_byte
         HZ_CUDA(ctx, cudaMemcpyAsync(pin + off_out, d_out.p, btotal, cudaMemcpyDeviceToHost, ctx->stream));
         HZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (fut_wr.valid() && !fut_wr.get()) return hz_fail(ctx, HZ_ERR_IO, "write failed");
-        fut_wr = std::async(std::launch::async, [&dst, pin, off_out, btotal] { return dst.write(pin + off_out, btotal); });
+        fut_wr = std::async(std::launch::async, [&dst, &io, pin, off_out, btotal] {
+            HostClock c; const bool ok = dst.write(pin + off_out, btotal); io.add(c.ms(), btotal); return ok; });
         for (size_t i = 0; i < kb; ++i) {
             ChunkMeta& c = h.chunks[(size_t)k0 + i];
             c.index = (uint32_t)(k0 + i);
@@ -369,9 +431,12 @@ int compress_core(hz_ctx* ctx, const Source& src, Sink& dst, uint32_t chunk_byte
     std::vector<uint8_t> cat(32 * (size_t)K);
     for (size_t i = 0; i < (size_t)K; ++i) memcpy(&cat[32 * i], h.chunks[i].sha, 32);
     sha256_host(cat.data(), cat.size(), h.global);
+    HostClock hc;
     std::vector<uint8_t> footer;
     write_footer(h, comp_total, footer);
     if (!dst.write(footer.data(), footer.size())) return hz_fail(ctx, HZ_ERR_IO, "write failed (footer)");
+    ctx->stages.add(HZ_STAGE_HEADER_WRITE, hc.ms(), footer.size());                 // :178
+    ctx->stages.ms[HZ_STAGE_FILE_IO] += io.us / 1e3; ctx->stages.count[HZ_STAGE_FILE_IO] += io.count; ctx->stages.bytes[HZ_STAGE_FILE_IO] += io.bytes;
     return HZ_OK;
 }
 
@@ -414,7 +479,10 @@ int parse_container(hz_ctx* ctx, const Source& src, Header& h, uint64_t* data_st
 int decompress_core(hz_ctx* ctx, const Source& src, Sink* dst, hz_progress_fn progress, void* user) {
     HZ_CUDA(ctx, cudaSetDevice(ctx->device));
     Header h; uint64_t data_start = 0;
-    HZ_TRY(parse_container(ctx, src, h, &data_start));
+    IoAcc io;                                         // declared before the futures: the tasks reference it
+    StageScope scope(ctx, 0, true);
+    { HostClock c; const int prc = parse_container(ctx, src, h, &data_start); ctx->stages.add(HZ_STAGE_FILE_IO, c.ms(), 0); HZ_TRY(prc); }   // :395
+    scope.bytes = h.size;
     const size_t K = h.chunks.size();
     // batches of consecutive chunks, up to ~128 MiB of output each; two pinned slots [compressed][output]:
     // a reader task fetches batch b+1 while batch b is decoded and verified, a writer task drains batch b-1
@@ -435,16 +503,18 @@ int decompress_core(hz_ctx* ctx, const Source& src, Sink* dst, hz_progress_fn pr
     if (!batches.empty()) HZ_TRY(pin_reserve(ctx, slot_bytes * (batches.size() > 1 ? 2 : 1)));
     uint8_t* pin_base = (uint8_t*)ctx->h_pin;
     // the chunks of a batch are gathered back to back; consecutive chunks of a well-formed file are one extent
-    auto read_batch = [&src, &h, data_start](const Batch& B, uint8_t* dstp) -> long {
+    auto read_batch = [&src, &h, &io, data_start](const Batch& B, uint8_t* dstp) -> long {
+        HostClock clk;
         uint64_t ca = 0;
         size_t i = B.k0;
         while (i < B.k1) {
             size_t j = i; uint64_t ext = 0;
             const uint64_t start = h.chunks[i].compOff;
             while (j < B.k1 && h.chunks[j].compOff == start + ext) { ext += h.chunks[j].compSize; ++j; }
-            if (!src.read(data_start + start, dstp + ca, ext)) return (long)i;          // :429-436
+            if (start > UINT64_MAX - data_start || !src.read(data_start + start, dstp + ca, ext)) return (long)i;   // :429-436
             ca += ext; i = j;
         }
+        io.add(clk.ms(), ca);
         return -1;
     };
     std::future<long> fut_rd;
@@ -468,27 +538,51 @@ int decompress_core(hz_ctx* ctx, const Source& src, Sink* dst, hz_progress_fn pr
             ca += c.compSize; oa += c.origSize;
         }
         // this slot's output region was handed to the writer two batches ago; that write was joined last batch
-        int rc = hz_decode(ctx, pin + o_comp, B.cb, coff.data(), csz.data(), osz.data(), ooff.data(), lens.data(),
+        // thousands of equal-sized chunks: decode into device memory and hash them there (hz_sha256.cu), else through
+        // the host-buffer call (pipelined copies) and the host's SHA units
+        bool gpu_sha = kb >= kShaGpuMinChunks;
+        for (size_t i = 0; gpu_sha && i + 1 < kb; ++i) gpu_sha = osz[i] == osz[0];
+        if (gpu_sha && osz[kb - 1] > osz[0]) gpu_sha = false;
+        std::vector<uint8_t> dig(kb * 32);
+        int rc;
+        if (gpu_sha) {
+            rc = hz_reserve(ctx, &ctx->pipe_in[0], B.cb + 32);
+            if (rc == HZ_OK) rc = hz_reserve(ctx, &ctx->pipe_out[0], B.ob + 16);
+            if (rc == HZ_OK) rc = hz_reserve(ctx, &ctx->pipe_meta_d, kb * 32);
+            if (rc != HZ_OK) return rc;
+            HZ_CUDA(ctx, cudaMemcpyAsync(ctx->pipe_in[0].p, pin + o_comp, B.cb, cudaMemcpyHostToDevice, ctx->stream));
+            rc = hz_decode(ctx, (const uint8_t*)ctx->pipe_in[0].p, B.cb, coff.data(), csz.data(), osz.data(), ooff.data(), lens.data(),
+                           (uint32_t)kb, (uint8_t*)ctx->pipe_out[0].p, B.ob);
+            if (rc == HZ_OK) rc = hzk_sha256(ctx, (const uint8_t*)ctx->pipe_out[0].p, B.ob, osz[0], (uint32_t)kb, (uint8_t*)ctx->pipe_meta_d.p);
+            if (rc == HZ_OK) {
+                HZ_CUDA(ctx, cudaMemcpyAsync(dig.data(), ctx->pipe_meta_d.p, kb * 32, cudaMemcpyDeviceToHost, ctx->stream));
+                HZ_CUDA(ctx, cudaMemcpyAsync(pin + o_out, ctx->pipe_out[0].p, B.ob, cudaMemcpyDeviceToHost, ctx->stream));
+                rc = hz_sync(ctx);
+            }
+        } else {
+            rc = hz_decode(ctx, pin + o_comp, B.cb, coff.data(), csz.data(), osz.data(), ooff.data(), lens.data(),
                            (uint32_t)kb, pin + o_out, B.ob);
+        }
         if (rc != HZ_OK) {
             if (rc == HZ_ERR_DECODE || rc == HZ_ERR_BAD_LENGTHS)
                 return hz_fail(ctx, rc, "Chunk decompression failed: %s (chunks %zu..%zu)", hz_strerror(rc), k0, k1 - 1);
             return rc;
         }
-        std::vector<uint8_t> dig(kb * 32);
-        sha256_chunks_host(pin + o_out, ooff.data(), osz.data(), kb, dig.data());        // :536-550
+        if (!gpu_sha) { HostClock c; sha256_chunks_host(pin + o_out, ooff.data(), osz.data(), kb, dig.data()); ctx->stages.add(HZ_STAGE_CHECKSUM_VERIFY, c.ms(), B.ob); }   // :536-550
         for (size_t i = 0; i < kb; ++i)
             if (memcmp(&dig[32 * i], h.chunks[k0 + i].sha, 32) != 0)
                 return hz_fail(ctx, HZ_ERR_CHECKSUM, "Checksum mismatch in chunk %zu", k0 + i);
         if (dst) {
             if (fut_wr.valid() && !fut_wr.get()) return hz_fail(ctx, HZ_ERR_IO, "write failed");
             const uint64_t ob = B.ob;
-            fut_wr = std::async(std::launch::async, [dst, pin, o_out, ob] { return dst->write(pin + o_out, ob); });
+            fut_wr = std::async(std::launch::async, [dst, &io, pin, o_out, ob] {
+                HostClock c; const bool ok = dst->write(pin + o_out, ob); io.add(c.ms(), ob); return ok; });
         }
         for (size_t i = 0; i < kb; ++i)
             if (progress) progress((double)(++done) / (double)K, user);                  // :464-467
     }
     if (fut_wr.valid() && !fut_wr.get()) return hz_fail(ctx, HZ_ERR_IO, "write failed");
+    ctx->stages.ms[HZ_STAGE_FILE_IO] += io.us / 1e3; ctx->stages.count[HZ_STAGE_FILE_IO] += io.count; ctx->stages.bytes[HZ_STAGE_FILE_IO] += io.bytes;
     return HZ_OK;
 }
 
@@ -575,6 +669,18 @@ int hz_decompress_buffer(hz_ctx* ctx, const uint8_t* dcz, uint64_t n, uint8_t** 
 }
 
 void hz_free(void* p) { free(p); }
+
+int hz_stage_metrics(const hz_ctx* ctx, hz_stage_metric out[HZ_STAGE_COUNT]) {
+    if (!ctx || !out) return HZ_ERR_ARG;
+    for (int i = 0; i < HZ_STAGE_COUNT; ++i) { out[i].ms = ctx->stages.ms[i]; out[i].count = ctx->stages.count[i]; out[i].bytes = ctx->stages.bytes[i]; }
+    return HZ_OK;
+}
+
+const char* hz_stage_name(int stage) {
+    static const char* names[HZ_STAGE_COUNT] = {"FREQUENCY_ANALYSIS", "HUFFMAN_TREE_BUILD", "ENCODING", "CHECKSUM_COMPUTE",
+                                                "FILE_IO", "HEADER_WRITE", "DECODING", "CHECKSUM_VERIFY"};
+    return stage >= 0 && stage < HZ_STAGE_COUNT ? names[stage] : "";
+}
 
 // test hook: host SHA-256 (both the SHA-NI and the portable path are covered by tests)
 void hz_host_sha256(const uint8_t* data, uint64_t n, uint8_t* out32) { sha256_host(data, (size_t)n, out32); }

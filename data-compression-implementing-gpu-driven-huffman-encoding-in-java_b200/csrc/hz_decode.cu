@@ -80,16 +80,20 @@ struct DecPlan {
 __device__ __forceinline__ uint32_t ceil_div_u64(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
 __global__ void __launch_bounds__(1024)
-dec_plan_kernel(const uint32_t* __restrict__ comp_size, const uint32_t* __restrict__ orig_size,
-                const uint64_t* __restrict__ orig_off_in, uint32_t K, DecPlan P, uint32_t tab_min_seq,
-                const uint8_t* __restrict__ ident) {
+dec_plan_kernel(const uint64_t* __restrict__ comp_off, uint64_t comp_bytes, const uint32_t* __restrict__ comp_size,
+                const uint32_t* __restrict__ orig_size, const uint64_t* __restrict__ orig_off_in, uint32_t K, DecPlan P,
+                uint32_t tab_min_seq, uint8_t* __restrict__ ident, int* status) {
     __shared__ uint64_t part[6][1024];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (K + 1023) / 1024;
     const uint32_t lo = min(K, t * per), hi = min(K, lo + per);
     uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+    // a chunk must lie inside the addressable stream (untrusted footer fields reach this ABI): one that does not is
+    // skipped (no subsequences, no copy slices) and the call reports HZ_ERR_ARG
+    for (uint32_t i = lo; i < hi; ++i)
+        if (!(comp_off[i] <= comp_bytes && comp_size[i] <= comp_bytes - comp_off[i])) { ident[i] = 2; hz_set_status(status, HZ_ERR_ARG); }
     for (uint32_t i = lo; i < hi; ++i) {
-        s5 += ident[i] ? (orig_size[i] + DEC_IDENT_SLICE - 1) / DEC_IDENT_SLICE : 0u;
+        s5 += ident[i] == 1 ? (orig_size[i] + DEC_IDENT_SLICE - 1) / DEC_IDENT_SLICE : 0u;
         uint32_t ns = (orig_size[i] && !ident[i]) ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, DEC_SUB_BITS)) : 0;
         uint32_t nq = (ns + DT - 1) / DT;
         s0 += ns; s1 += nq; s2 += (nq + DEC_SEQ_PER_CTA - 1) / DEC_SEQ_PER_CTA; s3 += orig_size[i];
@@ -110,7 +114,7 @@ dec_plan_kernel(const uint32_t* __restrict__ comp_size, const uint32_t* __restri
     s0 = part[0][t]; s1 = part[1][t]; s2 = part[2][t]; s3 = part[3][t]; s4 = part[4][t]; s5 = part[5][t];
     for (uint32_t i = lo; i < hi; ++i) {
         P.islice[i] = (uint32_t)s5;
-        s5 += ident[i] ? (orig_size[i] + DEC_IDENT_SLICE - 1) / DEC_IDENT_SLICE : 0u;
+        s5 += ident[i] == 1 ? (orig_size[i] + DEC_IDENT_SLICE - 1) / DEC_IDENT_SLICE : 0u;
         uint32_t ns = (orig_size[i] && !ident[i]) ? max(1u, ceil_div_u64((uint64_t)comp_size[i] * 8, DEC_SUB_BITS)) : 0;
         uint32_t nq = (ns + DT - 1) / DT;
         P.nsub[i] = ns; P.sub_base[i] = (uint32_t)s0; P.seq_base[i] = (uint32_t)s1; P.cta_base[i] = (uint32_t)s2;
@@ -1064,7 +1068,8 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
                   d_orig_size, p_orig_off, p_islice, K, d_out, out_cap, ctx->d_status);
         return HZ_OK;
     }
-    HZ_LAUNCH(ctx, "dec_plan", dec_plan_kernel, 1, 1024, 0, d_comp_size, d_orig_size, d_orig_off, K, P, tab_min_seq, ident);
+    HZ_LAUNCH(ctx, "dec_plan", dec_plan_kernel, 1, 1024, 0, d_comp_off, comp_bytes, d_comp_size, d_orig_size, d_orig_off, K, P,
+              tab_min_seq, ident, ctx->d_status);
     // upper bounds (no host sync): every chunk has at most ceil(comp_size*8/SUB_BITS)+1 subsequences
     const uint64_t max_sub = comp_bytes * 8 / DEC_SUB_BITS + 2ull * K + 2;
     const uint64_t max_seq = max_sub / DT + K + 1;

@@ -1,5 +1,6 @@
 package com.datacomp.service.b200;
 
+import com.datacomp.model.StageMetrics;
 import com.datacomp.service.CompressionService;
 
 import java.io.IOException;
@@ -9,12 +10,17 @@ import java.nio.file.Path;
 import java.util.function.Consumer;
 
 import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_DOUBLE;
 import static java.lang.foreign.ValueLayout.JAVA_INT;
+import static java.lang.foreign.ValueLayout.JAVA_LONG;
 
 /**
- * CompressionService (service/CompressionService.java:11-66) backed by libhuffb200.so: the whole
- * per-chunk pipeline (histogram, canonical codebook, bit-packed encode, chunked decode, SHA-256)
- * runs on the B200; the .dcz written is byte-identical to CpuCompressionService's
+ * CompressionService (service/CompressionService.java:11-66) backed by libhuffb200.so: the per-chunk
+ * hot path (histogram, canonical codebook, bit-packed encode, chunked decode) runs on the B200; the
+ * per-chunk SHA-256 of the file calls is computed by the library on the HOST's SHA units while the GPU
+ * codes the same batch (a handful of 16-32 MiB chunks per batch hash faster there than on the GPU, whose
+ * kernel, hz_sha256_chunks, only wins with hundreds of chunks per batch); the .dcz written is
+ * byte-identical to CpuCompressionService's
  * (service/cpu/CpuCompressionService.java:57-205) for the same input, chunk size, file name and
  * modification time.  Constructor mirrors CpuCompressionService(int chunkSizeMB) (:36-47);
  * withChunkBytes() adds the bytes-granular chunk size of the 64 KiB - 4 MiB sweeps.
@@ -95,6 +101,30 @@ public final class B200CompressionService implements CompressionService, AutoClo
         } catch (Throwable t) {
             throw new IOException(t);
         }
+    }
+
+    /**
+     * Stage timings of the last compress / decompress / verifyIntegrity call, as the reference's services expose
+     * them (cpu/CpuCompressionService.java:52; the GUI reaches it by an instanceof cast,
+     * ui/CompressController.java:292-297): hz_stage_metrics fills one {double ms, uint64 count, uint64 bytes}
+     * per StageMetrics.Stage constant, in declaration order (model/StageMetrics.java:11-20).
+     */
+    public synchronized StageMetrics getLastStageMetrics() {
+        StageMetrics m = new StageMetrics();
+        try (Arena a = Arena.ofConfined()) {
+            StageMetrics.Stage[] stages = StageMetrics.Stage.values();
+            MemorySegment buf = a.allocate(24L * stages.length, 8);
+            int rc = (int) HuffB200.hz_stage_metrics.invokeExact(ctx, buf);
+            if (rc != HuffB200.HZ_OK) return m;
+            for (int i = 0; i < stages.length; i++) {
+                double ms = buf.get(JAVA_DOUBLE, 24L * i);
+                long count = buf.get(JAVA_LONG, 24L * i + 8), bytes = buf.get(JAVA_LONG, 24L * i + 16);
+                if (count > 0) m.recordStage(stages[i], (long) (ms * 1e6), bytes);
+            }
+        } catch (Throwable t) {
+            // metrics are best effort, like the reference's
+        }
+        return m;
     }
 
     @Override

@@ -70,6 +70,15 @@ final class HuffB200 {
     static final MethodHandle hz_verify_file = h("hz_verify_file",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
 
+    // int hz_stage_metrics(const hz_ctx*, hz_stage_metric out[8])   {double ms; uint64_t count; uint64_t bytes;}
+    static final MethodHandle hz_stage_metrics = h("hz_stage_metrics", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    // int hz_encode_global(hz_ctx*, in, n, chunk_bytes, out, out_cap, comp_off, len256_out)   (multi-GPU extension mode)
+    static final MethodHandle hz_encode_global = h("hz_encode_global", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS,
+            JAVA_LONG, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS));
+    // int hz_comm_unique_id(void* id128); int hz_comm_init(hz_ctx*, const void* id128, int nranks, int rank)
+    static final MethodHandle hz_comm_unique_id = h("hz_comm_unique_id", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle hz_comm_init = h("hz_comm_init", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
+
     /** typedef void (*hz_progress_fn)(double fraction, void* user) */
     static final FunctionDescriptor PROGRESS_FN = FunctionDescriptor.ofVoid(JAVA_DOUBLE, ADDRESS);
 

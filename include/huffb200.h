@@ -168,6 +168,26 @@ int hz_compress_buffer(hz_ctx* ctx, const uint8_t* data, uint64_t n, uint32_t ch
 int hz_decompress_buffer(hz_ctx* ctx, const uint8_t* dcz, uint64_t n, uint8_t** out, uint64_t* out_n);
 void hz_free(void* p);
 
+/* Stage timings of the LAST file- or buffer-level call (hz_compress_file, hz_decompress_file, hz_verify_file,
+ * hz_compress_buffer, hz_decompress_buffer), one entry per model/StageMetrics.Stage constant in declaration order
+ * (model/StageMetrics.java:11-20).  Replaces getLastStageMetrics() of the service classes
+ * (cpu/CpuCompressionService.java:52, reached from ui/CompressController.java:292-297): the Java shim feeds every
+ * entry to StageMetrics.recordStage(stage, ns, bytes).  Kernel stages are CUDA-event times of the kernels that do
+ * that stage's work (histogram; codebook build and decode-table rebuild; bit packing; decode); checksum and file
+ * I/O are host wall-clock times of the pipeline's tasks (they overlap with the GPU stages).                  */
+#define HZ_STAGE_FREQUENCY_ANALYSIS 0
+#define HZ_STAGE_HUFFMAN_TREE_BUILD 1
+#define HZ_STAGE_ENCODING 2
+#define HZ_STAGE_CHECKSUM_COMPUTE 3
+#define HZ_STAGE_FILE_IO 4
+#define HZ_STAGE_HEADER_WRITE 5
+#define HZ_STAGE_DECODING 6
+#define HZ_STAGE_CHECKSUM_VERIFY 7
+#define HZ_STAGE_COUNT 8
+typedef struct hz_stage_metric { double ms; uint64_t count; uint64_t bytes; } hz_stage_metric;
+int hz_stage_metrics(const hz_ctx* ctx, hz_stage_metric out[HZ_STAGE_COUNT]);
+const char* hz_stage_name(int stage);               /* "FREQUENCY_ANALYSIS", ... (the enum constant's name) */
+
 /* ---- introspection for the bench harness --------------------------------------------------- */
 
 /* Names and accumulated CUDA-event milliseconds / launch counts of the library's kernels since

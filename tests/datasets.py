@@ -28,14 +28,24 @@ def reference_cases():
     ]
 
 
+TEST_INPUT_SHA256 = "fcd8ad1070c6f303848f387385e8f1204be2e2b1a832ea8ce7c12d3ec983c37d"
+
+
 def fixture_bytes(name):
-    """The reference's three binary fixtures, regenerated (they are trivially describable):
-    test_small.bin = 2048 x 'A', test_2mb.bin = 2 MiB x 'A'; test_input.bin (1 MiB uniform random,
-    every code length 8) is represented by its committed SHA-256 and a same-shape stand-in."""
+    """The reference's three binary fixtures: test_small.bin = 2048 x 'A' and test_2mb.bin = 2 MiB x 'A' are
+    regenerated (trivially describable); test_input.bin (1 MiB, all 256 byte values, order-0 entropy 7.9998 bits:
+    every code length is 8) is the reference's own file, committed as tests/golden/test_input.bin and pinned by
+    its SHA-256 (service/gpu/Phase3IntegrationTest.java:148-195 uses it)."""
     if name == "test_small.bin":
         return b"A" * 2048
     if name == "test_2mb.bin":
         return b"A" * (2 * MiB)
+    if name == "test_input.bin":
+        import hashlib
+        with open(os.path.join(GOLDEN_DIR, "test_input.bin"), "rb") as f:
+            d = f.read()
+        assert hashlib.sha256(d).hexdigest() == TEST_INPUT_SHA256, "tests/golden/test_input.bin is not the reference's fixture"
+        return d
     raise KeyError(name)
 
 

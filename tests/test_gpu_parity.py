@@ -154,8 +154,16 @@ def test_fixtures(codec, decmode):
         assert not payload.any() and payload.size == 262144
     payload, _, lens = check_encode(codec, datasets.fixture_bytes("test_small.bin"), 32 * MiB)
     assert payload.size == 256 and lens[0, 65] == 1
-    uni = orc.java_random_bytes(7, 1 * MiB)                     # stand-in for test_input.bin
-    check_encode(codec, uni, 16 * MiB)
+    # test_input.bin, the reference's own 1 MiB fixture: all 256 code lengths are 8, so code[s] == s and the payload
+    # IS the input; .dcz = payload + 68 + len(name) + 572 + 8 bytes
+    uni = np.frombuffer(datasets.fixture_bytes("test_input.bin"), dtype=np.uint8)
+    for chunk in (16 * MiB, 32 * MiB):
+        payload, _, lens = check_encode(codec, uni, chunk)
+        assert (lens[0] == 8).all() and np.array_equal(payload, uni)
+    z = codec.compress_buffer(uni, 16 * MiB, "test_input.bin", 0)
+    assert len(z) == 1048576 + 68 + len("test_input.bin") + 572 + 8 and z == orc.compress(uni, 16 * MiB, "test_input.bin", 0)
+    assert codec.decompress_buffer(z) == uni.tobytes()
+    check_encode(codec, orc.java_random_bytes(7, 1 * MiB), 16 * MiB)
 
 
 @pytest.mark.parametrize("entropy", [1, 2, 3, 4, 5, 6, 7, 8])
@@ -306,6 +314,28 @@ def test_global_codebook_extension(codec):
     assert np.array_equal(back, data)
 
 
+def test_stage_metrics_of_the_file_calls(codec, hz):
+    """getLastStageMetrics() (cpu/CpuCompressionService.java:52): after compress the stages of
+    model/StageMetrics.java:11-20 that the reference records there carry time, after decompress those it records
+    there; names and order are the enum's."""
+    data = datasets.zipf_stream(5 * MiB + 3, 4, seed=21)
+    z = codec.compress_buffer(data, MiB, "m.bin", 0)
+    m = codec.stage_metrics()
+    assert list(m) == ["FREQUENCY_ANALYSIS", "HUFFMAN_TREE_BUILD", "ENCODING", "CHECKSUM_COMPUTE", "FILE_IO", "HEADER_WRITE",
+                       "DECODING", "CHECKSUM_VERIFY"]
+    for st in ("FREQUENCY_ANALYSIS", "HUFFMAN_TREE_BUILD", "ENCODING", "CHECKSUM_COMPUTE", "FILE_IO", "HEADER_WRITE"):
+        assert m[st][0] > 0 and m[st][1] > 0, st
+    assert m["DECODING"][1] == 0 and m["ENCODING"][2] == data.size and m["CHECKSUM_COMPUTE"][2] == data.size
+    assert codec.decompress_buffer(z) == data.tobytes()
+    m = codec.stage_metrics()
+    for st in ("HUFFMAN_TREE_BUILD", "DECODING", "CHECKSUM_VERIFY", "FILE_IO"):
+        assert m[st][0] > 0 and m[st][1] > 0, st
+    assert m["ENCODING"][1] == 0 and m["DECODING"][2] == data.size
+    svc = hz.B200CompressionService.__new__(hz.B200CompressionService)
+    svc._codec = codec
+    assert svc.get_last_stage_metrics() == m
+
+
 def test_encode_global_in_library(codec):
     """hz_encode_global (one histogram pass, device-side reduction, codebook and encode in one call; the NCCL
     all-reduce is skipped without a communicator) == histogram + hz_build_codebooks + hz_encode_with_lengths, and
@@ -387,6 +417,66 @@ def test_service_files_multi_batch(hz, tmp_path, n, chunk_mib):
         assert not svc.verify_integrity(str(tmp_path / "bad.dcz"))
 
 
+def test_container_thousands_of_small_chunks_hash_on_the_gpu(codec, hz):
+    """>= 1536 chunks per batch: the per-chunk SHA-256 comes from the GPU kernel (compress: on the batch already in
+    device memory; decompress / verify: on the decoded batch before it leaves the device).  The container must still
+    be the oracle's byte for byte, a flipped payload byte must still be caught, and the ragged last chunk counts."""
+    data = datasets.zipf_stream(40 * MiB + 1234, 5, seed=31).tobytes()
+    chunk = 16 * 1024
+    z = codec.compress_buffer(data, chunk, "small.bin", 7)
+    assert z == orc.compress(data, chunk, "small.bin", 7)
+    m = codec.stage_metrics()
+    assert m["CHECKSUM_COMPUTE"][0] > 0
+    assert codec.decompress_buffer(z) == data
+    assert codec.stage_metrics()["CHECKSUM_VERIFY"][0] > 0
+    bad = bytearray(z); bad[12345] ^= 1
+    with pytest.raises(hz.HzError) as e:
+        codec.decompress_buffer(bytes(bad))
+    assert e.value.status in (hz.HZ_ERR_CHECKSUM, hz.HZ_ERR_DECODE)
+
+
+def test_untrusted_metadata_is_rejected_not_followed(codec, decmode, hz):
+    """Chunk offsets / sizes reach hz_decode from a footer nobody vouches for: a chunk that does not lie inside the
+    stream is reported (HZ_ERR_ARG) instead of being read; the context stays usable.  Same for a footer whose
+    compressedOffset wraps around 2^64 (buffer API)."""
+    data = datasets.zipf_stream(600_000, 4, seed=8)
+    payload, off, lens = codec.encode(data, 200_000)[:3]
+    sizes = np.diff(off).astype(np.uint32)
+    orig = np.full(3, 200_000, np.uint32)
+    for bad_off, bad_size in (([0, int(off[1]), payload.size - 10], sizes), (off[:-1], [sizes[0], sizes[1], sizes[2] + 4096]),
+                              ([0, 2**63, int(off[2])], sizes)):
+        with pytest.raises(hz.HzError) as e:
+            codec.decode(payload, np.array(bad_off, dtype=np.uint64), np.array(bad_size, dtype=np.uint32), orig, lens)
+        assert e.value.status == hz.HZ_ERR_ARG
+    assert np.array_equal(codec.decode(payload, off[:-1], sizes, orig, lens), data)
+    z = bytearray(orc.compress(data.tobytes(), 200_000, "x.bin", 0))
+    fo = int.from_bytes(z[-8:], "big")
+    rec0 = fo + 4 + 4 + 4 + 5 + 8 + 8 + 4 + 32 + 4            # first chunk record (name "x.bin")
+    z[rec0 + 16: rec0 + 24] = (2**64 - 8).to_bytes(8, "big")   # compressedOffset of chunk 0
+    with pytest.raises(hz.HzError):
+        codec.decompress_buffer(bytes(z))
+
+
+def test_fixed_length_encode_of_a_large_host_buffer_may_expand(codec):
+    """hz_encode_with_lengths on >= 128 MiB of HOST data takes the pipelined path; a table built for other data can
+    expand a batch beyond its input size (here 9/8): the slots must hold that, and the result must equal the
+    device-resident path's."""
+    import torch
+    n, chunk = 160 * MiB, 4 * MiB
+    lens256 = np.full(256, 9, dtype=np.uint8)        # 256 x 9 bits (Kraft sum 0.5): every byte costs 9 bits
+    data = datasets.zipf_stream(n, 8, seed=4)
+    payload, off = codec.encode_with_lengths(data, chunk, lens256)                   # host path (pipelined)
+    assert int(off[-1]) == payload.size > n
+    d = torch.from_numpy(data).cuda()
+    K = len(off) - 1
+    out = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    doff = torch.zeros(K + 1, dtype=torch.int64, device="cuda")
+    codec.encode_with_lengths_raw(d.data_ptr(), n, chunk, torch.from_numpy(lens256).cuda().data_ptr(), out.data_ptr(), 2 * n, doff.data_ptr())
+    codec.sync()
+    assert np.array_equal(doff.cpu().numpy().astype(np.uint64), off)
+    assert np.array_equal(out[: int(off[-1])].cpu().numpy(), payload)
+
+
 def test_legacy_header_first_layout(codec):
     data = b"Hello World! " * 100
     z = orc.compress(data, MiB, "t.txt", 5)
@@ -424,6 +514,39 @@ def test_large_device_resident_roundtrip(codec):
         ref, ln, _ = orc.encode_chunk(src[k * chunk:(k + 1) * chunk].cpu().numpy())
         assert np.array_equal(lens[k].cpu().numpy(), ln.astype(np.uint8))
         assert np.array_equal(comp[int(offh[k]):int(offh[k + 1])].cpu().numpy(), ref)
+    sizes = (off[1:] - off[:-1]).to(torch.int32)
+    orig = torch.full((K,), chunk, dtype=torch.int32, device="cuda")
+    back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    codec.decode_raw(comp.data_ptr(), int(offh[K]), off.data_ptr(), sizes.data_ptr(), orig.data_ptr(), None,
+                     lens.data_ptr(), K, back.data_ptr(), n)
+    codec.sync()
+    assert torch.equal(back, src)
+
+
+def test_config3_1gib_32mib_chunks_every_chunk_against_the_oracle(codec):
+    """BASELINE config 3 (1 GiB Zipf, ~4 bits/symbol) at the CLI's default chunk size of 32 MiB: code lengths,
+    compressed sizes and the SHA-256 of EVERY chunk's payload equal the oracle's (chunk-parallel fast coder), and
+    the stream decodes back."""
+    import torch
+    n, chunk = 1024 * MiB, 32 * MiB
+    K = n // chunk
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    codec.synth_fill(src.data_ptr(), n, 0, 0x5EED0003, datasets.zipf_qtable(4))
+    comp = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(K + 1, dtype=torch.int64, device="cuda")
+    lens = torch.zeros((K, 256), dtype=torch.uint8, device="cuda")
+    codec.encode_raw(src.data_ptr(), n, chunk, comp.data_ptr(), n, off.data_ptr(), lens.data_ptr(), None)
+    codec.sync()
+    offh = off.cpu().numpy().astype(np.uint64)
+    host = src.cpu().numpy()
+    rcomp, rsizes, rlens, _ = orc.encode_chunks_mt(host, chunk, literal=False)
+    assert np.array_equal(np.diff(offh).astype(np.uint64), np.asarray(rsizes, dtype=np.uint64))
+    assert np.array_equal(lens.cpu().numpy(), np.asarray(rlens, dtype=np.uint8).reshape(K, 256))
+    got = comp[: int(offh[K])].cpu().numpy()
+    for k in range(K):                                   # the oracle's chunk k sits at k * (chunk + 8)
+        a = hashlib.sha256(got[int(offh[k]):int(offh[k + 1])]).digest()
+        b = hashlib.sha256(rcomp[k * (chunk + 8): k * (chunk + 8) + int(rsizes[k])]).digest()
+        assert a == b, "payload of chunk %d" % k
     sizes = (off[1:] - off[:-1]).to(torch.int32)
     orig = torch.full((K,), chunk, dtype=torch.int32, device="cuda")
     back = torch.zeros(n, dtype=torch.uint8, device="cuda")

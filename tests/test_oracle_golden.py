@@ -125,6 +125,39 @@ def test_fixtures():
     assert len(z) == 262144 + 80 + 572 + 8
     z = orc.compress(datasets.fixture_bytes("test_2mb.bin"), 1 * datasets.MiB, "test_2mb.bin", 0)
     assert int.from_bytes(z[-8:], "big") == 2 * 131072
+    # test_input.bin (the reference's file itself): every length 8 -> canonical code[s] == s -> payload == input
+    d = np.frombuffer(datasets.fixture_bytes("test_input.bin"), dtype=np.uint8)
+    p, ln, _ = orc.encode_chunk(d)
+    assert (ln == 8).all() and np.array_equal(p, d)
+    z = orc.compress(d, 16 * datasets.MiB, "test_input.bin", 0)
+    assert len(z) == 1048576 + 68 + 14 + 572 + 8 and z[:1048576] == d.tobytes()
+    assert orc.decompress(z) == d.tobytes()
+
+
+def test_literal_and_fast_decoders_agree_on_damaged_streams():
+    """The GPU parity tests compare damaged streams with the oracle's word-at-a-time decoder; this pins that decoder to
+    the literal restatement of TableBasedHuffmanDecoder (one-bit peeks, 10-bit table, bit-by-bit fallback:
+    core/TableBasedHuffmanDecoder.java:103-152,180-231) on exactly such inputs: flipped bits, truncated payloads
+    (zero bits past the end, :204-208) and a short orig_size, for short and long codes."""
+    rng = np.random.default_rng(2026)
+    n = 60_000
+    for H in (1, 2, 4, 5, 7):
+        data = datasets.zipf_stream(n, H, seed=H + 90)
+        p, ln, _ = orc.encode_chunk(data)
+        ln = ln.astype(np.int32)
+        for trial in range(6):
+            bad = p.copy()
+            for f in rng.integers(0, bad.size * 8, 12):
+                bad[f >> 3] ^= 0x80 >> (f & 7)
+            bad = bad[: bad.size - int(rng.integers(0, 4))]
+            n_out = n - int(rng.integers(0, 3)) * 500
+            a, ra = orc.decode(bad, ln, n_out, literal=True)
+            b, rb = orc.decode(bad, ln, n_out, literal=False)
+            assert ra == rb and np.array_equal(a, b), "H=%d trial %d" % (H, trial)
+    # an incomplete code (one symbol): a stray 1 bit is an error for both
+    one = np.zeros(256, dtype=np.int32); one[65] = 1
+    comp = np.zeros(8, dtype=np.uint8); comp[3] = 0x10
+    assert orc.decode(comp, one, 40, literal=True)[1] == orc.decode(comp, one, 40, literal=False)[1] != 0
 
 
 def test_decode_literal_vs_fast_and_long_codes():
