@@ -558,6 +558,13 @@ __device__ __forceinline__ uint32_t fu_one(const DecAux& A, uint32_t wlut_a, uin
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+// -DFU_CHECK (developer build; compute-sanitizer is closed on the B200 pool): bounds assertions of our own on every
+// shared-memory region and global range the kernel addresses; a violation prints once per thread and latches HZ_ERR_CUDA
+#ifdef FU_CHECK
+#define FU_ASSERT(cond, what) do { if (!(cond)) { printf("FU_CHECK %s failed: block %d thread %d\n", what, (int)blockIdx.x, (int)threadIdx.x); hz_set_status(a.status, HZ_ERR_CUDA); } } while (0)
+#else
+#define FU_ASSERT(cond, what) do { } while (0)
+#endif
 // -DFU_TIMING (developer build): per-phase clock64 totals over all warps, printed by the launcher
 #ifdef FU_TIMING
 #define FU_T(i) do { const long long now__ = clock64(); tim__[i] += now__ - last__; last__ = now__; } while (0)
@@ -664,6 +671,9 @@ dec_fused_kernel(const FuArgs a) {
         if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
         while (u < nunit) {
             const UnitGeom g = fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw);
+            FU_ASSERT(g.need > 0 && g.need <= FU_STAGE_BYTES && g.tlo >= 0 && g.tlo <= g.thi && g.thi <= g.need && (g.tlo & 15) == 0 && (g.thi & 15) == 0, "stage geometry");
+            FU_ASSERT(g.a0 + (uint64_t)g.tlo >= (reinterpret_cast<uint64_t>(a.comp) & ~15ull) && g.a0 + (uint64_t)g.thi <= reinterpret_cast<uint64_t>(a.comp) + a.comp_bytes, "bulk copy inside the stream");
+            FU_ASSERT(g.bit0 >= lead * 32 && g.bit0 / 8 + 128 * Sw + 32 <= (uint32_t)g.need + 15, "unit inside the stage");
             FU_T(0);
             fu_mbar_wait(bar_a, phase); phase ^= 1;
             FU_T(1);
@@ -707,6 +717,8 @@ dec_fused_kernel(const FuArgs a) {
                     FU_T(7);
                     fu_walk(C, r, Cend, wlut_a, acc, sp, Cb, exl, badc, ovf);
                     FU_T(3);
+                    FU_ASSERT(sp >= rows_a + lane * 4 && sp <= rows_a + lane * 4 + (FU_ROW_WORDS - 1) * 128, "row pointer");
+                    FU_ASSERT(r.wa >= stage_a && r.wa + 4 < stage_a + (uint32_t)g.need, "reader inside the stage");
                     if (ovf) fu_skim(C, r, Cend, wlut_a, Cb, exl);
                     else sts32(sp, acc);                  // bytes still in the accumulator (the row has two guard words)
                     C = fu_settle(C, Cb, exl, end - org, aux_a);
@@ -780,6 +792,7 @@ dec_fused_kernel(const FuArgs a) {
             } else {
                 if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
                 const uint32_t T = warp_sum(cw);
+                FU_ASSERT(T == 0 || (T <= 32 * FU_CAP_SYMS && (uint64_t)prefix + T <= osize && ooff + prefix + T <= a.out_cap), "window inside the output");
                 if (T) {
                     const uint32_t first = __shfl_sync(0xffffffffu, obase, 0);
                     const uint64_t g0 = gout + first;                     // global address of the window's first symbol
@@ -800,6 +813,7 @@ dec_fused_kernel(const FuArgs a) {
                         }
                     }
                     __syncwarp();
+                    FU_ASSERT((cw == 0 || d + cw <= 15 + T) && 15 + T + 4 <= FU_ROWS_BYTES, "window inside the rows");
                     const uint32_t bs = (d & 3) * 8;
                     const uint32_t w0 = rows_a + (d & ~3u);               // window word that holds the first symbol
                     for (uint32_t j = 0; j < hn; ++j) sts8(w0 + (d & 3) + j, rw[0] >> (8 * j));
