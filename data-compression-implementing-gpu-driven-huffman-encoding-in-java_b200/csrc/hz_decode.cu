@@ -293,27 +293,13 @@ struct SyncSmem {
 };
 
 
-// Right shifts inside the hand-written loops.  -DHZ_DEC_FMA_SHIFTS (A/B variant for the next GPU session, never the
-// default) takes them as hi32(x * 2^(32 - s)) on the FMA pipe: both loops are bound
-// by the half-rate integer ALU pipe (sync 73 %, write 63 % busy) while the FMA pipe idles.
-#if defined(HZ_DEC_FMA_SHIFTS) && HZ_DEC_FMA_SHIFTS >= 1
-#define HZ_SHR20(D, S) "mul.hi.u32 " D ", " S ", 4096;\n"
-#define HZ_SHR16(D, S) "mul.hi.u32 " D ", " S ", 65536;\n"
-#define HZ_SHR12(D, S) "mul.hi.u32 " D ", " S ", 1048576;\n"
-#else
+// Right shifts inside the hand-written loops stay SHF: taking them as hi32(x * 2^(32 - s)) on the FMA pipe was
+// measured on B200 and rejected (dec_sync 1.93 -> 2.12 ms, dec_write 3.66 -> 3.71 ms).
 #define HZ_SHR20(D, S) "shr.u32 " D ", " S ", 20;\n"
 #define HZ_SHR16(D, S) "shr.u32 " D ", " S ", 16;\n"
 #define HZ_SHR12(D, S) "shr.u32 " D ", " S ", 12;\n"
-#endif
-// Level 2 (-DHZ_DEC_FMA_SHIFTS=2) also advances the reader / writer pointers with a multiply-add by a 2 that ptxas
-// cannot fold (TWO = the operand holding 2 * gridDim.y; grids are one-dimensional).
-#if defined(HZ_DEC_FMA_SHIFTS) && HZ_DEC_FMA_SHIFTS >= 2
-#define HZ_ADD4(PRED, R, TWO) PRED " mad.lo.u32 " R ", " TWO ", 2, " R ";\n"
-#define HZ_W_TWO_OPERAND , "r"(2u * gridDim.y)
-#else
 #define HZ_ADD4(PRED, R, TWO) PRED " add.u32 " R ", " R ", 4;\n"
 #define HZ_W_TWO_OPERAND
-#endif
 
 // Advance from `pos` to the first codeword boundary >= limit; returns the number of codewords
 // that began before `limit`.  Unmatched patterns consume one bit.

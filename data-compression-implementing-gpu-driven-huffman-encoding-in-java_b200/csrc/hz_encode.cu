@@ -234,13 +234,7 @@ __device__ __forceinline__ void acc_pair(Acc& a, uint32_t e0, uint32_t e1) {
     const uint32_t nb2 = a.nb + e0 + e1;
     if ((a.nb ^ nb2) & 32) {                                 // <= 32 bits were added: at most one word completes
         enc_sts32(a.ptr, __funnelshift_r(a.lo, a.hi, nb2));  // the 32 bits above the (nb2 & 31) pending ones
-#if defined(HZ_ENC_IMAD_EXTRACT) && HZ_ENC_IMAD_EXTRACT >= 3
-        // A/B level 3: the row pointer advances on the FMA pipe too (blockDim.x / ENC_CTA is 1, but not for ptxas,
-        // so the multiply-add stays an IMAD instead of becoming an ALU-pipe add)
-        asm("mad.lo.u32 %0, %1, 4, %0;" : "+r"(a.ptr) : "r"(blockDim.x / ENC_CTA));
-#else
         a.ptr += 4;
-#endif
     }
     a.nb = nb2;
 }
@@ -248,27 +242,8 @@ __device__ __forceinline__ void acc_pair(Acc& a, uint32_t e0, uint32_t e1) {
 // LUT address of byte J of x: lut[sym][lane]
 template <int J>
 __device__ __forceinline__ uint32_t lut_addr(uint32_t x, uint32_t lanebase) {
-#if defined(HZ_ENC_IMAD_EXTRACT)
-    // A/B variant for the next GPU session (never the default): the kernel is bound by
-    // the half-rate ALU pipe, and PRMT is one of its 5 ALU instructions per symbol.  The byte can be taken on the
-    // FMA pipe instead: byte 0 = hi32((x << 24) * 2^15) >> 7 folded into the address multiply-add, byte J =
-    // hi32((x << (24 - 8J)) * 2^8).  Level 1 converts bytes 0 and 3 (same instruction count), level 2 all four,
-    // level 3 also advances the private-row pointer with an IMAD (acc_pair).
-    if (J == 0) {
-        uint32_t t, a;
-        asm("mul.lo.u32 %0, %1, 16777216;" : "=r"(t) : "r"(x));                         // x << 24: only byte 0 left
-        asm("mad.hi.u32 %0, %1, 32768, %2;" : "=r"(a) : "r"(t), "r"(lanebase));         // byte0 * 128 + lanebase
-        return a;
-    }
-    if (J == 3 || HZ_ENC_IMAD_EXTRACT >= 2) {
-        uint32_t t = x, sym, a;
-        if (J == 1) asm("mul.lo.u32 %0, %1, 65536;" : "=r"(t) : "r"(x));
-        if (J == 2) asm("mul.lo.u32 %0, %1, 256;" : "=r"(t) : "r"(x));
-        asm("mul.hi.u32 %0, %1, 256;" : "=r"(sym) : "r"(t));                            // the top byte, exactly
-        asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(sym), "r"(lanebase));
-        return a;
-    }
-#endif
+    // (taking the byte on the FMA pipe instead - IMAD.HI by a power of two - was measured on B200 and rejected:
+    //  encode_kernel 2.174 -> 2.163 ms for bytes 0 and 3, 2.275 ms for all four)
     const uint32_t sym = __byte_perm(x, 0, 0x4440 + J);
     uint32_t a;
     asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(sym), "r"(lanebase));
