@@ -766,6 +766,7 @@ dec_fused_kernel(const FuArgs a) {
             const uint32_t obase = prefix + rel;                           // chunk-relative index of the lane's first symbol
             const uint32_t cw = obase >= osize ? 0u : min(count, osize - obase);   // symbols of this lane that exist
             const bool over = __any_sync(0xffffffffu, count > FU_CAP_SYMS);
+            uint32_t tk = 0; bool tk_drawn = false;                            // the next unit's ticket (lane 0)
             if (badc != 0xFFFFFFFFu && obase + ((badc - FU_OUT_BIAS) >> 3) < osize) hz_set_status(a.status, HZ_ERR_DECODE);
             if (over) {
                 // a row overflowed (far more symbols than the chunk's average in one subsequence): every lane
@@ -808,6 +809,10 @@ dec_fused_kernel(const FuArgs a) {
                         }
                     }
                     __syncwarp();
+                    // the rows are in registers: draw the next ticket now, its round trip runs under the stores below
+                    // (about a third of a microsecond before the last possible moment, see the note at the loop's end)
+                    if (lane == 0) tk = atomicAdd(a.P.unit_ctr + k, 1u);
+                    tk_drawn = true;
                     FU_ASSERT((cw == 0 || d + cw <= 15 + T) && 15 + T + 4 <= FU_ROWS_BYTES, "window inside the rows");
                     const uint32_t bs = (d & 3) * 8;
                     const uint32_t w0 = rows_a + (d & ~3u);               // window word that holds the first symbol
@@ -856,8 +861,8 @@ dec_fused_kernel(const FuArgs a) {
             // publishing that unit's record delays all the warps behind it.  Drawing the ticket before the output
             // phase (to hide the fetch behind it) measured 1.4 % slower, drawing it a whole unit ahead 33 % slower, and handing
             // tickets out of a per-CTA pool of blocks drawn ahead 5 % slower (30 % where CTAs share a chunk).
-            if (lane == 0) u = atomicAdd(a.P.unit_ctr + k, 1u);
-            u = __shfl_sync(0xffffffffu, u, 0);
+            if (!tk_drawn && lane == 0) tk = atomicAdd(a.P.unit_ctr + k, 1u);
+            u = __shfl_sync(0xffffffffu, tk, 0);
             if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
             // the chunk's last unit: when the stream holds fewer symbols than orig_size the decoder goes on reading
             // zero bits (TableBasedHuffmanDecoder.java:204-208), i.e. the all-zero codeword's symbol repeats
