@@ -8,7 +8,7 @@
 // subsequences of S 32-bit words (S per chunk, so that a subsequence holds ~128 symbols); 32 consecutive
 // subsequences form a UNIT, the work item of one warp.  A warp
 //   1. receives its unit's bytes by a 1-D TMA bulk copy into its private stage (cp.async.bulk + mbarrier),
-//      byte-swaps them in place (the bit reader then needs no PRMT) and zero-fills what lies outside the chunk;
+//      zero-fills what lies outside the chunk (units at a chunk's ends only; the reader byte-swaps words as it refills);
 //   2. lane i starts a few words before subsequence i (a guess), walks to the first codeword boundary inside it
 //      (self-synchronisation), then decodes the subsequence ONCE, up to four symbols per table lookup, into its
 //      private row of shared memory (word-interleaved rows: lane == bank, no conflicts), counting symbols;
@@ -314,28 +314,26 @@ __device__ __forceinline__ void fu_mbar_wait(uint32_t bar_a, uint32_t parity) {
         "}\n" ::"r"(bar_a), "r"(parity) : "memory");
 }
 
-// After the bulk copy landed: words become big-endian values (stream bit 0 = bit 31 of word 0), bytes outside
-// the chunk read as zero (TableBasedHuffmanDecoder.java:204-208), chunk bytes the 16-byte aligned copy could
-// not deliver are fetched one by one.  All lanes of the warp.
+// After the bulk copy landed.  The stage keeps the stream's bytes as they are (the bit reader byte-swaps a word when
+// it becomes current, at no cost: the refill's register move is a PRMT instead), so nothing is left to do for a unit
+// whose stage lies inside the chunk and was delivered whole.  Units at a chunk's ends: bytes outside the chunk read
+// as zero (TableBasedHuffmanDecoder.java:204-208), chunk bytes the 16-byte aligned copy could not deliver are fetched
+// one by one.  All lanes of the warp.
 __device__ __forceinline__ void fu_stage_prepare(uint32_t stage_a, const UnitGeom& g, uint32_t lane) {
     const int32_t glo = g.vlo > g.tlo ? g.vlo : g.tlo, ghi = g.vhi < g.thi ? g.vhi : g.thi;   // good bytes
+    if (glo == 0 && ghi >= g.need) return;
     for (int32_t b0 = (int32_t)lane * 16; b0 < g.need; b0 += 32 * 16) {
-        uint4 w;
-        if (b0 >= glo && b0 + 16 <= ghi) {
-            w = lds128(stage_a + b0);
-        } else {
-            uint32_t x[4] = {0, 0, 0, 0};
-            for (int32_t j = 0; j < 16; ++j) {
-                const int32_t b = b0 + j;
-                uint32_t v = 0;
-                if (b >= g.vlo && b < g.vhi)
-                    v = (b >= g.tlo && b < g.thi) ? lds8(stage_a + b) : *reinterpret_cast<const uint8_t*>(g.a0 + (uint64_t)b);
-                x[j >> 2] |= v << (8 * (j & 3));
-            }
-            w = make_uint4(x[0], x[1], x[2], x[3]);
+        if (b0 >= glo && b0 + 16 <= ghi) continue;
+        uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+        for (int32_t j = 0; j < 16; ++j) {
+            const int32_t b = b0 + j;
+            uint32_t v = 0;
+            if (b >= g.vlo && b < g.vhi)
+                v = (b >= g.tlo && b < g.thi) ? lds8(stage_a + b) : *reinterpret_cast<const uint8_t*>(g.a0 + (uint64_t)b);
+            v <<= 8 * (j & 3);
+            if (j < 4) x0 |= v; else if (j < 8) x1 |= v; else if (j < 12) x2 |= v; else x3 |= v;
         }
-        w.x = bswap32(w.x); w.y = bswap32(w.y); w.z = bswap32(w.z); w.w = bswap32(w.w);
-        sts128(stage_a + b0, w);
+        sts128(stage_a + b0, make_uint4(x0, x1, x2, x3));
     }
 }
 
@@ -346,10 +344,10 @@ __device__ __forceinline__ void fu_stage_prepare(uint32_t stage_a, const UnitGeo
 // bytes already in the accumulator.  One add of the table entry's .y advances both; bit 31 / 30 of an
 // entry (long code / several candidate lengths) make the sum fail the loop's single compare.
 // ---------------------------------------------------------------------------------------------
-struct Reader { uint32_t hi, lo, nx, wa; };      // stream words j, j+1, j+2 and the shared address of word j+2
+struct Reader { uint32_t hi, lo, nx, wa; };      // stream words j, j+1 (big-endian values), word j+2 as stored, its shared address
 __device__ __forceinline__ void fu_seek(Reader& r, uint32_t stage_a, uint32_t pos) {
     const uint32_t a = stage_a + ((pos >> 5) << 2);
-    r.hi = lds32(a); r.lo = lds32(a + 4); r.nx = lds32(a + 8); r.wa = a + 8;
+    r.hi = bswap32(lds32(a)); r.lo = bswap32(lds32(a + 4)); r.nx = lds32(a + 8); r.wa = a + 8;
 }
 
 #define FU_REFILL(CI, CO)                                                     \
@@ -357,7 +355,7 @@ __device__ __forceinline__ void fu_seek(Reader& r, uint32_t stage_a, uint32_t po
     "and.b32 a, t, 0x200000;\n"                                               \
     "setp.ne.u32 p0, a, 0;\n"                                                 \
     "@p0 mov.u32 %1, %2;\n"                                                   \
-    "@p0 mov.u32 %2, %3;\n"                                                   \
+    "@p0 prmt.b32 %2, %3, z, 0x0123;\n"                                       \
     "@p0 ld.shared.u32 %3, [%4+4];\n"                                         \
     "@p0 add.u32 %4, %4, 4;\n"
 
@@ -410,7 +408,8 @@ __device__ __forceinline__ void fu_skim(uint32_t& C, Reader& r, uint32_t Cend, u
     asm volatile(
         "{\n"
         ".reg .pred pl, px, p0, pq;\n"
-        ".reg .u32 D, s, v, ix, ex, ey, t, u, a, l, m, auxb;\n"
+        ".reg .u32 D, s, v, ix, ex, ey, t, u, a, z, l, m, auxb;\n"
+        "mov.u32 z, 0;\n"
         "FS_TOP:\n"
         FU_SSTEP("%0", "D", "1")
         FU_SSTEP("D", "%0", "2")
@@ -439,7 +438,7 @@ __device__ __forceinline__ void fu_walk(uint32_t& C, Reader& r, uint32_t Cend, u
     "and.b32 a, t, 32;\n"                                                     \
     "setp.ne.u32 p1, a, 0;\n"                                                 \
     "@p0 mov.u32 %1, %2;\n"                                                   \
-    "@p0 mov.u32 %2, %3;\n"                                                   \
+    "@p0 prmt.b32 %2, %3, z, 0x0123;\n"                                       \
     "@p0 ld.shared.u32 %3, [%4+4];\n"                                         \
     "@p0 add.u32 %4, %4, 4;\n"                                                \
     "shf.l.wrap.b32 a, z, ex, " CI ";\n"                                      \
@@ -777,7 +776,7 @@ dec_fused_kernel(const FuArgs a) {
                     bool bad = false;
                     while (idx < stop) {
                         const uint32_t wa = stage_a + ((p >> 5) << 2);
-                        const uint32_t v = __funnelshift_l(lds32(wa + 4), lds32(wa), p);
+                        const uint32_t v = __funnelshift_l(bswap32(lds32(wa + 4)), bswap32(lds32(wa)), p);
                         uint32_t sym;
                         p += fu_one(A, wlut_a, v, sym, bad);
                         *reinterpret_cast<uint8_t*>(gout + idx) = (uint8_t)sym;
