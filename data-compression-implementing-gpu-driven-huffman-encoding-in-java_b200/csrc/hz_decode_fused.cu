@@ -534,11 +534,14 @@ __device__ __forceinline__ void fu_walk(uint32_t& C, Reader& r, uint32_t Cend, u
 __device__ __forceinline__ uint32_t fu_settle(uint32_t C, uint32_t Cb, uint32_t exl, uint32_t lim, uint32_t aux_a) {
     const uint32_t n = ((C - Cb) & 0xFFFFu) >> 3;
     if (n > 1 && (C >> 16) > lim) {
-        uint32_t q = Cb >> 16, j = 0;
-        do {
-            q += lds8(aux_a + (uint32_t)offsetof(DecAux, len) + ((exl >> (8 * j)) & 0xFFu));
-            ++j;
-        } while (q < lim && j < n);
+        // straight-line (the lanes of a warp that get here differ in n): the first three symbols' lengths at once,
+        // symbol k (k >= 1) stays iff it exists and the boundary before it lies before the limit
+        const uint32_t la = aux_a + (uint32_t)offsetof(DecAux, len);
+        const uint32_t l0 = lds8(la + (exl & 0xFFu)), l1 = lds8(la + ((exl >> 8) & 0xFFu)), l2 = lds8(la + ((exl >> 16) & 0xFFu));
+        const uint32_t q0 = (Cb >> 16) + l0, q1 = q0 + l1, q2 = q1 + l2;
+        const bool t1 = q0 < lim, t2 = t1 && n > 2 && q1 < lim, t3 = t2 && n > 3 && q2 < lim;
+        const uint32_t j = 1u + t1 + t2 + t3;
+        const uint32_t q = t3 ? (C >> 16) : (t2 ? q2 : (t1 ? q1 : q0));
         C = (q << 16) | ((Cb & 0xFFFFu) + 8 * j);
     }
     return C;
@@ -800,12 +803,10 @@ dec_fused_kernel(const FuArgs a) {
                     const uint32_t hn = min(cw, (4u - (d & 3)) & 3);      // bytes before the lane's first whole window word
                     const uint32_t nfull = (cw - hn) >> 2, tn = (cw - hn) & 3;
                     uint32_t tail = 0;                                    // the last tn bytes (row bytes hn + 4 nfull ...)
-                    {
+                    if (tn) {                                             // they sit in ONE row word: bytes tb & 3 ... of word tb >> 2
                         const uint32_t tb = hn + 4 * nfull;
-                        for (uint32_t j = 0; j < tn; ++j) {
-                            const uint32_t b = tb + j;
-                            tail |= lds8(rows_a + ((b >> 2) * 32 + lane) * 4 + (b & 3)) << (8 * j);
-                        }
+                        const uint32_t w = lds32(rows_a + ((tb >> 2) * 32 + lane) * 4), w2 = lds32(rows_a + (((tb >> 2) + 1) * 32 + lane) * 4);
+                        tail = __funnelshift_r(w, w2, 8 * (tb & 3));
                     }
                     __syncwarp();
                     // the rows are in registers: draw the next ticket now, its round trip runs under the stores below
@@ -815,7 +816,9 @@ dec_fused_kernel(const FuArgs a) {
                     FU_ASSERT((cw == 0 || d + cw <= 15 + T) && 15 + T + 4 <= FU_ROWS_BYTES, "window inside the rows");
                     const uint32_t bs = (d & 3) * 8;
                     const uint32_t w0 = rows_a + (d & ~3u);               // window word that holds the first symbol
-                    for (uint32_t j = 0; j < hn; ++j) sts8(w0 + (d & 3) + j, rw[0] >> (8 * j));
+                    if (hn > 0) sts8(w0 + (d & 3), rw[0]);
+                    if (hn > 1) sts8(w0 + (d & 3) + 1, rw[0] >> 8);
+                    if (hn > 2) sts8(w0 + (d & 3) + 2, rw[0] >> 16);
                     const uint32_t jmin = bs ? 1u : 0u;
                     {
                         // window word w0 + 4 j = row bytes [4 j - (d & 3), +4)
@@ -829,7 +832,9 @@ dec_fused_kernel(const FuArgs a) {
                     }
                     {
                         const uint32_t ta = w0 + 4 * (jmin + nfull);
-                        for (uint32_t j = 0; j < tn; ++j) sts8(ta + j, tail >> (8 * j));
+                        if (tn > 0) sts8(ta, tail);
+                        if (tn > 1) sts8(ta + 1, tail >> 8);
+                        if (tn > 2) sts8(ta + 2, tail >> 16);
                     }
                     __syncwarp();
                     // window bytes [shift, shift + T) -> global [g0, g0 + T): whole 16-byte units by one bulk copy
