@@ -456,10 +456,12 @@ def run_b200(a):
                                      % len(numa_cpus)) if numa_cpus else "none (NVML affinity unavailable)"}
         pc = pcie_ceiling(world)
         if pc:
-            # per step the busier direction moves max(N + C, C + N) bytes per GPU; with both directions busy the host
-            # sustains `duplex_GBps_per_direction` per GPU when `world` GPUs copy at once (tools/pcie_peak.py)
-            bound_s = max(e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"]) / (pc["duplex_GBps_per_direction"] * 1e9)
-            e2e["host_link_ceiling"] = dict(pc, bound_ms_per_step=1e3 * bound_s, frac_of_ceiling=bound_s / e2e_s)
+            # the two calls of a step do not overlap each other (decode consumes encode's output): the encode call is bound
+            # by its busier direction, max(N up, C down), and so is the decode call, max(C up, N down); with both directions
+            # busy the host sustains `duplex_GBps_per_direction` per GPU when `world` GPUs copy at once (tools/pcie_peak.py)
+            bound_s = 2.0 * max(n, C) / (pc["duplex_GBps_per_direction"] * 1e9)
+            e2e["host_link_ceiling"] = dict(pc, bound_ms_per_step=1e3 * bound_s, frac_of_ceiling=bound_s / e2e_s,
+                                            bound_is="2 * max(N, C) / duplex rate: the busier direction of each of the two calls")
         del h_src, h_comp, h_back
 
     cpu_sample = None

@@ -18,7 +18,7 @@ if [ "${SKIP_REF:-0}" != "1" ]; then
   cat $OUT/bench_ref.json
 fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-  CMD="python bench.py --steps 2 --warmup 3 --size-mib ${NCU_MIB:-1024} --no-e2e --no-cpu"
+  CMD="python bench.py --steps 2 --warmup 3 --size-mib ${NCU_MIB:-1024} --no-e2e --no-cpu --no-strong"
   $CMD > $OUT/ncu_plain.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
   echo "ncu launches rc=$?"
