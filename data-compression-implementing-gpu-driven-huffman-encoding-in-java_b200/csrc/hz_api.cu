@@ -91,6 +91,7 @@ void hz_read_knobs(hz_knobs* k) {
     k->dec_bulk = num("HZ_DEC_BULK", 1) != 0;
     k->fu_lead = num("HZ_FU_LEAD", 0);
     k->fu_grid = num("HZ_FU_GRID", 0);
+    k->fu_warps = num("HZ_FU_WARPS", 0);
     if (const char* ev = getenv("HZ_FU_DUMP")) k->fu_dump = ev;
 }
 

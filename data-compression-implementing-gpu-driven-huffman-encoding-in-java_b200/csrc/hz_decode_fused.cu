@@ -25,10 +25,7 @@
 #include <cstdio>
 #include "hz_decode_tables.cuh"
 
-#ifndef FU_WARPS
-#define FU_WARPS 24
-#endif
-#define FU_THREADS (FU_WARPS * 32)
+#define FU_WARPS_MAX 24                            // large chunks: ONE CTA of 24 warps per SM shares a chunk's table
 #define FU_SUB_MIN 3
 #define FU_SUB_MAX 17
 #define FU_ROW_WORDS 46                            // 44 words of symbols + 2 guard words (overflow is tested once per two lookups)
@@ -47,12 +44,14 @@ struct FuShared {
     __align__(16) uint2 wlut[LUTN];
     __align__(16) uint8_t aux[1024];
     __align__(16) uint4 ring[FU_RING];       // look-back records of the units THIS CTA decoded: {record, unit + 1}
-    __align__(8) uint64_t bar[FU_WARPS];
+    __align__(8) uint64_t bar[FU_WARPS_MAX];
+    __align__(8) uint64_t tbar;              // the chunk's table arrives by ONE bulk copy
     uint32_t s_k, s_pick;
 };
 static_assert(offsetof(FuShared, aux) + offsetof(DecAux, sorted) == DEC_W_SORTED_REL, "long-code entries address sorted[] relative to wlut");
+static_assert(offsetof(FuShared, wlut) == 0 && offsetof(FuShared, aux) == LUTN * 8, "wlut + aux are one contiguous bulk-copy destination");
 #define FU_SHARED_BYTES ((sizeof(FuShared) + 15) & ~(size_t)15)
-#define FU_SMEM_BYTES (FU_SHARED_BYTES + (size_t)FU_WARPS * FU_WARP_BYTES)
+#define FU_SMEM_BYTES(W) (FU_SHARED_BYTES + (size_t)(W) * FU_WARP_BYTES)
 
 struct FuPlan {
     uint64_t* orig_off;     // [K+1]
@@ -582,18 +581,32 @@ struct FuArgs {
     uint32_t* dbg;          // developer dump (HZ_FU_DUMP): entry | exit << 8 | count << 16 per subsequence
 };
 
-// chunk for this CTA: a fresh one from the ticket, else (few large chunks) one that still has units left
-__device__ uint32_t fu_pick_chunk(const FuArgs& a, FuShared& S) {
+// Chunk for this CTA.  Thread 0 holds a ticket drawn one chunk AHEAD (`ahead`: the atomic's round trip ran under
+// the previous chunk's decode), resolves it to a chunk that has units, requests that chunk's table (ONE bulk copy
+// of wlut + aux, completion on S.tbar) and draws the next ticket.  When the tickets have run out (few large
+// chunks) the CTA joins a chunk that still has units.  Called by all threads after a barrier that follows the last
+// use of the previous table.
+__device__ __forceinline__ void fu_table_issue(const FuArgs& a, FuShared& S, uint32_t k) {
+    const uint32_t bar_a = smem_u32(&S.tbar), dst = smem_u32(S.wlut);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "n"(FU_TABLE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(a.tables + (size_t)k * FU_TABLE_BYTES), "n"(FU_TABLE_BYTES), "r"(bar_a) : "memory");
+}
+__device__ uint32_t fu_pick_chunk(const FuArgs& a, FuShared& S, uint32_t& ahead) {
     const uint32_t K = a.K;
     if (threadIdx.x == 0) {
-        uint32_t k = FU_NONE;
+        uint32_t k = FU_NONE, t = ahead;
         for (;;) {
-            const uint32_t t = atomicAdd(&a.P.ctl[0], 1u);
             if (t >= K) break;
             if (a.P.nunit[t]) { k = t; break; }
+            t = atomicAdd(&a.P.ctl[0], 1u);
         }
+        if (k != FU_NONE) { fu_table_issue(a, S, k); ahead = atomicAdd(&a.P.ctl[0], 1u); }
+        else ahead = K;
         S.s_k = k; S.s_pick = FU_NONE;
     }
+    if (threadIdx.x < FU_RING) S.ring[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     if (S.s_k != FU_NONE) return S.s_k;
     if (K > 2048) return FU_NONE;                         // thousands of chunks balance by themselves
@@ -611,10 +624,17 @@ __device__ uint32_t fu_pick_chunk(const FuArgs& a, FuShared& S) {
     }
     __syncthreads();
     const uint32_t p = S.s_pick;
-    return p == FU_NONE ? FU_NONE : (start + p) % K;
+    if (p == FU_NONE) return FU_NONE;
+    const uint32_t k = (start + p) % K;
+    if (threadIdx.x == 0) fu_table_issue(a, S, k);
+    return k;
 }
 
-__global__ void __launch_bounds__(FU_THREADS, 1)
+// W = warps per CTA, MINB = CTAs per SM: <24, 1> for chunks of many units; <8, 2> and <5, 3> for streams of small
+// chunks, where several independent CTAs per SM (each with its own chunk's table) overlap one CTA's per-chunk
+// serial part (ticket, table copy, barriers, the chain of a few units) with the others' walks
+template <int W, int MINB>
+__global__ void __launch_bounds__(W * 32, MINB)
 dec_fused_kernel(const FuArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FuShared& S = *reinterpret_cast<FuShared*>(smem_raw);
@@ -627,50 +647,51 @@ dec_fused_kernel(const FuArgs a) {
     const DecAux& A = *reinterpret_cast<const DecAux*>(S.aux);
     if (lane == 0) {
         mbar_init(&S.bar[wid], 1);
+        if (wid == 0) mbar_init(&S.tbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 #ifdef FU_TIMING
     long long tim__[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last__ = clock64();
 #endif
     uint32_t phase = 0;                                   // parity of this warp's mbarrier
+    uint32_t tphase = 0;                                  // parity of the table's mbarrier
     bool out_pending = false;                             // a bulk copy out of this warp's rows may still be reading them
+    uint32_t ahead = 0;                                   // thread 0: the chunk ticket drawn ahead
+    if (threadIdx.x == 0) ahead = atomicAdd(&a.P.ctl[0], 1u);
     __syncthreads();
 
     for (;;) {
-        const uint32_t k = fu_pick_chunk(a, S);
+        const uint32_t k = fu_pick_chunk(a, S, ahead);
         if (k == FU_NONE) break;
-        {
-            const uint8_t* tb = a.tables + (size_t)k * FU_TABLE_BYTES;
-            copy_g2s16(S.wlut, tb, LUTN * 8);
-            copy_g2s16(S.aux, tb + LUTN * 8, 1024);
-            if (threadIdx.x < FU_RING) S.ring[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncthreads();
+        // the chunk's geometry and this warp's first unit are fetched while the table is on its way
         const uint32_t osize = a.orig_size[k];
         const uint64_t ooff = a.P.orig_off[k];
         const uint32_t nunit = a.P.nunit[k];
-        int reject = 0;
-        if (A.bad) reject = HZ_ERR_BAD_LENGTHS;
-        else if (ooff + osize > a.out_cap) reject = HZ_ERR_OUT_TOO_SMALL;
-        if (reject) {
-            if (threadIdx.x == 0) { hz_set_status(a.status, reject); atomicMax(a.P.unit_ctr + k, nunit); }
-            __syncthreads();
-            continue;
-        }
         const uint64_t coff = a.comp_off[k];
         const uint32_t csize = a.comp_size[k];
         const uint32_t nsub = a.P.nsub[k];
         const uint32_t Sw = a.P.geom[k] & 0xFF, lead = a.P.geom[k] >> 8;
         const uint32_t sub_bits = Sw * 32;
-        const uint32_t U = (uint32_t)A.uniform;
         uint64_t* R = a.rec + a.P.unit_base[k];
         const uint64_t gout = reinterpret_cast<uint64_t>(a.out) + ooff;
-
-        // ---- warp loop over the chunk's units -------------------------------------------------
         uint32_t u = 0;
         if (lane == 0) u = atomicAdd(a.P.unit_ctr + k, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
+        fu_mbar_wait(smem_u32(&S.tbar), tphase); tphase ^= 1;
+        int reject = 0;
+        if (A.bad) reject = HZ_ERR_BAD_LENGTHS;
+        else if (ooff + osize > a.out_cap) reject = HZ_ERR_OUT_TOO_SMALL;
+        if (reject) {
+            // (the units already ticketed have their stage copies in flight: drain them, the stage is reused)
+            if (u < nunit) { fu_mbar_wait(bar_a, phase); phase ^= 1; }
+            if (threadIdx.x == 0) { hz_set_status(a.status, reject); atomicMax(a.P.unit_ctr + k, nunit); }
+            __syncthreads();
+            continue;
+        }
+        const uint32_t U = (uint32_t)A.uniform;
+
+        // ---- warp loop over the chunk's units -------------------------------------------------
         while (u < nunit) {
             const UnitGeom g = fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw);
             FU_ASSERT(g.need > 0 && g.need <= FU_STAGE_BYTES && g.tlo >= 0 && g.tlo <= g.thi && g.thi <= g.need && (g.tlo & 15) == 0 && (g.thi & 15) == 0, "stage geometry");
@@ -913,7 +934,10 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
     HZ_TRY(hz_reserve(ctx, &ctx->dec_rec, max_units * sizeof(uint64_t)));
     HZ_TRY(hz_reserve(ctx, &ctx->dec_tables, (size_t)K * FU_TABLE_BYTES));
     if (!ctx->attr_decode_fused) {
-        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(24)));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(12)));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(8)));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(5)));
         ctx->attr_decode_fused = true;
     }
     const uint32_t lead_knob = (uint32_t)ctx->knobs.fu_lead;   // developer knob
@@ -930,9 +954,28 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
 #endif
     const char* dump = ctx->knobs.fu_dump.empty() ? nullptr : ctx->knobs.fu_dump.c_str();   // developer knob: per-subsequence records to a file
     if (dump) { cudaMallocManaged(&a.dbg, max_units * 32 * sizeof(uint32_t)); cudaMemset(a.dbg, 0xFF, max_units * 32 * sizeof(uint32_t)); }
+    // CTA shape by the stream's average chunk (no host synchronisation: from the call's sizes): units per chunk
+    uint32_t warps = 24;
+    {
+        uint64_t s = out_cap ? comp_bytes * 34 / out_cap : 17;
+        s = s < FU_SUB_MIN ? FU_SUB_MIN : (s > FU_SUB_MAX ? FU_SUB_MAX : s);
+        const uint64_t unit_bytes = ((s - 1) | 1) * 128;
+        const uint64_t upc = comp_bytes / K / unit_bytes;                  // units per chunk
+        if (upc < 96) warps = 12;
+        if (upc < 40) warps = 8;
+        if (upc < 10) warps = 5;
+    }
+    if (ctx->knobs.fu_warps > 0) warps = (uint32_t)ctx->knobs.fu_warps;   // developer knob
     const int grid_knob = ctx->knobs.fu_grid;   // developer knob
-    const unsigned grid = grid_knob > 0 ? (unsigned)grid_knob : (unsigned)ctx->sm_count;
-    HZ_LAUNCH(ctx, "dec_fused", dec_fused_kernel, grid, FU_THREADS, FU_SMEM_BYTES, a);
+    const unsigned per_sm = warps == 24 ? 1u : (warps == 5 ? 3u : 2u);
+    const unsigned grid = grid_knob > 0 ? (unsigned)grid_knob : per_sm * (unsigned)ctx->sm_count;
+    void (*kfn)(const FuArgs) = nullptr;
+    if (warps == 24) kfn = dec_fused_kernel<24, 1>;
+    else if (warps == 12) kfn = dec_fused_kernel<12, 2>;
+    else if (warps == 8) kfn = dec_fused_kernel<8, 2>;
+    else if (warps == 5) kfn = dec_fused_kernel<5, 3>;
+    else return hz_fail(ctx, HZ_ERR_ARG, "HZ_FU_WARPS must be 24, 12, 8 or 5");
+    HZ_LAUNCH(ctx, "dec_fused", kfn, grid, warps * 32, FU_SMEM_BYTES(warps), a);
 #ifdef FU_TIMING
     cudaStreamSynchronize(ctx->stream);
     {
