@@ -43,7 +43,7 @@ struct hz_knobs {
     int dec_bulk = 1;          // HZ_DEC_BULK
     int fu_lead = 0;           // HZ_FU_LEAD      lead-in words of the fused decoder
     int fu_grid = 0;           // HZ_FU_GRID      CTAs of the fused decoder
-    int fu_warps = 0;          // HZ_FU_WARPS     warps per CTA of the fused decoder (24, 12, 8 or 5)
+    int fu_warps = 0;          // HZ_FU_WARPS     warps per CTA of the fused decoder (24, 8 or 5)
     std::string fu_dump;       // HZ_FU_DUMP      file for per-subsequence records
 };
 void hz_read_knobs(hz_knobs* k);

@@ -1035,17 +1035,12 @@ int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const ui
     uint8_t* ident = (uint8_t*)ctx->dec_misc.p;
     const uint32_t ident_on = ctx->knobs.ident;   // developer knob: HZ_IDENT=0 sends identity chunks through the table walk
     HZ_LAUNCH(ctx, "dec_ident", dec_ident_flags_kernel, (K + DT / 32 - 1) / (DT / 32), DT, 0, d_len, d_orig_size, K, ident, ident_on);
-    // Chunks of >= ~64 units (a unit = 32 subsequences, 0.4 - 2 KiB of stream) go to the fused single-walk kernel; streams
-    // of smaller chunks keep the multi-pass kernels below, whose CTAs are not tied to one chunk's table for long
-    // (measured on B200 at 4 bits/symbol: 64 KiB chunks 387 vs 246 GB/s, 256 KiB 574 vs 499, 1 MiB 646 vs 763).
+    // Every stream goes to the fused single-walk kernel (hz_decode_fused.cu), whose CTA shape follows the units per
+    // chunk; the multi-pass kernels below remain as the developer knob HZ_DEC=legacy (A/B and a second implementation
+    // for the parity tests).  Measured on B200 at 4 bits/symbol, fused vs multi-pass, GB/s of output: 1 KiB chunks
+    // 23.5 vs 7.2, 4 KiB 89 vs 29, 16 KiB 308 vs 130, 64 KiB 579 vs 384, 256 KiB 762 vs 572, 1 MiB 958 vs 647, 16 MiB 886 vs 711.
     const int mode = ctx->knobs.dec_mode;   // developer knob HZ_DEC=legacy|fused
-    bool fused = mode != 1;
-    if (mode == 0) {
-        uint64_t s = out_cap ? comp_bytes * 34 / out_cap : 17;
-        s = s < 3 ? 3 : (s > 17 ? 17 : s);
-        const uint64_t unit_bytes = ((s - 1) | 1) * 128;
-        fused = comp_bytes / K >= 64 * unit_bytes;
-    }
+    const bool fused = mode != 1;
     if (fused) {
         const uint64_t* p_orig_off = nullptr; const uint32_t* p_islice = nullptr;
         HZ_TRY(hzk_decode_fused(ctx, d_comp, comp_bytes, d_comp_off, d_comp_size, d_orig_size, d_orig_off, d_len, K, d_out, out_cap,

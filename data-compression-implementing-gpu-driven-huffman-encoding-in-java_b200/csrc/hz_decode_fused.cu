@@ -90,47 +90,62 @@ __device__ __forceinline__ void fu_chunk_geom(uint32_t csize, uint32_t osize, bo
     if (ns == 0) ns = 1;
 }
 
+// Rounds of 1024 consecutive chunks (coalesced loads, one chunk per thread), a block-wide exclusive scan of
+// {units | identity slices << 32, original bytes} per round, running carries.
+__device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int d) {
+    const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d), hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
 __global__ void __launch_bounds__(1024)
 fu_plan_kernel(const uint64_t* __restrict__ comp_off, const uint32_t* __restrict__ comp_size,
                const uint32_t* __restrict__ orig_size, const uint64_t* __restrict__ orig_off_in, uint64_t comp_bytes,
                uint32_t K, FuPlan P, const uint8_t* __restrict__ ident, uint32_t lead_knob, int* status) {
-    __shared__ uint64_t part[3][1024];
-    const uint32_t t = threadIdx.x;
-    const uint32_t per = (K + 1023) / 1024;
-    const uint32_t lo = min(K, t * per), hi = min(K, lo + per);
-    uint64_t s0 = 0, s1 = 0, s2 = 0;
-    for (uint32_t i = lo; i < hi; ++i) {
-        // the chunk must lie inside the addressable stream (untrusted footer fields reach this ABI)
-        const bool ok = comp_off[i] <= comp_bytes && comp_size[i] <= comp_bytes - comp_off[i];
-        if (!ok) hz_set_status(status, HZ_ERR_ARG);
-        uint32_t S, lead, ns;
-        fu_chunk_geom(comp_size[i], orig_size[i], ident[i] != 0, ok, lead_knob, S, lead, ns);
-        s0 += (ns + 31) / 32; s1 += orig_size[i];
-        s2 += (ok && ident[i]) ? (orig_size[i] + FU_IDENT_SLICE - 1) / FU_IDENT_SLICE : 0u;
+    __shared__ uint64_t wtot[2][2][32];                   // [round parity][value][warp]
+    const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    uint64_t carry_a = 0, carry_b = 0;                    // units | slices << 32, original bytes: before this round
+    uint32_t par = 0;
+    for (uint32_t base = 0; base < K; base += 1024, par ^= 1) {
+        const uint32_t i = base + t;
+        uint64_t va = 0, vb = 0;
+        uint32_t S = FU_SUB_MAX, lead = 3, ns = 0;
+        if (i < K) {
+            // the chunk must lie inside the addressable stream (untrusted footer fields reach this ABI)
+            const uint64_t co = comp_off[i];
+            const uint32_t cs = comp_size[i], os = orig_size[i];
+            const bool id = ident[i] != 0;
+            const bool ok = co <= comp_bytes && cs <= comp_bytes - co;
+            if (!ok) hz_set_status(status, HZ_ERR_ARG);
+            fu_chunk_geom(cs, os, id, ok, lead_knob, S, lead, ns);
+            va = (uint64_t)((ns + 31) / 32) | ((uint64_t)((ok && id) ? (os + FU_IDENT_SLICE - 1) / FU_IDENT_SLICE : 0u) << 32);
+            vb = os;
+        }
+        uint64_t ia = va, ib = vb;                        // inclusive scans within the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t xa = shfl_up64(ia, d), xb = shfl_up64(ib, d);
+            if (lane >= (uint32_t)d) { ia += xa; ib += xb; }
+        }
+        if (lane == 31) { wtot[par][0][wid] = ia; wtot[par][1][wid] = ib; }
+        __syncthreads();
+        uint64_t pa = carry_a, pb = carry_b, ta = 0, tb = 0;
+        for (uint32_t w = 0; w < 32; ++w) {
+            const uint64_t xa = wtot[par][0][w], xb = wtot[par][1][w];
+            if (w < wid) { pa += xa; pb += xb; }
+            ta += xa; tb += xb;
+        }
+        if (i < K) {
+            const uint64_t ea = pa + ia - va, eb = pb + ib - vb;   // exclusive prefixes of chunk i
+            P.nsub[i] = ns; P.nunit[i] = (ns + 31) / 32; P.unit_base[i] = (uint32_t)ea; P.geom[i] = S | (lead << 8);
+            P.unit_ctr[i] = 0;
+            P.orig_off[i] = orig_off_in ? orig_off_in[i] : eb;
+            P.islice[i] = (uint32_t)(ea >> 32);
+        }
+        carry_a += ta; carry_b += tb;
     }
-    part[0][t] = s0; part[1][t] = s1; part[2][t] = s2;
-    __syncthreads();
-    if (t < 3) {
-        uint64_t a = 0;
-        for (int j = 0; j < 1024; ++j) { uint64_t x = part[t][j]; part[t][j] = a; a += x; }
-        if (t == 0) P.unit_base[K] = (uint32_t)a;
-        if (t == 1) P.orig_off[K] = a;
-        if (t == 2) P.islice[K] = (uint32_t)a;
+    if (t == 0) {
+        P.unit_base[K] = (uint32_t)carry_a; P.orig_off[K] = carry_b; P.islice[K] = (uint32_t)(carry_a >> 32);
+        P.ctl[0] = 0;
     }
-    __syncthreads();
-    s0 = part[0][t]; s1 = part[1][t]; s2 = part[2][t];
-    for (uint32_t i = lo; i < hi; ++i) {
-        const bool ok = comp_off[i] <= comp_bytes && comp_size[i] <= comp_bytes - comp_off[i];
-        uint32_t S, lead, ns;
-        fu_chunk_geom(comp_size[i], orig_size[i], ident[i] != 0, ok, lead_knob, S, lead, ns);
-        P.nsub[i] = ns; P.nunit[i] = (ns + 31) / 32; P.unit_base[i] = (uint32_t)s0; P.geom[i] = S | (lead << 8);
-        P.unit_ctr[i] = 0;
-        P.orig_off[i] = orig_off_in ? orig_off_in[i] : s1;
-        P.islice[i] = (uint32_t)s2;
-        s0 += (ns + 31) / 32; s1 += orig_size[i];
-        s2 += (ok && ident[i]) ? (orig_size[i] + FU_IDENT_SLICE - 1) / FU_IDENT_SLICE : 0u;
-    }
-    if (t == 0) P.ctl[0] = 0;
 }
 
 // look-back records of the units that exist (their number is only known on the device)
@@ -141,7 +156,7 @@ fu_zero_kernel(uint64_t* __restrict__ rec, const uint32_t* __restrict__ unit_bas
 }
 
 // tables: one CTA per chunk, written to global memory once, copied by every CTA that works on the chunk
-__global__ void __launch_bounds__(DT)
+__global__ void __launch_bounds__(DT, 6)
 fu_tables_kernel(const uint8_t* __restrict__ len_tab, FuPlan P, uint8_t* __restrict__ tables) {
     __shared__ __align__(16) uint8_t scratch[DEC_BUILD_SCRATCH];
     __shared__ __align__(16) uint8_t aux_raw[1024];
@@ -323,6 +338,7 @@ __device__ __forceinline__ void fu_stage_prepare(uint32_t stage_a, const UnitGeo
     if (glo == 0 && ghi >= g.need) return;
     for (int32_t b0 = (int32_t)lane * 16; b0 < g.need; b0 += 32 * 16) {
         if (b0 >= glo && b0 + 16 <= ghi) continue;
+        if (b0 + 16 <= g.vlo || b0 >= g.vhi) { sts128(stage_a + b0, make_uint4(0u, 0u, 0u, 0u)); continue; }   // outside the chunk
         uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
         for (int32_t j = 0; j < 16; ++j) {
             const int32_t b = b0 + j;
@@ -569,8 +585,12 @@ __device__ __forceinline__ uint32_t fu_one(const DecAux& A, uint32_t wlut_a, uin
 // -DFU_TIMING (developer build): per-phase clock64 totals over all warps, printed by the launcher
 #ifdef FU_TIMING
 #define FU_T(i) do { const long long now__ = clock64(); tim__[i] += now__ - last__; last__ = now__; } while (0)
+// per-warp event trace of CTA 0 (a.tim[16] = count, a.tim[32 + 2 i] = clock, [33 + 2 i] = warp << 48 | event << 32 | value)
+#define FU_TRACE(ev, val) do { if (blockIdx.x == 0 && lane == 0 && a.tim) { const unsigned long long ix__ = atomicAdd(a.tim + 16, 1ull); \
+    if (ix__ < 4000) { a.tim[32 + 2 * ix__] = (unsigned long long)clock64(); a.tim[33 + 2 * ix__] = ((unsigned long long)wid << 48) | ((unsigned long long)(ev) << 32) | (unsigned long long)(uint32_t)(val); } } } while (0)
 #else
 #define FU_T(i) do { } while (0)
+#define FU_TRACE(ev, val) do { } while (0)
 #endif
 struct FuArgs {
     const uint8_t* comp; uint64_t comp_bytes;
@@ -651,7 +671,7 @@ dec_fused_kernel(const FuArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 #ifdef FU_TIMING
-    long long tim__[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last__ = clock64();
+    long long tim__[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, last__ = clock64();
 #endif
     uint32_t phase = 0;                                   // parity of this warp's mbarrier
     uint32_t tphase = 0;                                  // parity of the table's mbarrier
@@ -663,6 +683,8 @@ dec_fused_kernel(const FuArgs a) {
     for (;;) {
         const uint32_t k = fu_pick_chunk(a, S, ahead);
         if (k == FU_NONE) break;
+        FU_T(11);
+        FU_TRACE(0, k);
         // the chunk's geometry and this warp's first unit are fetched while the table is on its way
         const uint32_t osize = a.orig_size[k];
         const uint64_t ooff = a.P.orig_off[k];
@@ -678,7 +700,9 @@ dec_fused_kernel(const FuArgs a) {
         if (lane == 0) u = atomicAdd(a.P.unit_ctr + k, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
+        FU_T(8);
         fu_mbar_wait(smem_u32(&S.tbar), tphase); tphase ^= 1;
+        FU_T(9);
         int reject = 0;
         if (A.bad) reject = HZ_ERR_BAD_LENGTHS;
         else if (ooff + osize > a.out_cap) reject = HZ_ERR_OUT_TOO_SMALL;
@@ -698,8 +722,10 @@ dec_fused_kernel(const FuArgs a) {
             FU_ASSERT(g.a0 + (uint64_t)g.tlo >= (reinterpret_cast<uint64_t>(a.comp) & ~15ull) && g.a0 + (uint64_t)g.thi <= reinterpret_cast<uint64_t>(a.comp) + a.comp_bytes, "bulk copy inside the stream");
             FU_ASSERT(g.bit0 >= lead * 32 && g.bit0 / 8 + 128 * Sw + 32 <= (uint32_t)g.need + 15, "unit inside the stage");
             FU_T(0);
+            FU_TRACE(1, u);
             fu_mbar_wait(bar_a, phase); phase ^= 1;
             FU_T(1);
+            FU_TRACE(2, u);
             fu_stage_prepare(stage_a, g, lane);
             if (out_pending) {                            // the previous unit's window must have left the rows
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -709,7 +735,12 @@ dec_fused_kernel(const FuArgs a) {
 
             const uint32_t i = u * 32 + lane;             // subsequence index within the chunk
             const bool active = i < nsub;
-            const uint32_t nominal = g.bit0 + lane * sub_bits, end = nominal + sub_bits;     // stage-relative bits
+            // stage-relative bits.  The chunk's last subsequence ends with the chunk: the zero bits behind it would decode
+            // to a long run of the all-zero codeword's symbol (a row overflow in every chunk's last unit); symbols that
+            // the stream does not hold are written by the tail fill below
+            const uint32_t nominal = g.bit0 + lane * sub_bits;
+            const uint64_t left = (uint64_t)csize * 8 - (uint64_t)i * sub_bits;      // (only meaningful for active lanes)
+            const uint32_t end = nominal + (active && left < sub_bits ? (uint32_t)left : sub_bits);
             uint32_t entry = 0;
             if (active && i != 0) {
                 if (U) {                                  // equal-length code: boundaries are the multiples of U
@@ -725,6 +756,7 @@ dec_fused_kernel(const FuArgs a) {
                 }
             }
             FU_T(2);
+            FU_TRACE(3, u);
             // decode (and re-decode where a guess was wrong) until the chain of the unit is consistent and
             // anchored in the chunk's earlier units
             bool need = active;
@@ -740,6 +772,7 @@ dec_fused_kernel(const FuArgs a) {
                     FU_T(7);
                     fu_walk(C, r, Cend, wlut_a, acc, sp, Cb, exl, badc, ovf);
                     FU_T(3);
+                    FU_TRACE(4, u);
                     FU_ASSERT(sp >= rows_a + lane * 4 && sp <= rows_a + lane * 4 + (FU_ROW_WORDS - 1) * 128, "row pointer");
                     FU_ASSERT(r.wa >= stage_a && r.wa + 4 < stage_a + (uint32_t)g.need, "reader inside the stage");
                     if (ovf) fu_skim(C, r, Cend, wlut_a, Cb, exl);
@@ -770,6 +803,7 @@ dec_fused_kernel(const FuArgs a) {
                 FU_T(7);
                 const bool lb_ok = fu_lookback(R, ring_a, u, uentry, lane, prefix, true_entry);
                 FU_T(4);
+                FU_TRACE(5, u);
                 if (lb_ok) {
                     if (lane == 0) fu_put(R, ring_a, u, fu_pack(FU_FINAL, uentry, uexit, ucount, prefix + ucount));
                     break;
@@ -881,6 +915,7 @@ dec_fused_kernel(const FuArgs a) {
                 }
             }
             FU_T(6);
+            FU_TRACE(6, u_cur);
             // The next unit's ticket is drawn as LATE as possible, right before its bytes are fetched: a unit waits (in
             // its look-back) for every unit with a smaller ticket, so whatever a warp does between drawing a ticket and
             // publishing that unit's record delays all the warps behind it.  Drawing the ticket before the output
@@ -900,12 +935,15 @@ dec_fused_kernel(const FuArgs a) {
             }
             __syncwarp();
         }
+        FU_T(0);
         __syncthreads();                                  // every warp is done with this chunk's table
+        FU_T(10);
+        FU_TRACE(7, k);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the copies
 #ifdef FU_TIMING
     FU_T(0);
-    if (lane == 0 && a.tim) for (int i = 0; i < 8; ++i) atomicAdd(a.tim + i, (unsigned long long)tim__[i]);
+    if (lane == 0 && a.tim) for (int i = 0; i < 12; ++i) atomicAdd(a.tim + i, (unsigned long long)tim__[i]);
 #endif
 }
 
@@ -935,7 +973,6 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
     HZ_TRY(hz_reserve(ctx, &ctx->dec_tables, (size_t)K * FU_TABLE_BYTES));
     if (!ctx->attr_decode_fused) {
         HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(24)));
-        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(12)));
         HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(8)));
         HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(5)));
         ctx->attr_decode_fused = true;
@@ -950,7 +987,7 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
     a.K = K; a.P = P; a.tables = (const uint8_t*)ctx->dec_tables.p; a.rec = (uint64_t*)ctx->dec_rec.p;
     a.out = d_out; a.out_cap = out_cap; a.status = ctx->d_status; a.dbg = nullptr; a.tim = nullptr;
 #ifdef FU_TIMING
-    cudaMallocManaged(&a.tim, 8 * sizeof(unsigned long long)); cudaMemset(a.tim, 0, 8 * sizeof(unsigned long long));
+    cudaMallocManaged(&a.tim, (32 + 8000) * sizeof(unsigned long long)); cudaMemset(a.tim, 0, (32 + 8000) * sizeof(unsigned long long));
 #endif
     const char* dump = ctx->knobs.fu_dump.empty() ? nullptr : ctx->knobs.fu_dump.c_str();   // developer knob: per-subsequence records to a file
     if (dump) { cudaMallocManaged(&a.dbg, max_units * 32 * sizeof(uint32_t)); cudaMemset(a.dbg, 0xFF, max_units * 32 * sizeof(uint32_t)); }
@@ -961,9 +998,8 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
         s = s < FU_SUB_MIN ? FU_SUB_MIN : (s > FU_SUB_MAX ? FU_SUB_MAX : s);
         const uint64_t unit_bytes = ((s - 1) | 1) * 128;
         const uint64_t upc = comp_bytes / K / unit_bytes;                  // units per chunk
-        if (upc < 96) warps = 12;
-        if (upc < 40) warps = 8;
-        if (upc < 10) warps = 5;
+        if (upc < 64) warps = 8;      // measured on B200 (tools/dec_shapes.py, 4 bits/symbol): 64 KiB chunks 434 / 528 / 502 GB/s with
+        if (upc < 8) warps = 5;       // 24 / 8 / 5 warps, 16 KiB 137 / 204 / 241, 256 KiB 737 / 741 / 737, 1 MiB 933 / 829 / 786
     }
     if (ctx->knobs.fu_warps > 0) warps = (uint32_t)ctx->knobs.fu_warps;   // developer knob
     const int grid_knob = ctx->knobs.fu_grid;   // developer knob
@@ -971,19 +1007,25 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
     const unsigned grid = grid_knob > 0 ? (unsigned)grid_knob : per_sm * (unsigned)ctx->sm_count;
     void (*kfn)(const FuArgs) = nullptr;
     if (warps == 24) kfn = dec_fused_kernel<24, 1>;
-    else if (warps == 12) kfn = dec_fused_kernel<12, 2>;
     else if (warps == 8) kfn = dec_fused_kernel<8, 2>;
     else if (warps == 5) kfn = dec_fused_kernel<5, 3>;
-    else return hz_fail(ctx, HZ_ERR_ARG, "HZ_FU_WARPS must be 24, 12, 8 or 5");
+    else return hz_fail(ctx, HZ_ERR_ARG, "HZ_FU_WARPS must be 24, 8 or 5");
     HZ_LAUNCH(ctx, "dec_fused", kfn, grid, warps * 32, FU_SMEM_BYTES(warps), a);
 #ifdef FU_TIMING
     cudaStreamSynchronize(ctx->stream);
     {
-        static const char* nm[8] = {"idle/other", "tma wait", "prepare", "walk", "lookback", "ticket", "output", "skim+glue"};
-        double tot = 0; for (int i = 0; i < 8; ++i) tot += (double)a.tim[i];
+        static const char* nm[12] = {"unit glue", "tma wait", "prepare+lead", "walk", "lookback", "ticket", "output", "skim+glue", "meta+ticket", "table wait", "end barrier", "pick"};
+        double tot = 0; for (int i = 0; i < 12; ++i) tot += (double)a.tim[i];
         fprintf(stderr, "FU_TIMING");
-        for (int i = 0; i < 8; ++i) fprintf(stderr, "  %s %.1f%%", nm[i], 100.0 * (double)a.tim[i] / tot);
+        for (int i = 0; i < 12; ++i) fprintf(stderr, "  %s %.1f%%", nm[i], 100.0 * (double)a.tim[i] / tot);
         fprintf(stderr, "\n");
+        if (getenv("HZ_FU_TRACE")) {
+            static const char* ev[8] = {"chunk", "unit", "staged", "lead", "walk", "lookback", "out", "endbar"};
+            const unsigned long long n = a.tim[16] < 4000 ? a.tim[16] : 4000, t0 = n ? a.tim[32] : 0;
+            for (unsigned long long i = 0; i < n && i < 600; ++i)
+                fprintf(stderr, "TR %8.2f us  w%llu %-8s %llu\n", (double)(a.tim[32 + 2 * i] - t0) / 1965.0, a.tim[33 + 2 * i] >> 48,
+                        ev[(a.tim[33 + 2 * i] >> 32) & 7], a.tim[33 + 2 * i] & 0xFFFFFFFFull);
+        }
         cudaFree(a.tim);
     }
 #endif

@@ -133,6 +133,7 @@ __device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __re
                 if (used + le > LUTB) break;
                 if (n < 4) { syms |= (e & 0xFF) << (8 * n); wtot = used + le; wn = n + 1; }
                 used += le; ++n; lprev = le;
+                if (!WANT_S && n == 4) break;             // (the count table alone looks beyond four symbols)
             }
             we = FMT ? make_uint2(syms, (wtot << 16) | (wn << 3)) : make_uint2(syms, wtot | (wn << 19));
             se = used | (l0 << 6) | (n << 12);
