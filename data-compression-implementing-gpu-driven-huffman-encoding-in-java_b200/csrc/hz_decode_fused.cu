@@ -286,6 +286,10 @@ __device__ __forceinline__ UnitGeom fu_geom(const uint8_t* comp, uint64_t comp_b
     g.a0 = (us - 4 * FU_LEAD_MAX) & ~(uint64_t)15;
     g.bit0 = (uint32_t)(us - g.a0) * 8;
     g.need = (int32_t)(((us - g.a0) + 128u * S + 32 + 15) & ~(uint64_t)15);
+    if (g.a0 >= cb && g.a0 + (uint64_t)g.need <= cb + chunk_size) {   // (warp-uniform) the stage lies inside the chunk:
+        g.vlo = g.tlo = 0; g.vhi = g.thi = g.need;                    // all of it exists and is delivered by the bulk copy
+        return g;
+    }
     int64_t vlo = (int64_t)cb - (int64_t)g.a0, vhi = vlo + chunk_size;
     if (vlo < 0) vlo = 0;
     if (vhi > g.need) vhi = g.need;
@@ -356,8 +360,9 @@ __device__ __forceinline__ void fu_stage_prepare(uint32_t stage_a, const UnitGeo
 // bit reader + walks.  Packed counter C: bits 16-27 stream position relative to a multiple of 32 at or
 // before the walk's start (so (C >> 16) & 31 is the reader's funnel-shift amount), bits 0-15 output bits
 // (8 per symbol) + FU_OUT_BIAS, whose low five bits are the shift that puts a lookup's symbols behind the
-// bytes already in the accumulator.  One add of the table entry's .y advances both; bit 31 / 30 of an
-// entry (long code / several candidate lengths) make the sum fail the loop's single compare.
+// bytes already in the accumulator.  One add of the table entry's .y advances both; bit 30 of an entry's .y
+// (several candidate lengths / no code) makes the sum fail the loop's single compare; .y >= 13 << 16 marks a
+// single-length long code (resolved by predicated instructions; the add is the same as for any entry).
 // ---------------------------------------------------------------------------------------------
 struct Reader { uint32_t hi, lo, nx, wa; };      // stream words j, j+1 (big-endian values), word j+2 as stored, its shared address
 __device__ __forceinline__ void fu_seek(Reader& r, uint32_t stage_a, uint32_t pos) {
@@ -365,14 +370,15 @@ __device__ __forceinline__ void fu_seek(Reader& r, uint32_t stage_a, uint32_t po
     r.hi = bswap32(lds32(a)); r.lo = bswap32(lds32(a + 4)); r.nx = lds32(a + 8); r.wa = a + 8;
 }
 
+// (the reader's pointer advances by a multiply-add of the toggled bit - 2^21 * 2^13 >> 32 = 4 - instead of a predicated
+//  add, which ptxas turns into an add and a select)
 #define FU_REFILL(CI, CO)                                                     \
-    "xor.b32 t, " CI ", " CO ";\n"                                            \
-    "and.b32 a, t, 0x200000;\n"                                               \
+    "lop3.b32 a, " CI ", " CO ", 0x200000, 0x28;\n"                           \
     "setp.ne.u32 p0, a, 0;\n"                                                 \
     "@p0 mov.u32 %1, %2;\n"                                                   \
     "@p0 prmt.b32 %2, %3, z, 0x0123;\n"                                       \
     "@p0 ld.shared.u32 %3, [%4+4];\n"                                         \
-    "@p0 add.u32 %4, %4, 4;\n"
+    "mad.hi.u32 %4, a, 8192, %4;\n"
 
 // resolves an entry with several candidate lengths / no code: l = its length, 0 when nothing matches
 #define FU_RARE_LEN(SFX, TAB, AUXOFF)                                         \
@@ -395,8 +401,6 @@ __device__ __forceinline__ void fu_skim(uint32_t& C, Reader& r, uint32_t Cend, u
     "mad.lo.u32 ix, ix, 8, %7;\n"                                             \
     "ld.shared.v2.u32 {ex, ey}, [ix];\n"                                      \
     "add.u32 " CO ", " CI ", ey;\n"                                           \
-    "setp.lt.s32 pl, ey, 0;\n"                                                \
-    "@pl add.u32 " CO ", " CO ", 0x80000000;\n"                               \
     "setp.ge.u32 px, " CO ", %8;\n"                                           \
     "@px bra FS_CHECK" SFX ";\n"                                              \
     "FS_BACK" SFX ":\n"                                                       \
@@ -447,20 +451,19 @@ __device__ __forceinline__ void fu_skim(uint32_t& C, Reader& r, uint32_t Cend, u
 __device__ __forceinline__ void fu_walk(uint32_t& C, Reader& r, uint32_t Cend, uint32_t wlut_a, uint32_t& acc, uint32_t& sp,
                                         uint32_t& Cb, uint32_t& exl, uint32_t& badc, uint32_t& ovf) {
 #define FU_COMMIT(CI, CO)                                                     \
-    "xor.b32 t, " CI ", " CO ";\n"                                            \
-    "and.b32 a, t, 0x200000;\n"                                               \
+    "lop3.b32 a, " CI ", " CO ", 0x200000, 0x28;\n"                           \
     "setp.ne.u32 p0, a, 0;\n"                                                 \
-    "and.b32 a, t, 32;\n"                                                     \
-    "setp.ne.u32 p1, a, 0;\n"                                                 \
+    "lop3.b32 u, " CI ", " CO ", 32, 0x28;\n"                                 \
+    "setp.ne.u32 p1, u, 0;\n"                                                 \
     "@p0 mov.u32 %1, %2;\n"                                                   \
     "@p0 prmt.b32 %2, %3, z, 0x0123;\n"                                       \
     "@p0 ld.shared.u32 %3, [%4+4];\n"                                         \
-    "@p0 add.u32 %4, %4, 4;\n"                                                \
+    "mad.hi.u32 %4, a, 8192, %4;\n"                                           \
     "shf.l.wrap.b32 a, z, ex, " CI ";\n"                                      \
     "shf.l.wrap.b32 t, ex, z, " CI ";\n"                                      \
     "add.u32 %5, %5, a;\n"                                                    \
     "@p1 st.shared.u32 [%6], %5;\n"                                           \
-    "@p1 add.u32 %6, %6, 128;\n"                                              \
+    "mad.lo.u32 %6, u, 4, %6;\n"                                              \
     "selp.b32 %5, t, %5, p1;\n"
 #define FU_WSTEP(CI, CO, SFX)                                                 \
     "shr.u32 s, " CI ", 16;\n"                                                \
@@ -473,9 +476,8 @@ __device__ __forceinline__ void fu_walk(uint32_t& C, Reader& r, uint32_t Cend, u
     "add.u32 a, a, t;\n"                                                      \
     "add.u32 a, a, %11;\n"                                                    \
     "add.u32 " CO ", " CI ", ey;\n"                                           \
-    "setp.lt.s32 pl, ey, 0;\n"                                                \
+    "setp.ge.u32 pl, ey, %16;\n"                                                \
     "@pl ld.shared.u8 ex, [a];\n"                                             \
-    "@pl add.u32 " CO ", " CO ", 0x80000000;\n"                               \
     "setp.ge.u32 px, " CO ", %12;\n"                                          \
     "@px bra FW_CHECK" SFX ";\n"                                              \
     "FW_BACK" SFX ":\n"                                                       \
@@ -535,7 +537,8 @@ __device__ __forceinline__ void fu_walk(uint32_t& C, Reader& r, uint32_t Cend, u
         "}\n"
         : "+r"(C), "+r"(r.hi), "+r"(r.lo), "+r"(r.nx), "+r"(r.wa), "+r"(acc), "+r"(sp), "+r"(badc),
           "=&r"(Cb), "=&r"(exl), "=&r"(ovf)
-        : "r"(wlut_a), "r"(Cend), "n"(LUTN * 8), "n"(offsetof(DecAux, symbase)), "n"(offsetof(DecAux, sorted))
+        : "r"(wlut_a), "r"(Cend), "n"(LUTN * 8), "n"(offsetof(DecAux, symbase)), "n"(offsetof(DecAux, sorted)),
+          "n"((LUTB + 1) << 16)
         : "memory");
 #undef FU_WSTEP
 #undef FU_WCHECK
@@ -565,7 +568,7 @@ __device__ __forceinline__ uint32_t fu_settle(uint32_t C, uint32_t Cb, uint32_t 
 // exactly one codeword at the 32 stream bits v (slow paths): returns its length, the symbol in sym
 __device__ __forceinline__ uint32_t fu_one(const DecAux& A, uint32_t wlut_a, uint32_t v, uint32_t& sym, bool& bad) {
     const uint2 e = lds64(wlut_a + ((v >> 20) << 3));
-    if ((int32_t)e.y >= 0) { sym = e.x & 0xFFu; return A.len[sym]; }
+    if (e.y < ((LUTB + 1u) << 16)) { sym = e.x & 0xFFu; return A.len[sym]; }
     const uint32_t l = long_len(A, v, LUTB + 1, (uint32_t)A.maxlen);
     if (!l) { bad = true; sym = 0; return 1; }
     sym = A.sorted[A.symbase[l] + (int32_t)(v >> (32 - l))];

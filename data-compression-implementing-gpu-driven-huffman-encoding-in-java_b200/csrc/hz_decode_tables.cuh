@@ -43,9 +43,10 @@ __device__ __forceinline__ void bt_sync() { asm volatile("bar.sync 1, %0;" ::"n"
 
 // FMT 0: wlut of the legacy write kernel (.y = ltot | 8n << 16).  FMT 1: wlut of the fused kernel, whose packed
 // counter keeps the stream position in the HIGH half: .y = ltot << 16 | 8n; a single-length long code (13..24 bits)
-// has .y = 0x80000000 | l << 16 | 8 and .x = (DEC_W_SORTED_REL + symbase[l]) << 5 | (32 - l): the low five bits are
-// the right shift that leaves the first l stream bits, the rest (arithmetic shift) the wlut-relative address of
-// sorted[symbase[l]].
+// has .y = l << 16 | 8 - so .y >= (LUTB + 1) << 16 is the predicate of the second-level load - and
+// .x = (DEC_W_SORTED_REL + symbase[l]) << 5 | (32 - l): the low five bits are the right shift that leaves the first l
+// stream bits, the rest (arithmetic shift) the wlut-relative address of sorted[symbase[l]]; entries with several
+// candidate lengths / no code have .y = 0x40000000 (the walk's end compare catches it).
 template <bool WANT_W, bool WANT_S, int FMT = 0>
 __device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __restrict__ slut,
                              uint8_t* __restrict__ scratch, const uint8_t* __restrict__ len_k) {
@@ -120,7 +121,7 @@ __device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __re
         const uint32_t e0 = base[x];
         // FMT 1: the fused kernel's predicated long-code load also runs (harmlessly) on entries with several
         // candidate lengths / no code, so their .x keeps 31 in the low five bits (address offset <= 1 + lmax << 6)
-        uint2 we = make_uint2(FMT ? 31u : 0u, 0xC0000000u);
+        uint2 we = make_uint2(FMT ? 31u : 0u, FMT ? 0x40000000u : 0xC0000000u);
         uint32_t se = 0;
         if (e0) {
             const uint32_t l0 = e0 >> 8;
@@ -148,7 +149,7 @@ __device__ void build_tables(DecAux& A, uint2* __restrict__ wlut, uint16_t* __re
                 // every code under this prefix has the same length: `sorted` is the second-level table
                 if (FMT) {
                     if (lmin == lmax && lmin <= 24)
-                        we = make_uint2(((DEC_W_SORTED_REL + (uint32_t)A.symbase[lmin]) << 5) | (32 - lmin), 0x80000000u | (lmin << 16) | 8u);
+                        we = make_uint2(((DEC_W_SORTED_REL + (uint32_t)A.symbase[lmin]) << 5) | (32 - lmin), (lmin << 16) | 8u);
                 } else if (lmin == lmax && lmin < 32)
                     we = make_uint2(DEC_W_SORTED_REL + (uint32_t)A.symbase[lmin], 0x80000000u | lmin | (8u << 16));
                 se = lmin == lmax ? (lmin | (lmin << 6) | (1u << 12)) : (lmin | (lmax << 6));
