@@ -246,6 +246,50 @@ def test_decode_damaged_streams_match_the_oracle(codec, decmode, H, chunk):
             assert np.array_equal(out, ref), "chunk %d trial %d" % (k, trial)
 
 
+@pytest.mark.parametrize("warps", ["24", "8", "5"])
+def test_fused_decoder_cta_shapes(codec, knob, warps):
+    """The fused decoder picks its CTA shape by the units per chunk (24 warps x 1 CTA per SM, 8 x 2, 5 x 3;
+    HZ_FU_WARPS forces one).  Every shape on: thousands of small chunks of mixed entropy with a ragged tail, chunks
+    whose payload ends exactly on / one byte around a subsequence and a unit boundary, a payload that holds MORE
+    symbols than orig_size and one that holds FEWER (the chunk's last subsequence stops at the chunk's end and the
+    all-zero codeword's symbol fills the rest, TableBasedHuffmanDecoder.java:204-208), damaged streams."""
+    knob("HZ_DEC", "fused")
+    knob("HZ_FU_WARPS", warps)
+    rng = np.random.default_rng(int(warps) + 40)
+    # 1. many small chunks
+    parts = [datasets.zipf_stream(200_000, H, seed=70 + H) for H in (1, 3, 4, 6, 7)]
+    data = np.concatenate(parts + [datasets.zipf_stream(12_345, 5, seed=80)])
+    for chunk in (3_000, 16 * 1024, 65_536):
+        check_encode(codec, data, chunk)
+    # 2. payload sizes around subsequence (S words) and unit (32 S words) boundaries: trim the symbol count until the
+    #    chunk's compressed size hits the wanted value, then decode against the oracle with longer / shorter orig_size
+    base = datasets.zipf_stream(400_000, 4, seed=91)
+    for target in (17 * 4 * 32 * 9, 17 * 4 * 32 * 9 + 1, 17 * 4 * 32 * 9 - 1, 17 * 4 * 40, 17 * 4 * 40 + 3):
+        n = int(target * 8 / 4.03)
+        for _ in range(60):
+            comp, ln, _ = orc.encode_chunk(base[:n])
+            if comp.size == target: break
+            n += int((target - comp.size) * 8 / 4.03) or (1 if comp.size < target else -1)
+        lens = ln.astype(np.uint8)[None, :]
+        for n_out in (n, n - 7, n + 5000):
+            ref, rc = orc.decode(comp, ln.astype(np.int32), n_out, literal=False)
+            assert rc == 0
+            out = codec.decode(comp, [0], [comp.size], [n_out], lens)
+            assert np.array_equal(out, ref), "payload %d bytes, %d of %d symbols" % (comp.size, n_out, n)
+    # 3. damaged small chunks
+    chunk = 50_000
+    d3 = datasets.zipf_stream(8 * chunk, 5, seed=93)
+    payload, off, lens = codec.encode(d3, chunk)[:3]
+    bad = payload.copy()
+    for f in rng.integers(0, bad.size * 8, 200):
+        bad[f >> 3] ^= 0x80 >> (f & 7)
+    sizes = np.diff(off).astype(np.uint32)
+    out = codec.decode(bad, off[:-1], sizes, [chunk] * 8, lens)
+    for k in range(8):
+        ref, rc = orc.decode(bad[int(off[k]):int(off[k + 1])], lens[k].astype(np.int32), chunk, literal=False)
+        assert rc == 0 and np.array_equal(out[k * chunk:(k + 1) * chunk], ref), "damaged chunk %d" % k
+
+
 def test_decode_reads_zero_bits_past_the_end(codec, decmode):
     # TableBasedHuffmanDecoder.java:204-208: bits past the end of the chunk are 0
     ln = np.zeros((1, 256), dtype=np.uint8); ln[0, 7] = 1; ln[0, 9] = 1      # 7 -> '0', 9 -> '1'
