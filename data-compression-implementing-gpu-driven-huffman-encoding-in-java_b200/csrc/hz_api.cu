@@ -92,6 +92,7 @@ void hz_read_knobs(hz_knobs* k) {
     k->fu_lead = num("HZ_FU_LEAD", 0);
     k->fu_grid = num("HZ_FU_GRID", 0);
     k->fu_warps = num("HZ_FU_WARPS", 0);
+    k->enc_chain = num("HZ_ENC_CHAIN", 1);
     if (const char* ev = getenv("HZ_FU_DUMP")) k->fu_dump = ev;
 }
 
@@ -166,7 +167,7 @@ void hz_destroy(hz_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     hz_comm_destroy(c);
     DevBuf* bufs[] = {&c->glob, &c->seg_hist, &c->chunk_hist, &c->len, &c->code, &c->chunk_bits, &c->comp_size, &c->comp_off,
-                      &c->seg_bitoff, &c->counter, &c->stage_in, &c->stage_out, &c->stage_a, &c->stage_b,
+                      &c->seg_bitoff, &c->counter, &c->chain, &c->stage_in, &c->stage_out, &c->stage_a, &c->stage_b,
                       &c->stage_c, &c->stage_d, &c->stage_e, &c->dec_meta, &c->dec_rec, &c->dec_seqcnt, &c->dec_misc, &c->dec_tables};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->d_status) cudaFree(c->d_status);
@@ -363,6 +364,31 @@ static int encode_device(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t 
     HZ_TRY(hz_reserve(ctx, &ctx->chunk_bits, (size_t)K * 8));
     HZ_TRY(hz_reserve(ctx, &ctx->comp_size, (size_t)K * 4));
     HZ_TRY(hz_reserve(ctx, &ctx->seg_bitoff, nseg * 8));
+    // Streams of >= 8 large chunks: histogram, codebooks and offsets in ONE launch whose CTAs build a chunk's codebook as
+    // soon as its histogram is complete, and an encoder launched with programmatic stream serialization that waits per
+    // chunk (hz_codebook.cu: hist_chain_kernel) - the codebook stage's 0.16 ms of latency leaves the critical path.
+    // (Streams of smaller chunks and caller-supplied lengths keep the separate launches.)
+    // Chunks of >= 8 MiB only: a tail holds its CTA for ~0.16 ms, so 0.16 ms x 5.3 TB/s / chunk bytes tails are resident
+    // beside the histogram at any time (16 MiB chunks: 50 of the 888 CTA slots; 4 MiB: 200, and the stage gets slower -
+    // measured 3.30 -> 3.94 ms per 4 GiB, against 3.16 -> 3.05 ms at 16 MiB).
+    if (ctx->knobs.enc_chain && !global_len256 && !d_fixed && K >= 8 && chunk_bytes >= (8u << 20)) {
+        const size_t kk = ((size_t)K + 1) & ~(size_t)1;
+        const size_t bytes = 16 + kk * 4 + 2 * (size_t)K * 8;
+        HZ_TRY(hz_reserve(ctx, &ctx->chain, bytes));
+        uint8_t* m = (uint8_t*)ctx->chain.p;
+        HzChain c;
+        c.ticket = (uint32_t*)m; m += 16;
+        c.prefix = (uint64_t*)m; m += (size_t)K * 8;
+        c.ready = (uint64_t*)m; m += (size_t)K * 8;
+        c.done = (uint32_t*)m;
+        HZ_CUDA(ctx, cudaMemsetAsync(ctx->chain.p, 0, bytes, ctx->stream));
+        HZ_TRY(hzk_hist_codebook_chain(ctx, d_in, n, chunk_bytes, K, (uint32_t*)ctx->seg_hist.p, c, d_hist, d_len,
+                                       (uint32_t*)ctx->code.p, (uint64_t*)ctx->chunk_bits.p, (uint32_t*)ctx->comp_size.p,
+                                       d_off, (uint64_t*)ctx->seg_bitoff.p));
+        HZ_TRY(hzk_encode(ctx, d_in, n, chunk_bytes, K, d_len, (const uint32_t*)ctx->code.p, d_off,
+                          (const uint64_t*)ctx->seg_bitoff.p, d_out, dcap, c.ready, (const uint32_t*)ctx->comp_size.p));
+        return HZ_OK;
+    }
     HZ_TRY(hzk_histogram(ctx, d_in, n, chunk_bytes, K, (uint32_t*)ctx->seg_hist.p));
     if (global_len256) {
         HZ_TRY(hz_reserve(ctx, &ctx->glob, 256 * 8 + 256 * 4));

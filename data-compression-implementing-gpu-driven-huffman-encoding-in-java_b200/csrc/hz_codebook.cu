@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "hz_common.cuh"
+#include "hz_hist_lanes.cuh"
 
 #define CB_THREADS 256
 
@@ -178,23 +179,36 @@ __device__ void block_scan_inplace_u64(uint64_t* data, uint32_t count, uint64_t*
     }
 }
 
-__global__ void __launch_bounds__(CB_THREADS)
-codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* __restrict__ chunk_hist_out,
-                uint8_t* __restrict__ len_out, uint32_t* __restrict__ code_out,
-                uint64_t* __restrict__ chunk_bits, uint32_t* __restrict__ comp_size,
-                uint64_t* __restrict__ seg_bitoff, const uint8_t* __restrict__ fixed_len,
-                const uint32_t* __restrict__ direct_hist, int* status) {
-    __shared__ uint32_t hist[256];
-    __shared__ __align__(16) uint64_t heap[258];
-    __shared__ uint16_t parent[512];
-    __shared__ uint16_t leaf_id[256];
-    __shared__ int s_len[256];
-    __shared__ uint32_t lcount[34];
-    __shared__ uint32_t first[34];
-    __shared__ uint64_t s_warp[9];
-    __shared__ int s_root, s_nsym, s_maxlen;
+// Shared memory of one codebook build (6.3 KiB).  The chained kernel overlays it on its histogram counters.
+struct __align__(16) CbShared {
+    uint64_t heap[258];
+    uint64_t s_warp[9];
+    uint32_t hist[256];
+    int s_len[256];
+    uint32_t lcount[34];
+    uint32_t first[34];
+    uint16_t parent[512];
+    uint16_t leaf_id[256];
+    int s_root, s_nsym, s_maxlen;
+};
 
-    const uint32_t k = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+// The codebook of chunk k by the CB_THREADS threads of a CTA.  CHAIN: the segment histograms were written by other CTAs
+// of the SAME grid (hist_chain_kernel): they are read through L2 (ld.global.cg), never through the non-coherent path.
+// Returns (to every thread) the chunk's compressed size in bytes.
+template <bool CHAIN>
+__device__ __forceinline__ uint32_t codebook_body(CbShared& S, const uint32_t k, const uint32_t* __restrict__ seg_hist, uint32_t spc,
+                                                  uint32_t* __restrict__ chunk_hist_out,
+                                                  uint8_t* __restrict__ len_out, uint32_t* __restrict__ code_out,
+                                                  uint64_t* __restrict__ chunk_bits, uint32_t* __restrict__ comp_size,
+                                                  uint64_t* __restrict__ seg_bitoff, const uint8_t* __restrict__ fixed_len,
+                                                  const uint32_t* __restrict__ direct_hist, int* status) {
+    uint32_t* hist = S.hist; uint64_t* heap = S.heap; uint16_t* parent = S.parent; uint16_t* leaf_id = S.leaf_id;
+    int* s_len = S.s_len; uint32_t* lcount = S.lcount; uint32_t* first = S.first; uint64_t* s_warp = S.s_warp;
+    int& s_root = S.s_root; int& s_nsym = S.s_nsym; int& s_maxlen = S.s_maxlen;
+    auto LD = [](const uint32_t* p) -> uint32_t { return CHAIN ? __ldcg(p) : __ldg(p); };
+    uint32_t my_bytes = 0;
+
+    const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
 
     // 1. chunk histogram = sum of its segment histograms (or a caller-supplied histogram)
     uint32_t f = 0;
@@ -207,11 +221,11 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
         for (; s + 16 <= spc; s += 16) {
             uint32_t v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __ldg(sh + (size_t)(s + j) * 256);
+            for (int j = 0; j < 16; ++j) v[j] = LD(sh + (size_t)(s + j) * 256);
 #pragma unroll
             for (int j = 0; j < 16; ++j) f += v[j];
         }
-        for (; s < spc; ++s) f += __ldg(sh + (size_t)s * 256);
+        for (; s < spc; ++s) f += LD(sh + (size_t)s * 256);
     }
     hist[t] = f;
     if (chunk_hist_out) chunk_hist_out[(size_t)k * 256 + t] = f;
@@ -310,7 +324,10 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
             uint64_t bytes = (a + 7) >> 3;
             if (bytes > 0x7fffffffull) { hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); bytes = 0; }
             comp_size[k] = (uint32_t)bytes;
+            s_warp[8] = bytes;
         }
+        __syncthreads();
+        my_bytes = (uint32_t)s_warp[8];
         __syncthreads();
     }
 
@@ -327,7 +344,7 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
             for (int q = 0; q < 4; ++q) {
                 const uint32_t* sh = seg_hist + ((size_t)k * spc + min(s0 + q, spc - 1)) * 256 + lane;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[q][j] = __ldg(sh + 32 * j);
+                for (int j = 0; j < 8; ++j) v[q][j] = LD(sh + 32 * j);
             }
             uint64_t b[4];
 #pragma unroll
@@ -347,6 +364,86 @@ codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* _
         }
         __syncthreads();
         block_scan_inplace_u64(so, spc, s_warp);
+    }
+    return my_bytes;
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+codebook_kernel(const uint32_t* __restrict__ seg_hist, uint32_t spc, uint32_t* __restrict__ chunk_hist_out,
+                uint8_t* __restrict__ len_out, uint32_t* __restrict__ code_out,
+                uint64_t* __restrict__ chunk_bits, uint32_t* __restrict__ comp_size,
+                uint64_t* __restrict__ seg_bitoff, const uint8_t* __restrict__ fixed_len,
+                const uint32_t* __restrict__ direct_hist, int* status) {
+    __shared__ CbShared S;
+    codebook_body<false>(S, blockIdx.x, seg_hist, spc, chunk_hist_out, len_out, code_out, chunk_bits, comp_size, seg_bitoff,
+                         fixed_len, direct_hist, status);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chained histogram -> codebook -> offsets (large streams of large chunks; hz_api.cu: encode_device).
+// The codebook stage is 0.16 ms of pure latency (one warp replays one chunk's heap) whatever the chunk count; as a
+// kernel of its own it sits between the histogram and the encoder.  Here the histogram CTAs take their ranges from a
+// ticket (so that start order == range order), and the CTA that completes a chunk's histogram (a counter per chunk)
+// builds that chunk's codebook on the spot, obtains the chunk's output offset by a decoupled look-back over the
+// chunks before it (prefix[k-1]: its predecessor's tail has a smaller ticket, so it is running or done) and raises
+// ready[k].  Every CTA issues griddepcontrol.launch_dependents at its start: the encoder, launched with programmatic
+// stream serialization, becomes resident as histogram CTAs retire and its CTAs wait for ready[chunk] - the last
+// chunks' codebooks are built while the first chunks are being encoded.  All waits are bounded (a fault latches
+// HZ_ERR_CUDA instead of hanging the device).
+// ---------------------------------------------------------------------------------------------
+#define HZ_CHAIN_SPIN_MAX (1u << 22)
+__device__ __forceinline__ uint64_t chain_ld_acquire(const uint64_t* p) {
+    uint64_t v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void chain_st_release(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(HZ_THREADS, 6)
+hist_chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t spc, uint32_t mult, uint32_t K,
+                  uint32_t* __restrict__ seg_hist, HzChain c, uint32_t* __restrict__ chunk_hist_out,
+                  uint8_t* __restrict__ len_out, uint32_t* __restrict__ code_out, uint64_t* __restrict__ chunk_bits,
+                  uint32_t* __restrict__ comp_size, uint64_t* __restrict__ comp_off, uint64_t* __restrict__ seg_bitoff,
+                  int* status) {
+    __shared__ __align__(16) uint32_t h[256 * 32];
+    __shared__ uint32_t s_bid, s_last;
+    static_assert(sizeof(CbShared) <= sizeof(uint32_t) * 256 * 32, "the codebook's shared memory overlays the counters");
+    static_assert(HZ_THREADS == CB_THREADS, "the tail runs with the histogram's CTA");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t t = threadIdx.x;
+    if (t == 0) s_bid = atomicAdd(c.ticket, 1u);
+    __syncthreads();
+    const uint32_t bid = s_bid;
+    const uint32_t rpc = (spc + mult - 1) / mult;
+    const uint32_t k = bid / rpc;
+    hist_range_lanes(h, in, n, chunk_bytes, spc, mult, seg_hist, bid);
+    __threadfence();                                      // this CTA's bins are visible device-wide ...
+    __syncthreads();
+    if (t == 0) s_last = atomicAdd(c.done + k, 1u) == rpc - 1 ? 1u : 0u;   // ... before it counts as done
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- tail: this CTA completed chunk k's histogram ----------------------------------------------------
+    CbShared& S = *reinterpret_cast<CbShared*>(h);
+    const uint32_t bytes = codebook_body<true>(S, k, seg_hist, spc, chunk_hist_out, len_out, code_out, chunk_bits, comp_size,
+                                               seg_bitoff, nullptr, nullptr, status);
+    __threadfence();                                      // lengths, codes, segment offsets: visible before ready[k]
+    __syncthreads();
+    if (t == 0) {
+        uint64_t off = 0;
+        if (k > 0) {
+            uint64_t v = 0; uint32_t spins = 0, ns = 64;
+            while (!((v = chain_ld_acquire(c.prefix + (k - 1))) >> 63)) {
+                if (++spins > HZ_CHAIN_SPIN_MAX) { hz_set_status(status, HZ_ERR_CUDA); break; }
+                __nanosleep(ns); if (ns < 1024) ns += ns;
+            }
+            off = v & ~(1ull << 63);
+        }
+        comp_off[k] = off;
+        if (k == K - 1) comp_off[K] = off + bytes;
+        chain_st_release(c.prefix + k, (off + bytes) | (1ull << 63));
+        __threadfence();
+        chain_st_release(c.ready + k, 1ull);
     }
 }
 
@@ -776,6 +873,21 @@ int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t spc, uint32_t
     }
     if (d_comp_off)
         HZ_LAUNCH(ctx, "chunk_offsets", chunk_offsets_kernel, 1, 1024, 0, d_comp_size, K, d_comp_off);
+    return HZ_OK;
+}
+
+// histogram + codebooks + chunk offsets of K chunks in ONE launch (hist_chain_kernel); the encoder that follows waits
+// for c.ready[chunk]
+int hzk_hist_codebook_chain(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K, uint32_t* d_seg_hist,
+                            const HzChain& c, uint32_t* d_chunk_hist, uint8_t* d_len, uint32_t* d_code, uint64_t* d_chunk_bits,
+                            uint32_t* d_comp_size, uint64_t* d_comp_off, uint64_t* d_seg_bitoff) {
+    const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
+    const uint32_t mult = hz_range_mult(spc, ctx->knobs.range_mult);
+    const uint32_t rpc = (spc + mult - 1) / mult;
+    const uint64_t grid = (uint64_t)K * rpc;
+    if (grid > 0x7fffffffull) return hz_fail(ctx, HZ_ERR_ARG, "too many ranges");
+    HZ_LAUNCH(ctx, "hist_codebook_chain", hist_chain_kernel, (unsigned)grid, HZ_THREADS, 0, d_in, n, chunk_bytes, spc, mult, K,
+              d_seg_hist, c, d_chunk_hist, d_len, d_code, d_chunk_bits, d_comp_size, d_comp_off, d_seg_bitoff, ctx->d_status);
     return HZ_OK;
 }
 

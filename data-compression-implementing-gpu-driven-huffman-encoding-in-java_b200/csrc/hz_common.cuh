@@ -44,6 +44,7 @@ struct hz_knobs {
     int fu_lead = 0;           // HZ_FU_LEAD      lead-in words of the fused decoder
     int fu_grid = 0;           // HZ_FU_GRID      CTAs of the fused decoder
     int fu_warps = 0;          // HZ_FU_WARPS     warps per CTA of the fused decoder (24, 8 or 5)
+    int enc_chain = 1;         // HZ_ENC_CHAIN    0: separate histogram / codebook / offsets / encode launches
     std::string fu_dump;       // HZ_FU_DUMP      file for per-subsequence records
 };
 void hz_read_knobs(hz_knobs* k);
@@ -77,7 +78,7 @@ struct hz_ctx {
     int* d_status = nullptr;
     int* h_status = nullptr;
     // scratch
-    DevBuf seg_hist, chunk_hist, len, code, chunk_bits, comp_size, comp_off, seg_bitoff, counter;
+    DevBuf seg_hist, chunk_hist, len, code, chunk_bits, comp_size, comp_off, seg_bitoff, counter, chain;
     DevBuf stage_in, stage_out, stage_a, stage_b, stage_c, stage_d, stage_e;
     DevBuf dec_meta, dec_rec, dec_seqcnt, dec_misc, dec_tables;
     void* h_pin = nullptr; size_t h_pin_cap = 0;
@@ -128,6 +129,14 @@ void hz_prof_resolve(hz_ctx* ctx);
         if (e__ != cudaSuccess) return hz_cuda_fail((ctx), e__, name);                    \
     } while (0)
 
+// flags of the chained histogram -> codebook -> encode pipeline (zeroed before every chained call)
+struct HzChain {
+    uint32_t* ticket;       // [1]  next histogram range
+    uint32_t* done;         // [K]  histogram ranges of chunk k that are complete
+    uint64_t* prefix;       // [K]  bit 63: valid; low bits: payload bytes of chunks 0..k
+    uint64_t* ready;        // [K]  != 0: chunk k's lengths, codes, offsets are in memory
+};
+
 // ---- launchers implemented in the kernel files ------------------------------------------------
 int hzk_histogram(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
                   uint32_t* d_seg_hist);
@@ -135,10 +144,14 @@ int hzk_codebook(hz_ctx* ctx, const uint32_t* d_seg_hist, uint32_t segs_per_chun
                  uint32_t* d_chunk_hist, uint8_t* d_len, uint32_t* d_code, uint64_t* d_chunk_bits,
                  uint32_t* d_comp_size, uint64_t* d_comp_off, uint64_t* d_seg_bitoff,
                  const uint8_t* d_fixed_len256);
+int hzk_hist_codebook_chain(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K, uint32_t* d_seg_hist,
+                            const HzChain& c, uint32_t* d_chunk_hist, uint8_t* d_len, uint32_t* d_code, uint64_t* d_chunk_bits,
+                            uint32_t* d_comp_size, uint64_t* d_comp_off, uint64_t* d_seg_bitoff);
 int hzk_codes_from_lengths(hz_ctx* ctx, const uint8_t* d_len, uint32_t K, uint32_t* d_code);
 int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
                const uint8_t* d_len, const uint32_t* d_code, const uint64_t* d_comp_off,
-               const uint64_t* d_seg_bitoff, uint8_t* d_out, uint64_t out_cap);
+               const uint64_t* d_seg_bitoff, uint8_t* d_out, uint64_t out_cap,
+               const uint64_t* d_chain_ready = nullptr, const uint32_t* d_comp_size = nullptr);
 int hzk_decode(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, const uint64_t* d_comp_off,
                const uint32_t* d_comp_size, const uint32_t* d_orig_size, const uint64_t* d_orig_off,
                const uint8_t* d_len, uint32_t K, uint8_t* d_out, uint64_t out_cap);

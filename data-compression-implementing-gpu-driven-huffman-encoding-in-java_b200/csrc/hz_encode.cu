@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(ENC_CTA, 2)
 encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t spc, uint32_t cpc, uint32_t mult,
               const uint8_t* __restrict__ len_tab, const uint32_t* __restrict__ code_tab,
               const uint64_t* __restrict__ comp_off, const uint64_t* __restrict__ seg_bitoff,
-              uint32_t K, uint8_t* __restrict__ out, uint64_t out_cap, uint32_t ident_on, int* status) {
+              uint32_t K, uint8_t* __restrict__ out, uint64_t out_cap, uint32_t ident_on, int* status,
+              const uint64_t* __restrict__ chain_ready, const uint32_t* __restrict__ comp_size) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t t = threadIdx.x, lane = t & 31;
     const uint32_t grp = t / HZ_THREADS, tg = t % HZ_THREADS, wid = tg >> 5;
@@ -362,17 +363,35 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
     const uint32_t slen = idle ? 0u : (uint32_t)(clen - sbeg < seg_bytes ? clen - sbeg : seg_bytes);
     const bool last_seg = sbeg + slen >= clen;
     const uint8_t* p = in + cbeg + sbeg;
-    // every start-up load is issued before the first use (they are independent)
-    const uint32_t mylen = len_tab[(size_t)k * 256 + tg];
-    const uint32_t mycode = code_tab[(size_t)k * 256 + tg];
-    const uint64_t total_bytes = comp_off[K], chunk_off = comp_off[k];
-    const uint64_t seg_off = idle ? 0 : seg_bitoff[seg];
     const uint8_t* q = p + tg * ENC_SPT;                     // this thread's symbols of tile 0
     const int lmode = (reinterpret_cast<uintptr_t>(q) & 31) == 0 ? 0 : ((reinterpret_cast<uintptr_t>(q) & 3) == 0 ? 1 : 2);
     const uint32_t full_tiles = slen / ENC_TILE;
     uint32_t w[8], wn[8];
-    if (full_tiles) load_syms32(q, lmode, 32, wn);
-    if (total_bytes > out_cap) { if (t == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
+    if (full_tiles) load_syms32(q, lmode, 32, wn);           // (the input does not depend on the codebook: in flight during the wait)
+    // Chained launch (hz_codebook.cu: hist_chain_kernel): this kernel runs beside the tail of its predecessor, which raises
+    // ready[k] once chunk k's lengths, codes, segment offsets and output offset are in memory.  They were written by a grid
+    // that is still running, so they are read through L2 (ld.global.cg) - never through the non-coherent path, whose lines
+    // (comp_off and seg_bitoff share theirs with neighbouring chunks) could predate the writes.  The wait is bounded.
+    if (chain_ready) {
+        if (t == 0) {
+            uint64_t v; uint32_t spins = 0, ns = 64;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(chain_ready + k) : "memory");
+                if (v) break;
+                if (++spins > (1u << 22)) { hz_set_status(status, HZ_ERR_CUDA); break; }
+                __nanosleep(ns); if (ns < 1024) ns += ns;
+            }
+        }
+        __syncthreads();
+    }
+    // every start-up load is issued before the first use (they are independent)
+    const uint32_t mylen = __ldcg(len_tab + (size_t)k * 256 + tg);
+    const uint32_t mycode = __ldcg(code_tab + (size_t)k * 256 + tg);
+    const uint64_t chunk_off = __ldcg(comp_off + k);
+    // the payload must fit the caller's buffer: the whole stream's (comp_off[K]) or, chained, this chunk's end
+    const uint64_t need_bytes = chain_ready ? chunk_off + __ldcg(comp_size + k) : __ldcg(comp_off + K);
+    const uint64_t seg_off = idle ? 0 : __ldcg(seg_bitoff + seg);
+    if (need_bytes > out_cap) { if (t == 0) hz_set_status(status, HZ_ERR_OUT_TOO_SMALL); return; }
     // Identity chunk: all 256 symbols have 8-bit codes, so the canonical code of a symbol is the symbol itself
     // (CanonicalHuffman.java:99-132) and the chunk's bitstream is its plaintext - a byte copy (incompressible data).
     if (__syncthreads_and(ident_on && mylen == 8)) {
@@ -423,8 +442,8 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
             uint32_t bits = 0, have = 0;
             for (int j = 1; j <= 7 && have < r; ++j) {
                 uint32_t sym = p[-j];
-                uint32_t l = len_tab[(size_t)k * 256 + sym];
-                uint32_t c = code_tab[(size_t)k * 256 + sym];
+                uint32_t l = __ldcg(len_tab + (size_t)k * 256 + sym);
+                uint32_t c = __ldcg(code_tab + (size_t)k * 256 + sym);
                 uint32_t take = l < 8 ? l : 8;
                 bits |= (c & ((1u << take) - 1)) << have;
                 have += take;
@@ -518,7 +537,8 @@ encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, 
 
 int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_bytes, uint32_t K,
                const uint8_t* d_len, const uint32_t* d_code, const uint64_t* d_comp_off,
-               const uint64_t* d_seg_bitoff, uint8_t* d_out, uint64_t out_cap) {
+               const uint64_t* d_seg_bitoff, uint8_t* d_out, uint64_t out_cap,
+               const uint64_t* d_chain_ready, const uint32_t* d_comp_size) {
     if (K == 0) return HZ_OK;
     const uint32_t spc = (chunk_bytes + HZ_SEG_BYTES - 1) / HZ_SEG_BYTES;
     // longer ranges amortise the per-range start-up (LUT build, zeroing, first loads); short
@@ -533,7 +553,27 @@ int hzk_encode(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t chunk_byte
         ctx->attr_encode = true;
     }
     const uint32_t ident_on = ctx->knobs.ident;   // developer knob: HZ_IDENT=0 sends identity chunks through the bit packer
-    HZ_LAUNCH(ctx, "encode", encode_kernel, (unsigned)grid, ENC_CTA, ENC_SMEM_BYTES,
-              d_in, n, chunk_bytes, spc, cpc, mult, d_len, d_code, d_comp_off, d_seg_bitoff, K, d_out, out_cap, ident_on, ctx->d_status);
+    if (!d_chain_ready) {
+        HZ_LAUNCH(ctx, "encode", encode_kernel, (unsigned)grid, ENC_CTA, ENC_SMEM_BYTES,
+                  d_in, n, chunk_bytes, spc, cpc, mult, d_len, d_code, d_comp_off, d_seg_bitoff, K, d_out, out_cap, ident_on, ctx->d_status,
+                  (const uint64_t*)nullptr, (const uint32_t*)nullptr);
+        return HZ_OK;
+    }
+    // chained: programmatic stream serialization - the grid may start once every CTA of hist_chain_kernel has issued
+    // griddepcontrol.launch_dependents; it never executes griddepcontrol.wait, the per-chunk ready flags order the data.
+    // (With the per-kernel profiler on, the event between the two launches serialises them: same results, no overlap.)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(ENC_CTA); cfg.dynamicSmemBytes = ENC_SMEM_BYTES; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    hz_prof_begin(ctx);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, encode_kernel, d_in, n, chunk_bytes, spc, cpc, mult, d_len, d_code, d_comp_off, d_seg_bitoff,
+                                       K, d_out, out_cap, ident_on, ctx->d_status, d_chain_ready, d_comp_size);
+    ctx->launches++;
+    hz_prof_end(ctx, "encode");
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return hz_cuda_fail(ctx, e, "encode (chained)");
     return HZ_OK;
 }

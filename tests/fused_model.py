@@ -124,17 +124,18 @@ def decode_chunk(comp, lens, osize, S, lead):
             b, _ = walk(A, tab, rd, nominal - lead * 32, nominal)
             entry[i] = b - nominal
     repairs = 0
+    end = lambda i: min(i * sub + sub, len(comp) * 8)         # the chunk's last subsequence ends with the chunk
     for i in range(nsub):
         nominal = i * sub
-        b, s = walk(A, tab, rd, nominal + entry[i], nominal + sub)
-        exitv[i] = b - (nominal + sub); syms[i] = s
+        b, s = walk(A, tab, rd, nominal + entry[i], end(i))
+        exitv[i] = b - end(i); syms[i] = s
     for i in range(1, nsub):                                 # chain repair, in stream order
         if entry[i] != exitv[i - 1]:
             repairs += 1
             entry[i] = exitv[i - 1]
             nominal = i * sub
-            b, s = walk(A, tab, rd, nominal + entry[i], nominal + sub)
-            exitv[i] = b - (nominal + sub); syms[i] = s
+            b, s = walk(A, tab, rd, nominal + entry[i], end(i))
+            exitv[i] = b - end(i); syms[i] = s
     out = [x for s in syms for x in s]
     if len(out) < osize:
         out += [int(A["sorted"][0])] * (osize - len(out))
