@@ -567,6 +567,55 @@ def test_large_device_resident_roundtrip(codec):
     assert torch.equal(back, src)
 
 
+def test_chained_encode_equals_separate_launches(codec, knob, hz):
+    """Streams of >= 8 chunks of >= 8 MiB take the chained histogram -> codebook -> offsets kernel and an encoder that
+    waits per chunk (programmatic stream serialization).  Its payload, offsets, lengths and chunk histograms must equal
+    those of the separate launches (HZ_ENC_CHAIN=0) bit for bit - with a ragged last chunk, mixed entropies, an
+    incompressible (identity) chunk and a one-symbol chunk, repeatedly (flags are reset per call) - and chunk 0 / the
+    last chunk must equal the oracle's; a too small output buffer is reported, not overrun."""
+    import torch
+    chunk = 8 * MiB
+    n = 9 * chunk + 12_345
+    K = 10
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for i, H in enumerate((4, 2, 8, 6, 1, 4, 7, 3, 5)):
+        codec.synth_fill(src.data_ptr() + i * chunk, chunk, i * chunk, 0x5EED0100 + i, datasets.zipf_qtable(H))
+    codec.synth_fill(src.data_ptr() + 9 * chunk, 12_345, 0, 0x5EED0200, datasets.zipf_qtable(4))
+    src[4 * chunk:5 * chunk] = 0x41                        # a one-symbol chunk
+    codec.sync()
+    res = {}
+    for mode in ("0", "1", "1"):
+        knob("HZ_ENC_CHAIN", mode)
+        comp = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+        off = torch.zeros(K + 1, dtype=torch.int64, device="cuda")
+        lens = torch.zeros((K, 256), dtype=torch.uint8, device="cuda")
+        hist = torch.zeros((K, 256), dtype=torch.int32, device="cuda")
+        codec.encode_raw(src.data_ptr(), n, chunk, comp.data_ptr(), n, off.data_ptr(), lens.data_ptr(), hist.data_ptr())
+        codec.sync()
+        cur = (comp.cpu().numpy(), off.cpu().numpy(), lens.cpu().numpy(), hist.cpu().numpy())
+        if mode in res:
+            for a, b in zip(res[mode], cur): assert np.array_equal(a, b)
+        res[mode] = cur
+    for a, b, what in zip(res["0"], res["1"], ("payload", "offsets", "lengths", "histograms")):
+        assert np.array_equal(a, b), what
+    comp, off, lens, _ = res["1"]
+    for k in (0, 2, 4, K - 1):
+        ref, ln, _ = orc.encode_chunk(src[k * chunk:min(n, (k + 1) * chunk)].cpu().numpy())
+        assert np.array_equal(lens[k], ln.astype(np.uint8)) and np.array_equal(comp[int(off[k]):int(off[k + 1])], ref), k
+    # output capacity one byte short of the payload
+    total = int(off[K])
+    small = torch.zeros(total + 16, dtype=torch.uint8, device="cuda")
+    o2 = torch.zeros(K + 1, dtype=torch.int64, device="cuda")
+    with pytest.raises(hz.HzError) as e:
+        codec.encode_raw(src.data_ptr(), n, chunk, small.data_ptr(), total - 1, o2.data_ptr(), None, None)
+        codec.sync()
+    assert e.value.status == hz.HZ_ERR_OUT_TOO_SMALL
+    assert int(small[total - 1:].sum()) == 0               # nothing at or past the capacity was written
+    codec.encode_raw(src.data_ptr(), n, chunk, small.data_ptr(), total, o2.data_ptr(), None, None)   # the context stays usable
+    codec.sync()
+    assert np.array_equal(small[:total].cpu().numpy(), comp[:total])
+
+
 def test_config3_1gib_32mib_chunks_every_chunk_against_the_oracle(codec):
     """BASELINE config 3 (1 GiB Zipf, ~4 bits/symbol) at the CLI's default chunk size of 32 MiB: code lengths,
     compressed sizes and the SHA-256 of EVERY chunk's payload equal the oracle's (chunk-parallel fast coder), and
