@@ -235,7 +235,8 @@ __device__ bool fu_lookback(const uint64_t* __restrict__ R, uint32_t ring_a, uin
                             uint32_t& prefix, uint32_t& true_entry) {
     uint32_t acc = 0, expect = my_entry0;
     int base = (int)u - 1;
-    fu_wait_rec(R, ring_a, base, FU_SPEC);
+    // (no separate wait for the predecessor's record: the window read below finds it EMPTY and polls it then - one
+    //  round trip to L2 less per unit when the record comes from another CTA)
     for (;;) {
         const int j = base - (int)lane;
         const uint64_t rec = j >= 0 ? fu_get(R, ring_a, j) : 0ull;

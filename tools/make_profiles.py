@@ -21,7 +21,8 @@ out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 pre = os.path.join(out, "%s_%s_" % (rnd, tag))
 NAMES = {"hist_seg_private": "hist_seg_private", "hist_seg_atomic": "hist_seg_atomic", "hist_seg_lanes": "hist_seg_lanes", "encode_kernel": "encode",
-         "dec_sync_kernel": "dec_sync", "dec_write_kernel": "dec_write", "dec_fused_kernel": "dec_fused", "codebook_kernel": "codebook"}
+         "dec_sync_kernel": "dec_sync", "dec_write_kernel": "dec_write", "dec_fused_kernel": "dec_fused", "codebook_kernel": "codebook",
+         "hist_chain_kernel": "hist_codebook_chain"}
 
 for f in ("bench.json", "bench_ref.json"):
     p = os.path.join(src, f)
