@@ -69,6 +69,8 @@ for rep in sorted(glob.glob(os.path.join(src, "prof_*.ncu-rep"))):
         for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tb += float(d[m].replace(",", "")) * scale[u[m]]
         kname = d["Kernel Name"].split("(")[0]
+        if kname.startswith("void "): kname = kname[5:]              # template instances: "void dec_fused_kernel<24, 1>"
+        kname = kname.split("<")[0]
         nbytes = None
         bj = os.path.join(src, "ncu_plain.log")
         traffic[NAMES.get(kname, kname)] = {"dram_bytes_per_launch": tb, "kernel": kname, "capture": "%s_%s" % (rnd, tag),
