@@ -37,6 +37,13 @@ def test_shipped_objects_hold_the_claimed_instructions(objects):
     assert "ATOMS" in hist and "128" in hist                    # shared-memory atomics fed by 128-bit loads
     cb = _sass(os.path.join(objects, "hz_codebook.o"))
     assert cb.count("VOTE") >= 20 and "POPC" in cb              # warp_heap_replay: ballots + popcount
+    # the chained encode: every histogram CTA releases the dependent launch (griddepcontrol.launch_dependents = PREEXIT),
+    # look-back and ready flags are acquire loads / release stores at GPU scope, the encoder polls its chunk's flag
+    assert "PREEXIT" in cb and "LDG.E.64.STRONG.GPU" in cb and "NANOSLEEP" in cb
+    assert "LDG.E.64.STRONG.GPU" in enc and "NANOSLEEP" in enc and "PREEXIT" not in enc
+    fused = _sass(os.path.join(objects, "hz_decode_fused.o"))
+    for shape in ("ILi24ELi1E", "ILi8ELi2E", "ILi5ELi3E"):         # CTA shapes of the fused decoder: 24 x 1, 8 x 2, 5 x 3 warps
+        assert "dec_fused_kernel" + shape in fused
     for text in (dec, enc, hist, cb):
         assert "sm_100a" in text or "SM100" in text.upper() or "EF_CUDA_SM100" in text
 
@@ -71,7 +78,7 @@ def test_ab_switches_compile(tmp_path, src, flag, hot, expect):
 
 
 def test_hot_kernels_of_the_shipped_build_do_not_spill(objects):
-    hot = {"hz_hist": ("hist_seg_lanes",), "hz_codebook": ("codebook_kernel", "codebook_warp_kernel", "codebook_lane_kernel"),
+    hot = {"hz_hist": ("hist_seg_lanes",), "hz_codebook": ("codebook_kernel", "codebook_warp_kernel", "codebook_lane_kernel"),   # (hist_chain_kernel is capped at 40 registers for 6 CTAs per SM: its codebook tail spills one word)
            "hz_encode": ("encode_kernel",), "hz_decode": ("dec_sync_kernel", "dec_write_kernel")}
     # (dec_fused_kernel is register-capped at 80 by its 768-thread CTA; its compaction phase spills a few words)
     for unit, kernels in hot.items():

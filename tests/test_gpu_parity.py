@@ -616,6 +616,46 @@ def test_chained_encode_equals_separate_launches(codec, knob, hz):
     assert np.array_equal(small[:total].cpu().numpy(), comp[:total])
 
 
+def test_chained_encode_repeated_and_concurrent_contexts(hz, codec):
+    """The chain's flags live in per-context scratch and are reset per call: back-to-back calls of different shapes on
+    one context, and two contexts encoding at the same time on two streams, must keep producing the payload of the
+    separate launches (taken once per shape with HZ_ENC_CHAIN=0)."""
+    import torch
+    chunk = 8 * MiB
+    shapes = [(8 * chunk, 4), (11 * chunk + 77, 6), (9 * chunk - 1, 2)]
+    srcs, refs = [], []
+    os.environ["HZ_ENC_CHAIN"] = "0"; codec.reload_knobs()
+    try:
+        for i, (n, H) in enumerate(shapes):
+            K = (n + chunk - 1) // chunk
+            src = torch.empty(n, dtype=torch.uint8, device="cuda")
+            codec.synth_fill(src.data_ptr(), n, 0, 0x5EED0300 + i, datasets.zipf_qtable(H))
+            comp = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+            off = torch.zeros(K + 1, dtype=torch.int64, device="cuda")
+            codec.encode_raw(src.data_ptr(), n, chunk, comp.data_ptr(), n, off.data_ptr(), None, None)
+            codec.sync()
+            srcs.append(src); refs.append((comp, off))
+    finally:
+        os.environ.pop("HZ_ENC_CHAIN", None); codec.reload_knobs()
+    other = hz.Codec(0)
+    s2 = torch.cuda.Stream()
+    other.set_stream(s2.cuda_stream)
+    try:
+        outs = []
+        for it in range(12):
+            for c, i in ((codec, it % 3), (other, (it + 1) % 3)):
+                n = shapes[i][0]; K = (n + chunk - 1) // chunk
+                comp = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+                off = torch.zeros(K + 1, dtype=torch.int64, device="cuda")
+                c.encode_raw(srcs[i].data_ptr(), n, chunk, comp.data_ptr(), n, off.data_ptr(), None, None)
+                outs.append((i, comp, off))
+        codec.sync(); other.sync()
+        for i, comp, off in outs:
+            assert torch.equal(off, refs[i][1]) and torch.equal(comp, refs[i][0]), "shape %d" % i
+    finally:
+        other.close()
+
+
 def test_config3_1gib_32mib_chunks_every_chunk_against_the_oracle(codec):
     """BASELINE config 3 (1 GiB Zipf, ~4 bits/symbol) at the CLI's default chunk size of 32 MiB: code lengths,
     compressed sizes and the SHA-256 of EVERY chunk's payload equal the oracle's (chunk-parallel fast coder), and
