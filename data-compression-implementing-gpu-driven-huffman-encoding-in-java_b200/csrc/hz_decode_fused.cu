@@ -217,6 +217,12 @@ __device__ __forceinline__ void fu_put(uint64_t* R, uint32_t ring_a, uint32_t u,
     sts128(ring_a + (u & (FU_RING - 1)) * 16, make_uint4((uint32_t)rec, (uint32_t)(rec >> 32), u + 1, 0u));
     st_rec(R + u, rec);
 }
+// A warp marks the unit it has just been handed as PENDING in the ring (tag set, record EMPTY): a look-back that meets
+// the mark knows the record will appear HERE and polls shared memory - without it every look at a unit this CTA is
+// still decoding went to global memory (a round trip to L2 to read EMPTY, and again for every poll).
+__device__ __forceinline__ void fu_mark_pending(uint32_t ring_a, uint32_t u) {
+    sts128(ring_a + (u & (FU_RING - 1)) * 16, make_uint4(0u, 0u, u + 1, 0u));
+}
 __device__ __forceinline__ uint64_t fu_get(const uint64_t* R, uint32_t ring_a, int q) {
     const uint4 e = lds128(ring_a + ((uint32_t)q & (FU_RING - 1)) * 16);
     if (e.z == (uint32_t)q + 1) return (uint64_t)e.x | ((uint64_t)e.y << 32);
@@ -706,7 +712,7 @@ dec_fused_kernel(const FuArgs a) {
         uint32_t u = 0;
         if (lane == 0) u = atomicAdd(a.P.unit_ctr + k, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
-        if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
+        if (u < nunit && lane == 0) { fu_mark_pending(ring_a, u); fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw)); }
         FU_T(8);
         fu_mbar_wait(smem_u32(&S.tbar), tphase); tphase ^= 1;
         FU_T(9);
@@ -930,7 +936,7 @@ dec_fused_kernel(const FuArgs a) {
             // tickets out of a per-CTA pool of blocks drawn ahead 5 % slower (30 % where CTAs share a chunk).
             if (!tk_drawn && lane == 0) tk = atomicAdd(a.P.unit_ctr + k, 1u);
             u = __shfl_sync(0xffffffffu, tk, 0);
-            if (u < nunit && lane == 0) fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw));
+            if (u < nunit && lane == 0) { fu_mark_pending(ring_a, u); fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw)); }
             // the chunk's last unit: when the stream holds fewer symbols than orig_size the decoder goes on reading
             // zero bits (TableBasedHuffmanDecoder.java:204-208), i.e. the all-zero codeword's symbol repeats
             if (u_cur == nunit - 1) {
