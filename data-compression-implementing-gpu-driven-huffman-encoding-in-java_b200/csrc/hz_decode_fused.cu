@@ -20,8 +20,11 @@
 //   4. compacts the 32 rows in place (all rows to registers, then shifted word stores) into one contiguous
 //      window aligned like the destination and sends it to global memory with one asynchronous bulk copy.
 // Units are handed out in stream order by a per-chunk atomic counter, so a unit only ever waits for units that
-// running warps hold.  A CTA (24 warps) keeps one chunk's lookup table (32 KiB, shared by its warps); CTAs take
-// chunks from a global ticket and, when none are left, join chunks that still have units.
+// running warps hold.  A CTA keeps one chunk's lookup table (33 KiB, delivered by one bulk copy, shared by its warps);
+// CTAs take chunks from a global ticket (drawn a chunk ahead) and, when none are left, join chunks that still have
+// units.  The CTA shape follows the stream's units per chunk - 24 warps x 1 CTA per SM, 8 x 2 or 5 x 3 - so that
+// streams of small chunks keep several independent CTAs per SM (hzk_decode_fused); the chunk's last subsequence ends
+// with the chunk, symbols the stream does not hold are the all-zero codeword's (TableBasedHuffmanDecoder.java:204-208).
 #include <cstdio>
 #include "hz_decode_tables.cuh"
 
