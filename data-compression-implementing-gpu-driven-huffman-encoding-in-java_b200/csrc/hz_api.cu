@@ -93,6 +93,7 @@ void hz_read_knobs(hz_knobs* k) {
     k->fu_grid = num("HZ_FU_GRID", 0);
     k->fu_warps = num("HZ_FU_WARPS", 0);
     k->enc_chain = num("HZ_ENC_CHAIN", 1);
+    k->fu_cluster = num("HZ_FU_CLUSTER", -1);
     if (const char* ev = getenv("HZ_FU_DUMP")) k->fu_dump = ev;
 }
 

@@ -45,6 +45,7 @@ struct hz_knobs {
     int fu_grid = 0;           // HZ_FU_GRID      CTAs of the fused decoder
     int fu_warps = 0;          // HZ_FU_WARPS     warps per CTA of the fused decoder (24, 8 or 5)
     int enc_chain = 1;         // HZ_ENC_CHAIN    0: separate histogram / codebook / offsets / encode launches
+    int fu_cluster = -1;       // HZ_FU_CLUSTER   0 / 1: never / always launch the 24-warp fused decoder as cluster pairs
     std::string fu_dump;       // HZ_FU_DUMP      file for per-subsequence records
 };
 void hz_read_knobs(hz_knobs* k);

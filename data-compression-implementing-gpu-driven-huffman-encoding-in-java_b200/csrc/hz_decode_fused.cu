@@ -42,19 +42,26 @@
 #define FU_TABLE_BYTES (LUTN * 8 + 1024)           // wlut + DecAux
 #define FU_NONE 0xFFFFFFFFu
 #define FU_RING 64                                 // > look-back window (32) + units in flight in one CTA (24)
+#define FU_RING_CL 128                             // cluster pair: both CTAs' units of the shared chunk
 
-struct FuShared {
+template <int RN>
+struct FuSharedT {
     __align__(16) uint2 wlut[LUTN];
     __align__(16) uint8_t aux[1024];
-    __align__(16) uint4 ring[FU_RING];       // look-back records of the units THIS CTA decoded: {record, unit + 1}
+    __align__(16) uint4 ring[RN];            // look-back records: {record, unit + 1, chunk + 1} of the units THIS CTA decoded (and, in a cluster, its peer)
     __align__(8) uint64_t bar[FU_WARPS_MAX];
     __align__(8) uint64_t tbar;              // the chunk's table arrives by ONE bulk copy
     uint32_t s_k, s_pick;
+    uint32_t peer_k;                         // cluster: chunk + 1 the PEER CTA works on (written by the peer through DSMEM), 0 = none
 };
+typedef FuSharedT<FU_RING> FuShared;
 static_assert(offsetof(FuShared, aux) + offsetof(DecAux, sorted) == DEC_W_SORTED_REL, "long-code entries address sorted[] relative to wlut");
 static_assert(offsetof(FuShared, wlut) == 0 && offsetof(FuShared, aux) == LUTN * 8, "wlut + aux are one contiguous bulk-copy destination");
-#define FU_SHARED_BYTES ((sizeof(FuShared) + 15) & ~(size_t)15)
-#define FU_SMEM_BYTES(W) (FU_SHARED_BYTES + (size_t)(W) * FU_WARP_BYTES)
+static_assert(offsetof(FuSharedT<FU_RING_CL>, aux) == LUTN * 8, "same table layout with the larger ring");
+#define FU_SHARED_BYTES_RN(RN) ((sizeof(FuSharedT<RN>) + 15) & ~(size_t)15)
+#define FU_SMEM_BYTES_CL(W, CL) (FU_SHARED_BYTES_RN((CL) == 2 ? FU_RING_CL : FU_RING) + (size_t)(W) * FU_WARP_BYTES)
+#define FU_SMEM_BYTES(W) FU_SMEM_BYTES_CL(W, 1)
+static_assert(FU_SMEM_BYTES_CL(24, 2) <= 227 * 1024, "24 warps + the cluster ring fit one SM");
 
 struct FuPlan {
     uint64_t* orig_off;     // [K+1]
@@ -215,32 +222,49 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
 
 // A record lives in global memory (every CTA that works on the chunk sees it) and, for the units this CTA decoded
 // itself, in a shared-memory ring that spares the look-back the global round trips (a CTA that has a chunk to
-// itself never leaves shared memory).  Ring entries are written and read as ONE 128-bit access.
-__device__ __forceinline__ void fu_put(uint64_t* R, uint32_t ring_a, uint32_t u, uint64_t rec) {
-    sts128(ring_a + (u & (FU_RING - 1)) * 16, make_uint4((uint32_t)rec, (uint32_t)(rec >> 32), u + 1, 0u));
+// itself never leaves shared memory).  Ring entries are written and read as ONE 128-bit access and carry the unit and
+// the chunk they belong to.  In a cluster pair (streams with fewer chunks than SMs, where CTAs share chunks from the
+// start) a CTA also PUSHES its entries into the peer's ring through distributed shared memory while the peer works on
+// the same chunk: the peer's look-backs then stay in its own shared memory instead of polling L2.
+struct FuRing {
+    uint32_t a;          // shared address of this CTA's ring
+    uint32_t mask;       // entries - 1
+    uint32_t ktag;       // chunk + 1
+    uint32_t peer;       // shared::cluster address of the peer's ring while it works on this chunk, else 0
+};
+__device__ __forceinline__ void fu_remote_st128(uint32_t ra, uint4 v) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void fu_ring_store(const FuRing& g, uint32_t u, uint4 e) {
+    const uint32_t o = (u & g.mask) * 16;
+    sts128(g.a + o, e);
+    if (g.peer) fu_remote_st128(g.peer + o, e);
+}
+__device__ __forceinline__ void fu_put(uint64_t* R, const FuRing& g, uint32_t u, uint64_t rec) {
+    fu_ring_store(g, u, make_uint4((uint32_t)rec, (uint32_t)(rec >> 32), u + 1, g.ktag));
     st_rec(R + u, rec);
 }
 // A warp marks the unit it has just been handed as PENDING in the ring (tag set, record EMPTY): a look-back that meets
 // the mark knows the record will appear HERE and polls shared memory - without it every look at a unit this CTA is
 // still decoding went to global memory (a round trip to L2 to read EMPTY, and again for every poll).
-__device__ __forceinline__ void fu_mark_pending(uint32_t ring_a, uint32_t u) {
-    sts128(ring_a + (u & (FU_RING - 1)) * 16, make_uint4(0u, 0u, u + 1, 0u));
+__device__ __forceinline__ void fu_mark_pending(const FuRing& g, uint32_t u) {
+    fu_ring_store(g, u, make_uint4(0u, 0u, u + 1, g.ktag));
 }
-__device__ __forceinline__ uint64_t fu_get(const uint64_t* R, uint32_t ring_a, int q) {
-    const uint4 e = lds128(ring_a + ((uint32_t)q & (FU_RING - 1)) * 16);
-    if (e.z == (uint32_t)q + 1) return (uint64_t)e.x | ((uint64_t)e.y << 32);
+__device__ __forceinline__ uint64_t fu_get(const uint64_t* R, const FuRing& g, int q) {
+    const uint4 e = lds128(g.a + ((uint32_t)q & g.mask) * 16);
+    if (e.z == (uint32_t)q + 1 && e.w == g.ktag) return (uint64_t)e.x | ((uint64_t)e.y << 32);
     return ld_rec(R + q);
 }
-__device__ __forceinline__ void fu_wait_rec(const uint64_t* R, uint32_t ring_a, int q, uint32_t min_state) {
+__device__ __forceinline__ void fu_wait_rec(const uint64_t* R, const FuRing& g, int q, uint32_t min_state) {
     uint32_t ns = 32;
-    while (((uint32_t)fu_get(R, ring_a, q) & 3u) < min_state) { __nanosleep(ns); if (ns < 256) ns += ns; }
+    while (((uint32_t)fu_get(R, g, q) & 3u) < min_state) { __nanosleep(ns); if (ns < 256) ns += ns; }
 }
 
 // Decoupled look-back of unit u (u >= 1) over the chunk's records R[0..u).  Returns true with the number of
 // symbols before the unit in `prefix`, or false with the true entry of the unit's first subsequence in
 // `true_entry` when the unit has to re-walk (its guess differs from the FINAL exit of unit u - 1).
 // Waiting (for a record to be published, or for the owner of a broken link to finalise) polls ONE record.
-__device__ bool fu_lookback(const uint64_t* __restrict__ R, uint32_t ring_a, uint32_t u, uint32_t my_entry0, uint32_t lane,
+__device__ bool fu_lookback(const uint64_t* __restrict__ R, const FuRing ring_a, uint32_t u, uint32_t my_entry0, uint32_t lane,
                             uint32_t& prefix, uint32_t& true_entry) {
     uint32_t acc = 0, expect = my_entry0;
     int base = (int)u - 1;
@@ -622,70 +646,116 @@ struct FuArgs {
 // of wlut + aux, completion on S.tbar) and draws the next ticket.  When the tickets have run out (few large
 // chunks) the CTA joins a chunk that still has units.  Called by all threads after a barrier that follows the last
 // use of the previous table.
-__device__ __forceinline__ void fu_table_issue(const FuArgs& a, FuShared& S, uint32_t k) {
+template <class SH>
+__device__ __forceinline__ void fu_table_issue(const FuArgs& a, SH& S, uint32_t k) {
     const uint32_t bar_a = smem_u32(&S.tbar), dst = smem_u32(S.wlut);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "n"(FU_TABLE_BYTES) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(a.tables + (size_t)k * FU_TABLE_BYTES), "n"(FU_TABLE_BYTES), "r"(bar_a) : "memory");
 }
-__device__ uint32_t fu_pick_chunk(const FuArgs& a, FuShared& S, uint32_t& ahead) {
+// cluster pair (CL == 2): rank of this CTA and DSMEM helpers
+__device__ __forceinline__ uint32_t fu_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t fu_mapa(uint32_t local_a, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_a), "r"(rank)); return r;
+}
+__device__ __forceinline__ void fu_remote_st32(uint32_t ra, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fu_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// CL == 2: the pair works as ONE team - the even CTA picks (ticket, then helping), the odd CTA FOLLOWS it: it waits for
+// the peer's announcement (S.peer_k of this CTA, written by the peer through DSMEM; bounded wait, then it picks for
+// itself) and takes the same chunk, so that the chunk's units are shared by two CTAs whose rings see each other's
+// records.  Every CTA announces the chunk it is on to its peer (0xFFFFFFFF: no more work); stale values only cost a
+// missed or a useless push: ring entries carry their chunk, and every record is in global memory as well.
+// `ahead` of the odd CTA holds the last announcement it followed.
+#define FU_ANN_NONE 0xFFFFFFFFu
+template <class SH, int CL>
+__device__ uint32_t fu_pick_chunk(const FuArgs& a, SH& S, uint32_t& ahead, uint32_t cl_rank) {
     const uint32_t K = a.K;
+    bool follow = false;
     if (threadIdx.x == 0) {
-        uint32_t k = FU_NONE, t = ahead;
-        for (;;) {
-            if (t >= K) break;
-            if (a.P.nunit[t]) { k = t; break; }
-            t = atomicAdd(&a.P.ctl[0], 1u);
+        uint32_t k = FU_NONE;
+        bool decided = false;
+        if (CL == 2 && cl_rank == 1) {
+            uint32_t pk = ahead, spins = 0;
+            while ((pk = *reinterpret_cast<volatile uint32_t*>(&S.peer_k)) == ahead && ++spins < (1u << 16)) __nanosleep(64);
+            if (pk != ahead) {
+                ahead = pk; decided = true;
+                if (pk != FU_ANN_NONE && pk != 0) { k = pk - 1; fu_table_issue(a, S, k); }
+            }
         }
-        if (k != FU_NONE) { fu_table_issue(a, S, k); ahead = atomicAdd(&a.P.ctl[0], 1u); }
-        else ahead = K;
-        S.s_k = k; S.s_pick = FU_NONE;
+        if (!decided) {
+            uint32_t t = (CL == 2 && cl_rank == 1) ? atomicAdd(&a.P.ctl[0], 1u) : ahead;   // (a follower that timed out holds no ticket)
+            for (;;) {
+                if (t >= K) break;
+                if (a.P.nunit[t]) { k = t; break; }
+                t = atomicAdd(&a.P.ctl[0], 1u);
+            }
+            if (k != FU_NONE) { fu_table_issue(a, S, k); if (!(CL == 2 && cl_rank == 1)) ahead = atomicAdd(&a.P.ctl[0], 1u); }
+            else if (!(CL == 2 && cl_rank == 1)) ahead = K;
+        }
+        S.s_k = k; S.s_pick = (CL == 2 && cl_rank == 1 && decided) ? 0u : FU_NONE;    // s_pick == 0: the follower does not search
     }
-    if (threadIdx.x < FU_RING) S.ring[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = threadIdx.x; i < sizeof(S.ring) / sizeof(S.ring[0]); i += blockDim.x) S.ring[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    if (S.s_k != FU_NONE) return S.s_k;
-    if (K > 2048) return FU_NONE;                         // thousands of chunks balance by themselves
-    // helping: the first chunk (from a start that spreads the CTAs) whose unit counter has not run out
-    const uint32_t start = (uint32_t)(((uint64_t)blockIdx.x * K) / gridDim.x);
-    for (uint32_t i0 = 0; i0 < K; i0 += blockDim.x) {
-        const uint32_t i = i0 + threadIdx.x;
-        if (i < K) {
-            const uint32_t k = (start + i) % K;
-            const uint32_t nu = a.P.nunit[k];
-            if (nu && *reinterpret_cast<volatile uint32_t*>(a.P.unit_ctr + k) < nu) atomicMin(&S.s_pick, i);
+    uint32_t k = S.s_k;
+    follow = CL == 2 && cl_rank == 1 && S.s_pick == 0u;
+    if (threadIdx.x == 0 && follow) S.s_pick = FU_NONE;
+    __syncthreads();
+    if (k == FU_NONE && K <= 2048 && !follow) {           // (thousands of chunks balance by themselves)
+        // helping: the first chunk (from a start that spreads the CTAs) whose unit counter has not run out
+        const uint32_t start = (uint32_t)(((uint64_t)blockIdx.x * K) / gridDim.x);
+        for (uint32_t i0 = 0; i0 < K; i0 += blockDim.x) {
+            const uint32_t i = i0 + threadIdx.x;
+            if (i < K) {
+                const uint32_t c = (start + i) % K;
+                const uint32_t nu = a.P.nunit[c];
+                if (nu && *reinterpret_cast<volatile uint32_t*>(a.P.unit_ctr + c) < nu) atomicMin(&S.s_pick, i);
+            }
+            __syncthreads();
+            if (S.s_pick != FU_NONE) break;
         }
         __syncthreads();
-        if (S.s_pick != FU_NONE) break;
+        const uint32_t p = S.s_pick;
+        if (p != FU_NONE) {
+            k = (start + p) % K;
+            if (threadIdx.x == 0) fu_table_issue(a, S, k);
+        }
     }
-    __syncthreads();
-    const uint32_t p = S.s_pick;
-    if (p == FU_NONE) return FU_NONE;
-    const uint32_t k = (start + p) % K;
-    if (threadIdx.x == 0) fu_table_issue(a, S, k);
+    if (CL == 2 && threadIdx.x == 0)
+        fu_remote_st32(fu_mapa(smem_u32(&S.peer_k), cl_rank ^ 1u), k == FU_NONE ? FU_ANN_NONE : k + 1);
     return k;
 }
 
 // W = warps per CTA, MINB = CTAs per SM: <24, 1> for chunks of many units; <8, 2> and <5, 3> for streams of small
 // chunks, where several independent CTAs per SM (each with its own chunk's table) overlap one CTA's per-chunk
 // serial part (ticket, table copy, barriers, the chain of a few units) with the others' walks
-template <int W, int MINB>
+// CL = 2: launched as cluster pairs (streams with fewer chunks than SMs): the pair shares chunks through its rings.
+template <int W, int MINB, int CL>
 __global__ void __launch_bounds__(W * 32, MINB)
 dec_fused_kernel(const FuArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    FuShared& S = *reinterpret_cast<FuShared*>(smem_raw);
+    typedef FuSharedT<CL == 2 ? FU_RING_CL : FU_RING> SH;
+    SH& S = *reinterpret_cast<SH*>(smem_raw);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t stage_a = pin_reg(smem_u32(smem_raw + FU_SHARED_BYTES + (size_t)wid * FU_WARP_BYTES));
+    const uint32_t stage_a = pin_reg(smem_u32(smem_raw + FU_SHARED_BYTES_RN(CL == 2 ? FU_RING_CL : FU_RING) + (size_t)wid * FU_WARP_BYTES));
     const uint32_t rows_a = stage_a + FU_STAGE_BYTES;
     const uint32_t bar_a = smem_u32(&S.bar[wid]);
     const uint32_t wlut_a = pin_reg(smem_u32(S.wlut)), aux_a = pin_reg(smem_u32(S.aux));
-    const uint32_t ring_a = smem_u32(S.ring);
+    FuRing ring_a;
+    ring_a.a = smem_u32(S.ring); ring_a.mask = (CL == 2 ? FU_RING_CL : FU_RING) - 1; ring_a.ktag = 0; ring_a.peer = 0;
+    const uint32_t cl_rank = CL == 2 ? fu_cluster_rank() : 0u;
+    const uint32_t peer_ring = CL == 2 ? fu_mapa(ring_a.a, cl_rank ^ 1u) : 0u;
     const DecAux& A = *reinterpret_cast<const DecAux*>(S.aux);
     if (lane == 0) {
         mbar_init(&S.bar[wid], 1);
-        if (wid == 0) mbar_init(&S.tbar, 1);
+        if (wid == 0) { mbar_init(&S.tbar, 1); S.peer_k = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (CL == 2) fu_cluster_sync();                       // the peer CTA has started: its shared memory may be written
 #ifdef FU_TIMING
     long long tim__[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, last__ = clock64();
 #endif
@@ -693,12 +763,13 @@ dec_fused_kernel(const FuArgs a) {
     uint32_t tphase = 0;                                  // parity of the table's mbarrier
     bool out_pending = false;                             // a bulk copy out of this warp's rows may still be reading them
     uint32_t ahead = 0;                                   // thread 0: the chunk ticket drawn ahead
-    if (threadIdx.x == 0) ahead = atomicAdd(&a.P.ctl[0], 1u);
+    if (threadIdx.x == 0 && !(CL == 2 && cl_rank == 1)) ahead = atomicAdd(&a.P.ctl[0], 1u);   // (the odd CTA of a pair follows its peer)
     __syncthreads();
 
     for (;;) {
-        const uint32_t k = fu_pick_chunk(a, S, ahead);
+        const uint32_t k = fu_pick_chunk<SH, CL>(a, S, ahead, cl_rank);
         if (k == FU_NONE) break;
+        ring_a.ktag = CL == 2 ? k + 1 : 0u;               // (a lone CTA's ring is reset per chunk and only it writes to it)
         FU_T(11);
         FU_TRACE(0, k);
         // the chunk's geometry and this warp's first unit are fetched while the table is on its way
@@ -715,6 +786,7 @@ dec_fused_kernel(const FuArgs a) {
         uint32_t u = 0;
         if (lane == 0) u = atomicAdd(a.P.unit_ctr + k, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
+        if (CL == 2) ring_a.peer = *reinterpret_cast<volatile uint32_t*>(&S.peer_k) == k + 1 ? peer_ring : 0u;
         if (u < nunit && lane == 0) { fu_mark_pending(ring_a, u); fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw)); }
         FU_T(8);
         fu_mbar_wait(smem_u32(&S.tbar), tphase); tphase ^= 1;
@@ -939,6 +1011,7 @@ dec_fused_kernel(const FuArgs a) {
             // tickets out of a per-CTA pool of blocks drawn ahead 5 % slower (30 % where CTAs share a chunk).
             if (!tk_drawn && lane == 0) tk = atomicAdd(a.P.unit_ctr + k, 1u);
             u = __shfl_sync(0xffffffffu, tk, 0);
+            if (CL == 2) ring_a.peer = *reinterpret_cast<volatile uint32_t*>(&S.peer_k) == k + 1 ? peer_ring : 0u;
             if (u < nunit && lane == 0) { fu_mark_pending(ring_a, u); fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw)); }
             // the chunk's last unit: when the stream holds fewer symbols than orig_size the decoder goes on reading
             // zero bits (TableBasedHuffmanDecoder.java:204-208), i.e. the all-zero codeword's symbol repeats
@@ -957,6 +1030,7 @@ dec_fused_kernel(const FuArgs a) {
         FU_TRACE(7, k);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the copies
+    if (CL == 2) { __syncthreads(); fu_cluster_sync(); }  // ... and the peer's pushes into it: the pair leaves together
 #ifdef FU_TIMING
     FU_T(0);
     if (lane == 0 && a.tim) for (int i = 0; i < 12; ++i) atomicAdd(a.tim + i, (unsigned long long)tim__[i]);
@@ -988,9 +1062,10 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
     HZ_TRY(hz_reserve(ctx, &ctx->dec_rec, max_units * sizeof(uint64_t)));
     HZ_TRY(hz_reserve(ctx, &ctx->dec_tables, (size_t)K * FU_TABLE_BYTES));
     if (!ctx->attr_decode_fused) {
-        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(24)));
-        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(8)));
-        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(5)));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<24, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(24)));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<24, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES_CL(24, 2)));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<8, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(8)));
+        HZ_CUDA(ctx, cudaFuncSetAttribute(dec_fused_kernel<5, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES(5)));
         ctx->attr_decode_fused = true;
     }
     const uint32_t lead_knob = (uint32_t)ctx->knobs.fu_lead;   // developer knob
@@ -1022,11 +1097,39 @@ int hzk_decode_fused(hz_ctx* ctx, const uint8_t* d_comp, uint64_t comp_bytes, co
     const unsigned per_sm = warps == 24 ? 1u : (warps == 5 ? 3u : 2u);
     const unsigned grid = grid_knob > 0 ? (unsigned)grid_knob : per_sm * (unsigned)ctx->sm_count;
     void (*kfn)(const FuArgs) = nullptr;
-    if (warps == 24) kfn = dec_fused_kernel<24, 1>;
-    else if (warps == 8) kfn = dec_fused_kernel<8, 2>;
-    else if (warps == 5) kfn = dec_fused_kernel<5, 3>;
+    if (warps == 24) kfn = dec_fused_kernel<24, 1, 1>;
+    else if (warps == 8) kfn = dec_fused_kernel<8, 2, 1>;
+    else if (warps == 5) kfn = dec_fused_kernel<5, 3, 1>;
     else return hz_fail(ctx, HZ_ERR_ARG, "HZ_FU_WARPS must be 24, 8 or 5");
-    HZ_LAUNCH(ctx, "dec_fused", kfn, grid, warps * 32, FU_SMEM_BYTES(warps), a);
+    // Fewer chunks than CTAs (1 GiB in 16 MiB chunks: 64 chunks for 148 SMs): CTAs share chunks from the start, and a
+    // look-back at a unit another CTA holds costs round trips to L2 (look-back 17 % of the warps' time against 9 %).
+    // The grid is then launched as CLUSTER PAIRS: the odd CTA joins its peer's chunk and the two push their records into
+    // each other's ring through distributed shared memory (developer knob HZ_FU_CLUSTER=0|1 forces either).
+    // Measured on B200 (4 bits/symbol, 1 GiB): 64 chunks of 16 MiB 896 -> 968 GB/s, 32 chunks of 32 MiB 868 -> 908, H = 2: 966 -> 1,072;
+    // with a chunk or more per CTA the pairs lose (128 chunks of 8 MiB: 1,014 -> 960), so: pairs when every pair can own a chunk.
+    bool pairs = warps == 24 && grid_knob <= 0 && 2 * (uint64_t)K <= grid && (grid & 1u) == 0;
+    if (ctx->knobs.fu_cluster >= 0) pairs = ctx->knobs.fu_cluster == 1 && warps == 24 && (grid & 1u) == 0;
+    if (pairs) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(24 * 32); cfg.dynamicSmemBytes = FU_SMEM_BYTES_CL(24, 2); cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, dec_fused_kernel<24, 1, 2>, &cfg) != cudaSuccess) { cudaGetLastError(); max_clusters = 0; }
+        if ((unsigned)max_clusters * 2 >= grid) {         // every pair is resident at once (the kernel is persistent)
+            hz_prof_begin(ctx);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, dec_fused_kernel<24, 1, 2>, a);
+            ctx->launches++;
+            hz_prof_end(ctx, "dec_fused");
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e != cudaSuccess) return hz_cuda_fail(ctx, e, "dec_fused (cluster pairs)");
+        } else {
+            pairs = false;
+        }
+    }
+    if (!pairs) HZ_LAUNCH(ctx, "dec_fused", kfn, grid, warps * 32, FU_SMEM_BYTES(warps), a);
 #ifdef FU_TIMING
     cudaStreamSynchronize(ctx->stream);
     {

@@ -42,8 +42,9 @@ def test_shipped_objects_hold_the_claimed_instructions(objects):
     assert "PREEXIT" in cb and "LDG.E.64.STRONG.GPU" in cb and "NANOSLEEP" in cb
     assert "LDG.E.64.STRONG.GPU" in enc and "NANOSLEEP" in enc and "PREEXIT" not in enc
     fused = _sass(os.path.join(objects, "hz_decode_fused.o"))
-    for shape in ("ILi24ELi1E", "ILi8ELi2E", "ILi5ELi3E"):         # CTA shapes of the fused decoder: 24 x 1, 8 x 2, 5 x 3 warps
-        assert "dec_fused_kernel" + shape in fused
+    for shape in ("ILi24ELi1ELi1E", "ILi8ELi2ELi1E", "ILi5ELi3ELi1E", "ILi24ELi1ELi2E"):   # CTA shapes of the fused decoder: 24 x 1, 8 x 2,
+        assert "dec_fused_kernel" + shape in fused                                          # 5 x 3 warps, and 24 x 1 as cluster pairs
+    assert fused.count("UCGABAR_ARV") == 2 and fused.count("UCGABAR_WAIT") == 2           # the pair's two cluster barriers (start, exit)
     for text in (dec, enc, hist, cb):
         assert "sm_100a" in text or "SM100" in text.upper() or "EF_CUDA_SM100" in text
 

@@ -246,16 +246,18 @@ def test_decode_damaged_streams_match_the_oracle(codec, decmode, H, chunk):
             assert np.array_equal(out, ref), "chunk %d trial %d" % (k, trial)
 
 
-@pytest.mark.parametrize("warps", ["24", "8", "5"])
+@pytest.mark.parametrize("warps", ["24", "8", "5", "24 as cluster pairs"])
 def test_fused_decoder_cta_shapes(codec, knob, warps):
     """The fused decoder picks its CTA shape by the units per chunk (24 warps x 1 CTA per SM, 8 x 2, 5 x 3;
-    HZ_FU_WARPS forces one).  Every shape on: thousands of small chunks of mixed entropy with a ragged tail, chunks
+    HZ_FU_WARPS forces one; with fewer chunks than SMs the 24-warp grid is launched as cluster pairs, HZ_FU_CLUSTER=1).  Every shape on: thousands of small chunks of mixed entropy with a ragged tail, chunks
     whose payload ends exactly on / one byte around a subsequence and a unit boundary, a payload that holds MORE
     symbols than orig_size and one that holds FEWER (the chunk's last subsequence stops at the chunk's end and the
     all-zero codeword's symbol fills the rest, TableBasedHuffmanDecoder.java:204-208), damaged streams."""
     knob("HZ_DEC", "fused")
-    knob("HZ_FU_WARPS", warps)
-    rng = np.random.default_rng(int(warps) + 40)
+    knob("HZ_FU_WARPS", warps.split()[0])
+    if "pairs" in warps:                                   # the launch of streams with fewer chunks than SMs (DSMEM ring pushes)
+        knob("HZ_FU_CLUSTER", "1")
+    rng = np.random.default_rng(int(warps.split()[0]) + 40)
     # 1. many small chunks
     parts = [datasets.zipf_stream(200_000, H, seed=70 + H) for H in (1, 3, 4, 6, 7)]
     data = np.concatenate(parts + [datasets.zipf_stream(12_345, 5, seed=80)])
