@@ -48,12 +48,14 @@ template <int RN>
 struct FuSharedT {
     __align__(16) uint2 wlut[LUTN];
     __align__(16) uint8_t aux[1024];
-    __align__(16) uint4 ring[RN];            // look-back records: {record, unit + 1, chunk + 1} of the units THIS CTA decoded (and, in a cluster, its peer)
+    __align__(16) uint4 ring[RN + (RN == FU_RING_CL ? 1 : 0)];   // look-back records: {record, unit + 1, chunk + 1} of the units THIS CTA decoded (and, in a
+                                             // cluster, its peer); the cluster layout's extra entry holds peer_k (fu_peer_k): a lone CTA's layout is unchanged
     __align__(8) uint64_t bar[FU_WARPS_MAX];
     __align__(8) uint64_t tbar;              // the chunk's table arrives by ONE bulk copy
     uint32_t s_k, s_pick;
-    uint32_t peer_k;                         // cluster: chunk + 1 the PEER CTA works on (written by the peer through DSMEM), 0 = none
 };
+// cluster: chunk + 1 the PEER CTA works on (written by the peer through DSMEM), 0 = nothing announced yet
+template <class SH> __device__ __forceinline__ volatile uint32_t* fu_peer_k(SH& S) { return reinterpret_cast<volatile uint32_t*>(&S.ring[FU_RING_CL]); }
 typedef FuSharedT<FU_RING> FuShared;
 static_assert(offsetof(FuShared, aux) + offsetof(DecAux, sorted) == DEC_W_SORTED_REL, "long-code entries address sorted[] relative to wlut");
 static_assert(offsetof(FuShared, wlut) == 0 && offsetof(FuShared, aux) == LUTN * 8, "wlut + aux are one contiguous bulk-copy destination");
@@ -228,42 +230,48 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
 // the same chunk: the peer's look-backs then stay in its own shared memory instead of polling L2.
 struct FuRing {
     uint32_t a;          // shared address of this CTA's ring
-    uint32_t mask;       // entries - 1
     uint32_t ktag;       // chunk + 1
     uint32_t peer;       // shared::cluster address of the peer's ring while it works on this chunk, else 0
 };
 __device__ __forceinline__ void fu_remote_st128(uint32_t ra, uint4 v) {
     asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// (CL is the kernel's cluster size: for a lone CTA the ring size, the chunk tag and the peer are compile-time constants)
+template <int CL>
 __device__ __forceinline__ void fu_ring_store(const FuRing& g, uint32_t u, uint4 e) {
-    const uint32_t o = (u & g.mask) * 16;
+    const uint32_t o = (u & (CL == 2 ? FU_RING_CL - 1 : FU_RING - 1)) * 16;
     sts128(g.a + o, e);
-    if (g.peer) fu_remote_st128(g.peer + o, e);
+    if (CL == 2 && g.peer) fu_remote_st128(g.peer + o, e);
 }
+template <int CL>
 __device__ __forceinline__ void fu_put(uint64_t* R, const FuRing& g, uint32_t u, uint64_t rec) {
-    fu_ring_store(g, u, make_uint4((uint32_t)rec, (uint32_t)(rec >> 32), u + 1, g.ktag));
+    fu_ring_store<CL>(g, u, make_uint4((uint32_t)rec, (uint32_t)(rec >> 32), u + 1, CL == 2 ? g.ktag : 0u));
     st_rec(R + u, rec);
 }
 // A warp marks the unit it has just been handed as PENDING in the ring (tag set, record EMPTY): a look-back that meets
 // the mark knows the record will appear HERE and polls shared memory - without it every look at a unit this CTA is
 // still decoding went to global memory (a round trip to L2 to read EMPTY, and again for every poll).
+template <int CL>
 __device__ __forceinline__ void fu_mark_pending(const FuRing& g, uint32_t u) {
-    fu_ring_store(g, u, make_uint4(0u, 0u, u + 1, g.ktag));
+    fu_ring_store<CL>(g, u, make_uint4(0u, 0u, u + 1, CL == 2 ? g.ktag : 0u));
 }
+template <int CL>
 __device__ __forceinline__ uint64_t fu_get(const uint64_t* R, const FuRing& g, int q) {
-    const uint4 e = lds128(g.a + ((uint32_t)q & g.mask) * 16);
-    if (e.z == (uint32_t)q + 1 && e.w == g.ktag) return (uint64_t)e.x | ((uint64_t)e.y << 32);
+    const uint4 e = lds128(g.a + ((uint32_t)q & (CL == 2 ? FU_RING_CL - 1 : FU_RING - 1)) * 16);
+    if (e.z == (uint32_t)q + 1 && (CL != 2 || e.w == g.ktag)) return (uint64_t)e.x | ((uint64_t)e.y << 32);
     return ld_rec(R + q);
 }
+template <int CL>
 __device__ __forceinline__ void fu_wait_rec(const uint64_t* R, const FuRing& g, int q, uint32_t min_state) {
     uint32_t ns = 32;
-    while (((uint32_t)fu_get(R, g, q) & 3u) < min_state) { __nanosleep(ns); if (ns < 256) ns += ns; }
+    while (((uint32_t)fu_get<CL>(R, g, q) & 3u) < min_state) { __nanosleep(ns); if (ns < 256) ns += ns; }
 }
 
 // Decoupled look-back of unit u (u >= 1) over the chunk's records R[0..u).  Returns true with the number of
 // symbols before the unit in `prefix`, or false with the true entry of the unit's first subsequence in
 // `true_entry` when the unit has to re-walk (its guess differs from the FINAL exit of unit u - 1).
 // Waiting (for a record to be published, or for the owner of a broken link to finalise) polls ONE record.
+template <int CL>
 __device__ bool fu_lookback(const uint64_t* __restrict__ R, const FuRing ring_a, uint32_t u, uint32_t my_entry0, uint32_t lane,
                             uint32_t& prefix, uint32_t& true_entry) {
     uint32_t acc = 0, expect = my_entry0;
@@ -272,7 +280,7 @@ __device__ bool fu_lookback(const uint64_t* __restrict__ R, const FuRing ring_a,
     //  round trip to L2 less per unit when the record comes from another CTA)
     for (;;) {
         const int j = base - (int)lane;
-        const uint64_t rec = j >= 0 ? fu_get(R, ring_a, j) : 0ull;
+        const uint64_t rec = j >= 0 ? fu_get<CL>(R, ring_a, j) : 0ull;
         const uint32_t w = (uint32_t)rec;
         const uint32_t st = w & 3, en = (w >> 2) & 63, ex = (w >> 8) & 63, cnt = (w >> 14) & 0x3FFFF;
         const uint32_t en_up = __shfl_up_sync(0xffffffffu, en, 1);
@@ -291,15 +299,15 @@ __device__ bool fu_lookback(const uint64_t* __restrict__ R, const FuRing ring_a,
             // predecessor is FINAL.  Mine: do that; somebody else's: wait until that unit has finalised.
             if (d == 0 && base == (int)u - 1) {
                 if (mf & 1) { true_entry = __shfl_sync(0xffffffffu, ex, 0); return false; }
-                fu_wait_rec(R, ring_a, base, FU_FINAL);
+                fu_wait_rec<CL>(R, ring_a, base, FU_FINAL);
             } else {
-                fu_wait_rec(R, ring_a, base - (int)d + 1, FU_FINAL);
+                fu_wait_rec<CL>(R, ring_a, base - (int)d + 1, FU_FINAL);
             }
         } else if ((mf >> d) & 1) {
             prefix = __shfl_sync(0xffffffffu, (uint32_t)(rec >> 32), d) + acc + warp_sum(lane < d ? cnt : 0u);
             return true;
         } else {
-            fu_wait_rec(R, ring_a, base - (int)d, FU_SPEC);        // not published yet
+            fu_wait_rec<CL>(R, ring_a, base - (int)d, FU_SPEC);        // not published yet
         }
         acc = 0; expect = my_entry0; base = (int)u - 1;           // start over
     }
@@ -681,7 +689,7 @@ __device__ uint32_t fu_pick_chunk(const FuArgs& a, SH& S, uint32_t& ahead, uint3
         bool decided = false;
         if (CL == 2 && cl_rank == 1) {
             uint32_t pk = ahead, spins = 0;
-            while ((pk = *reinterpret_cast<volatile uint32_t*>(&S.peer_k)) == ahead && ++spins < (1u << 16)) __nanosleep(64);
+            while ((pk = *fu_peer_k(S)) == ahead && ++spins < (1u << 16)) __nanosleep(64);
             if (pk != ahead) {
                 ahead = pk; decided = true;
                 if (pk != FU_ANN_NONE && pk != 0) { k = pk - 1; fu_table_issue(a, S, k); }
@@ -699,12 +707,15 @@ __device__ uint32_t fu_pick_chunk(const FuArgs& a, SH& S, uint32_t& ahead, uint3
         }
         S.s_k = k; S.s_pick = (CL == 2 && cl_rank == 1 && decided) ? 0u : FU_NONE;    // s_pick == 0: the follower does not search
     }
-    for (uint32_t i = threadIdx.x; i < sizeof(S.ring) / sizeof(S.ring[0]); i += blockDim.x) S.ring[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = threadIdx.x; i < (CL == 2 ? FU_RING_CL : FU_RING); i += blockDim.x) S.ring[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     uint32_t k = S.s_k;
-    follow = CL == 2 && cl_rank == 1 && S.s_pick == 0u;
-    if (threadIdx.x == 0 && follow) S.s_pick = FU_NONE;
-    __syncthreads();
+    if (CL == 2) {
+        follow = cl_rank == 1 && S.s_pick == 0u;
+        __syncthreads();
+        if (threadIdx.x == 0 && follow) S.s_pick = FU_NONE;
+        __syncthreads();
+    }
     if (k == FU_NONE && K <= 2048 && !follow) {           // (thousands of chunks balance by themselves)
         // helping: the first chunk (from a start that spreads the CTAs) whose unit counter has not run out
         const uint32_t start = (uint32_t)(((uint64_t)blockIdx.x * K) / gridDim.x);
@@ -726,7 +737,7 @@ __device__ uint32_t fu_pick_chunk(const FuArgs& a, SH& S, uint32_t& ahead, uint3
         }
     }
     if (CL == 2 && threadIdx.x == 0)
-        fu_remote_st32(fu_mapa(smem_u32(&S.peer_k), cl_rank ^ 1u), k == FU_NONE ? FU_ANN_NONE : k + 1);
+        fu_remote_st32(fu_mapa(smem_u32((const void*)fu_peer_k(S)), cl_rank ^ 1u), k == FU_NONE ? FU_ANN_NONE : k + 1);
     return k;
 }
 
@@ -746,13 +757,13 @@ dec_fused_kernel(const FuArgs a) {
     const uint32_t bar_a = smem_u32(&S.bar[wid]);
     const uint32_t wlut_a = pin_reg(smem_u32(S.wlut)), aux_a = pin_reg(smem_u32(S.aux));
     FuRing ring_a;
-    ring_a.a = smem_u32(S.ring); ring_a.mask = (CL == 2 ? FU_RING_CL : FU_RING) - 1; ring_a.ktag = 0; ring_a.peer = 0;
+    ring_a.a = smem_u32(S.ring); ring_a.ktag = 0; ring_a.peer = 0;
     const uint32_t cl_rank = CL == 2 ? fu_cluster_rank() : 0u;
     const uint32_t peer_ring = CL == 2 ? fu_mapa(ring_a.a, cl_rank ^ 1u) : 0u;
     const DecAux& A = *reinterpret_cast<const DecAux*>(S.aux);
     if (lane == 0) {
         mbar_init(&S.bar[wid], 1);
-        if (wid == 0) { mbar_init(&S.tbar, 1); S.peer_k = 0; }
+        if (wid == 0) { mbar_init(&S.tbar, 1); if (CL == 2) *fu_peer_k(S) = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (CL == 2) fu_cluster_sync();                       // the peer CTA has started: its shared memory may be written
@@ -786,8 +797,8 @@ dec_fused_kernel(const FuArgs a) {
         uint32_t u = 0;
         if (lane == 0) u = atomicAdd(a.P.unit_ctr + k, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
-        if (CL == 2) ring_a.peer = *reinterpret_cast<volatile uint32_t*>(&S.peer_k) == k + 1 ? peer_ring : 0u;
-        if (u < nunit && lane == 0) { fu_mark_pending(ring_a, u); fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw)); }
+        if (CL == 2) ring_a.peer = *fu_peer_k(S) == k + 1 ? peer_ring : 0u;
+        if (u < nunit && lane == 0) { fu_mark_pending<CL>(ring_a, u); fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw)); }
         FU_T(8);
         fu_mbar_wait(smem_u32(&S.tbar), tphase); tphase ^= 1;
         FU_T(9);
@@ -879,21 +890,21 @@ dec_fused_kernel(const FuArgs a) {
                 const uint32_t uentry = __shfl_sync(0xffffffffu, entry, 0);
                 const uint32_t ucount = warp_sum(active ? count : 0);
                 if (u == 0) {
-                    if (lane == 0) fu_put(R, ring_a, 0, fu_pack(FU_FINAL, 0, uexit, ucount, ucount));
+                    if (lane == 0) fu_put<CL>(R, ring_a, 0, fu_pack(FU_FINAL, 0, uexit, ucount, ucount));
                     prefix = 0;
                     break;
                 }
                 if (!published) {
-                    if (lane == 0) fu_put(R, ring_a, u, fu_pack(FU_SPEC, uentry, uexit, ucount, 0));
+                    if (lane == 0) fu_put<CL>(R, ring_a, u, fu_pack(FU_SPEC, uentry, uexit, ucount, 0));
                     published = true;
                 }
                 uint32_t true_entry = 0;
                 FU_T(7);
-                const bool lb_ok = fu_lookback(R, ring_a, u, uentry, lane, prefix, true_entry);
+                const bool lb_ok = fu_lookback<CL>(R, ring_a, u, uentry, lane, prefix, true_entry);
                 FU_T(4);
                 FU_TRACE(5, u);
                 if (lb_ok) {
-                    if (lane == 0) fu_put(R, ring_a, u, fu_pack(FU_FINAL, uentry, uexit, ucount, prefix + ucount));
+                    if (lane == 0) fu_put<CL>(R, ring_a, u, fu_pack(FU_FINAL, uentry, uexit, ucount, prefix + ucount));
                     break;
                 }
                 need = lane == 0;                         // the guess of the first subsequence was wrong: re-walk from the truth
@@ -1011,8 +1022,8 @@ dec_fused_kernel(const FuArgs a) {
             // tickets out of a per-CTA pool of blocks drawn ahead 5 % slower (30 % where CTAs share a chunk).
             if (!tk_drawn && lane == 0) tk = atomicAdd(a.P.unit_ctr + k, 1u);
             u = __shfl_sync(0xffffffffu, tk, 0);
-            if (CL == 2) ring_a.peer = *reinterpret_cast<volatile uint32_t*>(&S.peer_k) == k + 1 ? peer_ring : 0u;
-            if (u < nunit && lane == 0) { fu_mark_pending(ring_a, u); fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw)); }
+            if (CL == 2) ring_a.peer = *fu_peer_k(S) == k + 1 ? peer_ring : 0u;
+            if (u < nunit && lane == 0) { fu_mark_pending<CL>(ring_a, u); fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw)); }
             // the chunk's last unit: when the stream holds fewer symbols than orig_size the decoder goes on reading
             // zero bits (TableBasedHuffmanDecoder.java:204-208), i.e. the all-zero codeword's symbol repeats
             if (u_cur == nunit - 1) {
