@@ -396,6 +396,11 @@ def test_encode_global_in_library(codec):
     p2, o2 = codec.encode_with_lengths(data, chunk, l256)
     assert np.array_equal(off, o2) and np.array_equal(payload, p2)
     K = len(off) - 1
+    # (8 chunks: both calls take the chained sizes kernel + dependent encoder) every chunk against the oracle's bit packer
+    cd, _ = orc.canonical_codes(l256.astype(np.int32))
+    for k in range(K):
+        ref = orc.encode(data[k * chunk:(k + 1) * chunk], l256.astype(np.int32), cd)
+        assert np.array_equal(payload[int(off[k]):int(off[k + 1])], ref), k
     orig = np.array([min(chunk, data.size - k * chunk) for k in range(K)], dtype=np.uint32)
     back = codec.decode(payload, off[:-1], np.diff(off).astype(np.uint32), orig, np.tile(l256, (K, 1)))
     assert np.array_equal(back, data)
