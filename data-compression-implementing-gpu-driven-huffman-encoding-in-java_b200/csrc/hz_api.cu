@@ -369,10 +369,13 @@ static int encode_device(hz_ctx* ctx, const uint8_t* d_in, uint64_t n, uint32_t 
     // soon as its histogram is complete, and an encoder launched with programmatic stream serialization that waits per
     // chunk (hz_codebook.cu: hist_chain_kernel) - the codebook stage's 0.16 ms of latency leaves the critical path.
     // (Streams of smaller chunks and caller-supplied lengths keep the separate launches.)
-    // Chunks of >= 8 MiB only: a tail holds its CTA for ~0.16 ms, so 0.16 ms x 5.3 TB/s / chunk bytes tails are resident
-    // beside the histogram at any time (16 MiB chunks: 50 of the 888 CTA slots; 4 MiB: 200, and the stage gets slower -
-    // measured 3.30 -> 3.94 ms per 4 GiB, against 3.16 -> 3.05 ms at 16 MiB).
-    if (ctx->knobs.enc_chain && !global_len256 && !d_fixed && K >= 8 && chunk_bytes >= (8u << 20)) {
+    // Chunks of >= 2 MiB: a tail holds its CTA for ~0.16 ms, so 0.16 ms x 5.3 TB/s / chunk bytes tails are resident beside
+    // the histogram at any time (16 MiB chunks: 50 of the 888 CTA slots, 4 MiB: 200).  Measured per 4 GiB: 16 MiB chunks
+    // 3.17 -> 3.06 ms, 8 MiB 3.17 -> 3.10, 4 MiB 3.31 -> 3.20; per 1 GiB: 8 MiB 0.938 -> 0.862, 4 MiB 0.940 -> 0.884,
+    // 2 MiB 0.962 -> 0.939 (per 4 GiB: 3 MiB 3.53 -> 3.37, 2 MiB 3.69 -> 3.53).  (With offsets chained prefix[k-1] -> prefix[k] instead of the decoupled look-back, 4 MiB
+    // chunks were SLOWER, 3.30 -> 3.94 ms: ~2 us per hop in series against tails that finish 0.75 us apart.)
+    const uint32_t chain_min = ctx->knobs.enc_chain > 1 ? (uint32_t)ctx->knobs.enc_chain << 10 : (2u << 20);   // developer knob: HZ_ENC_CHAIN=<min chunk KiB>
+    if (ctx->knobs.enc_chain && !global_len256 && !d_fixed && K >= 8 && chunk_bytes >= chain_min && !(K >= 1024 && spc <= 32)) {
         const size_t kk = ((size_t)K + 1) & ~(size_t)1;
         const size_t bytes = 16 + kk * 4 + 2 * (size_t)K * 8;
         HZ_TRY(hz_reserve(ctx, &ctx->chain, bytes));

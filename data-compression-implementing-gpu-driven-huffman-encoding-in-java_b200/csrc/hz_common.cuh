@@ -134,7 +134,7 @@ void hz_prof_resolve(hz_ctx* ctx);
 struct HzChain {
     uint32_t* ticket;       // [1]  next histogram range
     uint32_t* done;         // [K]  histogram ranges of chunk k that are complete
-    uint64_t* prefix;       // [K]  bit 63: valid; low bits: payload bytes of chunks 0..k
+    uint64_t* prefix;       // [K]  top two bits: 0 empty, 1 aggregate (this chunk's size), 2 prefix (payload bytes of chunks 0..k)
     uint64_t* ready;        // [K]  != 0: chunk k's lengths, codes, offsets are in memory
 };
 

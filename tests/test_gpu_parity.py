@@ -575,7 +575,7 @@ def test_large_device_resident_roundtrip(codec):
 
 
 def test_chained_encode_equals_separate_launches(codec, knob, hz):
-    """Streams of >= 8 chunks of >= 8 MiB take the chained histogram -> codebook -> offsets kernel and an encoder that
+    """Streams of >= 8 chunks of >= 2 MiB take the chained histogram -> codebook -> offsets kernel and an encoder that
     waits per chunk (programmatic stream serialization).  Its payload, offsets, lengths and chunk histograms must equal
     those of the separate launches (HZ_ENC_CHAIN=0) bit for bit - with a ragged last chunk, mixed entropies, an
     incompressible (identity) chunk and a one-symbol chunk, repeatedly (flags are reset per call) - and chunk 0 / the
