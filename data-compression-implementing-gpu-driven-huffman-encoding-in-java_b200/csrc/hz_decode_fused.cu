@@ -228,41 +228,46 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
 // the chunk they belong to.  In a cluster pair (streams with fewer chunks than SMs, where CTAs share chunks from the
 // start) a CTA also PUSHES its entries into the peer's ring through distributed shared memory while the peer works on
 // the same chunk: the peer's look-backs then stay in its own shared memory instead of polling L2.
-struct FuRing {
+template <int CL> struct FuRingT;
+template <> struct FuRingT<1> {      // a lone CTA: one register, the ring's shared address (chunk tag and peer are constants)
+    uint32_t a;
+};
+template <> struct FuRingT<2> {
     uint32_t a;          // shared address of this CTA's ring
     uint32_t ktag;       // chunk + 1
     uint32_t peer;       // shared::cluster address of the peer's ring while it works on this chunk, else 0
 };
+template <int CL> __device__ __forceinline__ uint32_t fu_ktag(const FuRingT<CL>& g) { if constexpr (CL == 2) return g.ktag; else return 0u; }
 __device__ __forceinline__ void fu_remote_st128(uint32_t ra, uint4 v) {
     asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // (CL is the kernel's cluster size: for a lone CTA the ring size, the chunk tag and the peer are compile-time constants)
 template <int CL>
-__device__ __forceinline__ void fu_ring_store(const FuRing& g, uint32_t u, uint4 e) {
+__device__ __forceinline__ void fu_ring_store(const FuRingT<CL>& g, uint32_t u, uint4 e) {
     const uint32_t o = (u & (CL == 2 ? FU_RING_CL - 1 : FU_RING - 1)) * 16;
     sts128(g.a + o, e);
-    if (CL == 2 && g.peer) fu_remote_st128(g.peer + o, e);
+    if constexpr (CL == 2) { if (g.peer) fu_remote_st128(g.peer + o, e); }
 }
 template <int CL>
-__device__ __forceinline__ void fu_put(uint64_t* R, const FuRing& g, uint32_t u, uint64_t rec) {
-    fu_ring_store<CL>(g, u, make_uint4((uint32_t)rec, (uint32_t)(rec >> 32), u + 1, CL == 2 ? g.ktag : 0u));
+__device__ __forceinline__ void fu_put(uint64_t* R, const FuRingT<CL>& g, uint32_t u, uint64_t rec) {
+    fu_ring_store<CL>(g, u, make_uint4((uint32_t)rec, (uint32_t)(rec >> 32), u + 1, fu_ktag<CL>(g)));
     st_rec(R + u, rec);
 }
 // A warp marks the unit it has just been handed as PENDING in the ring (tag set, record EMPTY): a look-back that meets
 // the mark knows the record will appear HERE and polls shared memory - without it every look at a unit this CTA is
 // still decoding went to global memory (a round trip to L2 to read EMPTY, and again for every poll).
 template <int CL>
-__device__ __forceinline__ void fu_mark_pending(const FuRing& g, uint32_t u) {
-    fu_ring_store<CL>(g, u, make_uint4(0u, 0u, u + 1, CL == 2 ? g.ktag : 0u));
+__device__ __forceinline__ void fu_mark_pending(const FuRingT<CL>& g, uint32_t u) {
+    fu_ring_store<CL>(g, u, make_uint4(0u, 0u, u + 1, fu_ktag<CL>(g)));
 }
 template <int CL>
-__device__ __forceinline__ uint64_t fu_get(const uint64_t* R, const FuRing& g, int q) {
+__device__ __forceinline__ uint64_t fu_get(const uint64_t* R, const FuRingT<CL>& g, int q) {
     const uint4 e = lds128(g.a + ((uint32_t)q & (CL == 2 ? FU_RING_CL - 1 : FU_RING - 1)) * 16);
-    if (e.z == (uint32_t)q + 1 && (CL != 2 || e.w == g.ktag)) return (uint64_t)e.x | ((uint64_t)e.y << 32);
+    if (e.z == (uint32_t)q + 1 && (CL != 2 || e.w == fu_ktag<CL>(g))) return (uint64_t)e.x | ((uint64_t)e.y << 32);
     return ld_rec(R + q);
 }
 template <int CL>
-__device__ __forceinline__ void fu_wait_rec(const uint64_t* R, const FuRing& g, int q, uint32_t min_state) {
+__device__ __forceinline__ void fu_wait_rec(const uint64_t* R, const FuRingT<CL>& g, int q, uint32_t min_state) {
     uint32_t ns = 32;
     while (((uint32_t)fu_get<CL>(R, g, q) & 3u) < min_state) { __nanosleep(ns); if (ns < 256) ns += ns; }
 }
@@ -272,7 +277,7 @@ __device__ __forceinline__ void fu_wait_rec(const uint64_t* R, const FuRing& g, 
 // `true_entry` when the unit has to re-walk (its guess differs from the FINAL exit of unit u - 1).
 // Waiting (for a record to be published, or for the owner of a broken link to finalise) polls ONE record.
 template <int CL>
-__device__ bool fu_lookback(const uint64_t* __restrict__ R, const FuRing ring_a, uint32_t u, uint32_t my_entry0, uint32_t lane,
+__device__ bool fu_lookback(const uint64_t* __restrict__ R, const FuRingT<CL> ring_a, uint32_t u, uint32_t my_entry0, uint32_t lane,
                             uint32_t& prefix, uint32_t& true_entry) {
     uint32_t acc = 0, expect = my_entry0;
     int base = (int)u - 1;
@@ -756,8 +761,9 @@ dec_fused_kernel(const FuArgs a) {
     const uint32_t rows_a = stage_a + FU_STAGE_BYTES;
     const uint32_t bar_a = smem_u32(&S.bar[wid]);
     const uint32_t wlut_a = pin_reg(smem_u32(S.wlut)), aux_a = pin_reg(smem_u32(S.aux));
-    FuRing ring_a;
-    ring_a.a = smem_u32(S.ring); ring_a.ktag = 0; ring_a.peer = 0;
+    FuRingT<CL> ring_a;
+    ring_a.a = smem_u32(S.ring);
+    if constexpr (CL == 2) { ring_a.ktag = 0; ring_a.peer = 0; }
     const uint32_t cl_rank = CL == 2 ? fu_cluster_rank() : 0u;
     const uint32_t peer_ring = CL == 2 ? fu_mapa(ring_a.a, cl_rank ^ 1u) : 0u;
     const DecAux& A = *reinterpret_cast<const DecAux*>(S.aux);
@@ -780,7 +786,7 @@ dec_fused_kernel(const FuArgs a) {
     for (;;) {
         const uint32_t k = fu_pick_chunk<SH, CL>(a, S, ahead, cl_rank);
         if (k == FU_NONE) break;
-        ring_a.ktag = CL == 2 ? k + 1 : 0u;               // (a lone CTA's ring is reset per chunk and only it writes to it)
+        if constexpr (CL == 2) ring_a.ktag = k + 1;       // (a lone CTA's ring is reset per chunk and only it writes to it)
         FU_T(11);
         FU_TRACE(0, k);
         // the chunk's geometry and this warp's first unit are fetched while the table is on its way
@@ -797,7 +803,7 @@ dec_fused_kernel(const FuArgs a) {
         uint32_t u = 0;
         if (lane == 0) u = atomicAdd(a.P.unit_ctr + k, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
-        if (CL == 2) ring_a.peer = *fu_peer_k(S) == k + 1 ? peer_ring : 0u;
+        if constexpr (CL == 2) ring_a.peer = *fu_peer_k(S) == k + 1 ? peer_ring : 0u;
         if (u < nunit && lane == 0) { fu_mark_pending<CL>(ring_a, u); fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw)); }
         FU_T(8);
         fu_mbar_wait(smem_u32(&S.tbar), tphase); tphase ^= 1;
@@ -1022,7 +1028,7 @@ dec_fused_kernel(const FuArgs a) {
             // tickets out of a per-CTA pool of blocks drawn ahead 5 % slower (30 % where CTAs share a chunk).
             if (!tk_drawn && lane == 0) tk = atomicAdd(a.P.unit_ctr + k, 1u);
             u = __shfl_sync(0xffffffffu, tk, 0);
-            if (CL == 2) ring_a.peer = *fu_peer_k(S) == k + 1 ? peer_ring : 0u;
+            if constexpr (CL == 2) ring_a.peer = *fu_peer_k(S) == k + 1 ? peer_ring : 0u;
             if (u < nunit && lane == 0) { fu_mark_pending<CL>(ring_a, u); fu_stage_issue(stage_a, bar_a, fu_geom(a.comp, a.comp_bytes, coff, csize, u, Sw)); }
             // the chunk's last unit: when the stream holds fewer symbols than orig_size the decoder goes on reading
             // zero bits (TableBasedHuffmanDecoder.java:204-208), i.e. the all-zero codeword's symbol repeats
