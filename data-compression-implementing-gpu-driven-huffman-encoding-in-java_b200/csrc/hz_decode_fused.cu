@@ -687,6 +687,42 @@ __device__ __forceinline__ void fu_cluster_sync() {
 #define FU_ANN_NONE 0xFFFFFFFFu
 template <class SH, int CL>
 __device__ uint32_t fu_pick_chunk(const FuArgs& a, SH& S, uint32_t& ahead, uint32_t cl_rank) {
+    if constexpr (CL != 2) {                              // a lone CTA: ticket drawn ahead, then helping
+        const uint32_t K = a.K;
+        if (threadIdx.x == 0) {
+            uint32_t k = FU_NONE, t = ahead;
+            for (;;) {
+                if (t >= K) break;
+                if (a.P.nunit[t]) { k = t; break; }
+                t = atomicAdd(&a.P.ctl[0], 1u);
+            }
+            if (k != FU_NONE) { fu_table_issue(a, S, k); ahead = atomicAdd(&a.P.ctl[0], 1u); }
+            else ahead = K;
+            S.s_k = k; S.s_pick = FU_NONE;
+        }
+        if (threadIdx.x < FU_RING) S.ring[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        if (S.s_k != FU_NONE) return S.s_k;
+        if (K > 2048) return FU_NONE;                         // thousands of chunks balance by themselves
+        // helping: the first chunk (from a start that spreads the CTAs) whose unit counter has not run out
+        const uint32_t start = (uint32_t)(((uint64_t)blockIdx.x * K) / gridDim.x);
+        for (uint32_t i0 = 0; i0 < K; i0 += blockDim.x) {
+            const uint32_t i = i0 + threadIdx.x;
+            if (i < K) {
+                const uint32_t k = (start + i) % K;
+                const uint32_t nu = a.P.nunit[k];
+                if (nu && *reinterpret_cast<volatile uint32_t*>(a.P.unit_ctr + k) < nu) atomicMin(&S.s_pick, i);
+            }
+            __syncthreads();
+            if (S.s_pick != FU_NONE) break;
+        }
+        __syncthreads();
+        const uint32_t p = S.s_pick;
+        if (p == FU_NONE) return FU_NONE;
+        const uint32_t k = (start + p) % K;
+        if (threadIdx.x == 0) fu_table_issue(a, S, k);
+        return k;
+    } else {
     const uint32_t K = a.K;
     bool follow = false;
     if (threadIdx.x == 0) {
@@ -744,6 +780,7 @@ __device__ uint32_t fu_pick_chunk(const FuArgs& a, SH& S, uint32_t& ahead, uint3
     if (CL == 2 && threadIdx.x == 0)
         fu_remote_st32(fu_mapa(smem_u32((const void*)fu_peer_k(S)), cl_rank ^ 1u), k == FU_NONE ? FU_ANN_NONE : k + 1);
     return k;
+    }
 }
 
 // W = warps per CTA, MINB = CTAs per SM: <24, 1> for chunks of many units; <8, 2> and <5, 3> for streams of small
