@@ -41,6 +41,10 @@
 #define FU_WARP_BYTES (FU_STAGE_BYTES + FU_ROWS_BYTES)
 #define FU_TABLE_BYTES (LUTN * 8 + 1024)           // wlut + DecAux
 #define FU_NONE 0xFFFFFFFFu
+#ifndef FU_NS0
+#define FU_NS0 32                                  // look-back polls: first sleep and its cap, ns
+#define FU_NSMAX 256
+#endif
 #define FU_RING 64                                 // > look-back window (32) + units in flight in one CTA (24)
 #define FU_RING_CL 128                             // cluster pair: both CTAs' units of the shared chunk
 
@@ -268,8 +272,8 @@ __device__ __forceinline__ uint64_t fu_get(const uint64_t* R, const FuRingT<CL>&
 }
 template <int CL>
 __device__ __forceinline__ void fu_wait_rec(const uint64_t* R, const FuRingT<CL>& g, int q, uint32_t min_state) {
-    uint32_t ns = 32;
-    while (((uint32_t)fu_get<CL>(R, g, q) & 3u) < min_state) { __nanosleep(ns); if (ns < 256) ns += ns; }
+    uint32_t ns = FU_NS0;
+    while (((uint32_t)fu_get<CL>(R, g, q) & 3u) < min_state) { __nanosleep(ns); if (ns < FU_NSMAX) ns += ns; }
 }
 
 // Decoupled look-back of unit u (u >= 1) over the chunk's records R[0..u).  Returns true with the number of
